@@ -1,0 +1,112 @@
+/* device_types.h -- plain structs shared by the host API and the CUDA kernels. */
+#ifndef AB_DEVICE_TYPES_H
+#define AB_DEVICE_TYPES_H
+
+#include <stdint.h>
+
+#define AB_NPLANETS 11
+#define AB_MAX_AST 16            /* asteroids held in the per-time body table */
+#define AB_MAX_BODIES (AB_NPLANETS + AB_MAX_AST)
+#define AB_MAXSEG 8              /* SPK segments per target */
+#define AB_MAX_PTGT 16           /* SPK targets in a planets kernel */
+#define AB_NVMAX 6               /* variational particles per system */
+#define AB_KMAX (1 + AB_NVMAX)
+#define AB_BLOCK 128
+
+#define AB_SRC_SPK 0
+#define AB_SRC_ASCII 2
+
+struct AbSpkTarget {
+    double beg, end, res, mass;
+    int code, cen, nseg, pad;
+    int one[AB_MAXSEG];
+    int two[AB_MAXSEG];
+};
+
+/* Everything a kernel needs to evaluate the ephemeris; passed by value (__grid_constant__). */
+struct AbEphem {
+    double jd_ref;
+    int planets_source;
+    int n_ast;
+    /* constants, reference src/assist.h:140-154 */
+    double AU, EMRAT, J2E, J3E, J4E, J2SUN, Re_eq, Rs_eq, c_squared, over_c_squared;
+    /* DE binary planets */
+    const double* ascii_img;
+    double a_beg, a_end, a_inc, a_cau, a_cem;
+    long long a_rec_words;
+    long long a_nrec;
+    int a_off[15], a_ncf[15], a_niv[15];
+    double a_mass[AB_NPLANETS];
+    /* SPK planets */
+    const double* spkp_img;
+    int p_index[AB_NPLANETS];
+    int emb_index;
+    int n_ptgt;
+    AbSpkTarget p_tgt[AB_MAX_PTGT];
+    /* SPK asteroids: descriptors live in global memory */
+    const double* spka_img;
+    const AbSpkTarget* a_tgt;
+};
+
+/* Force-model switches, snapshot of struct assist_extras at launch (reference src/assist.h:177-195). */
+struct AbForceOpts {
+    int forces;
+    int gr_eih_sources;
+    int geocentric;
+    int has_params;
+    double alpha, nk, nm, nn, r0;
+    /* pole orientation terms, computed on the host with libm exactly as the reference
+     * does (src/forces.c:484-490, 670-676) so that device and reference share the bits */
+    double e_cosa, e_sina, e_cosd, e_sind;
+    double s_cosa, s_sina, s_cosd, s_sind;
+};
+
+/* Body states at one time (AU, AU/day, AU/day^2), barycentric. */
+struct AbBodies {
+    double gm[AB_MAX_BODIES];
+    double pos[AB_MAX_BODIES][3];
+    double vel[AB_NPLANETS][3];     /* valid for j < gr_eih_sources (and Earth when geocentric) */
+    double earth_acc[3];            /* valid when geocentric */
+    /* particle-independent parts of the EIH term (reference src/forces.c:1418-1434, 1755-1770) */
+    double eih_term1[AB_NPLANETS];
+    double eih_ar[AB_NPLANETS][3];  /* a_j as the real-particle pass rounds it */
+    double eih_av[AB_NPLANETS][3];  /* a_j as the variational pass rounds it */
+    int status;
+};
+
+/* Device-side state of a batch.  Arrays are structure-of-arrays over systems:
+ * element (component k, system i) lives at [k * n + i]; the seven-deep IAS15
+ * tables at [(j * C + k) * n + i], C = 3 * K. */
+struct AbBatch {
+    int n;            /* systems */
+    int K;            /* bodies per system (1 + max variational) */
+    int C;            /* 3 * K */
+    int mode;
+    double *pos, *vel, *acc;                 /* [C][n]  current particles */
+    double *x0, *v0, *a0, *csx, *csv;        /* [C][n] */
+    double *b, *g, *e, *csb, *br, *er;       /* [7][C][n] */
+    double *ls_pos, *ls_vel, *ls_acc;        /* [C][n] state at the start of the last completed step */
+    double *prm;                             /* [C][n] A1 A2 A3 / dA1 dA2 dA3 */
+    int *nv;                                 /* [n] variational particles in use */
+    /* per-particle mode */
+    double *t, *dt, *dt_last;                /* [n] */
+    int *status;                             /* [n] REB_STATUS */
+    /* counters: [n] in per-particle mode, [1] in shared-step mode */
+    unsigned long long *steps, *rejected, *iters, *evals;
+    /* shared-step control block (device) */
+    struct AbShared* sh;
+    double epsilon, min_dt;
+    int has_params;
+};
+
+struct AbShared {
+    double t, dt, dt_last, last_full_dt;
+    int status;
+    int pad;
+    unsigned long long steps, rejected, iters, evals;
+    unsigned long long barrier;               /* monotone grid-barrier counter */
+    unsigned long long red[8][2];             /* ring of max-reduction slots (bit patterns of non-negative doubles) */
+    int err_status;                           /* first ASSIST_STATUS error seen */
+};
+
+#endif

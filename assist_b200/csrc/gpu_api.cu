@@ -1,0 +1,692 @@
+/*
+ * gpu_api.cu -- the thin C-ABI of include/assist_gpu.h: device memory, marshalling
+ * and kernel launches.  No physics here; the kernels are in kernels.cu.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "assist_gpu.h"
+#include "assist_ephem_files.h"
+#include "device_types.h"
+#include "launchers.h"
+#include "host_internal.h"
+
+/* ------------------------------------------------------------------------ */
+/* errors / device                                                          */
+/* ------------------------------------------------------------------------ */
+
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return set_err(ASSIST_GPU_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e));  \
+    } while (0)
+
+extern "C" const char* assist_gpu_last_error(void) { return g_err; }
+
+extern "C" int assist_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static bool g_const_uploaded[ASSIST_B200_MAX_DEVICES] = {false};
+
+/* Returns the current device after making sure a device exists and constants are loaded. */
+static int ensure_device(int* dev_out) {
+    if (assist_gpu_device_count() < 1)
+        return set_err(ASSIST_GPU_ERR_NO_DEVICE,
+                       "no CUDA device available: assist-b200 has no CPU compute path");
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= ASSIST_B200_MAX_DEVICES) return set_err(ASSIST_GPU_ERR_ARG, "device index %d out of range", dev);
+    if (!g_const_uploaded[dev]) {
+        CU(ab_upload_constants_strict());
+        CU(ab_upload_constants_fast());
+        g_const_uploaded[dev] = true;
+    }
+    *dev_out = dev;
+    return 0;
+}
+
+extern "C" int assist_gpu_set_device(int device) {
+    if (assist_gpu_device_count() < 1)
+        return set_err(ASSIST_GPU_ERR_NO_DEVICE, "no CUDA device available: assist-b200 has no CPU compute path");
+    CU(cudaSetDevice(device));
+    return 0;
+}
+
+extern "C" void assist_gpu_default_options(struct assist_gpu_options* opt) {
+    /* defaults of assist_init, reference src/assist.c:415-438, and REBOUND's IAS15 defaults */
+    opt->forces = ASSIST_FORCE_SUN | ASSIST_FORCE_PLANETS | ASSIST_FORCE_ASTEROIDS | ASSIST_FORCE_NON_GRAVITATIONAL |
+                  ASSIST_FORCE_EARTH_HARMONICS | ASSIST_FORCE_SUN_HARMONICS | ASSIST_FORCE_GR_EIH;
+    opt->gr_eih_sources = 1;
+    opt->geocentric = 0;
+    opt->math = ASSIST_GPU_MATH_STRICT;
+    opt->alpha = 1.0; opt->nk = 0.0; opt->nm = 2.0; opt->nn = 5.093; opt->r0 = 1.0;
+    opt->epsilon = 1e-9;
+    opt->min_dt = 0.0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* ephemeris upload                                                         */
+/* ------------------------------------------------------------------------ */
+
+static int upload_image(void** slot, const void* host, size_t len) {
+    if (*slot) return 0;
+    void* d = nullptr;
+    CU(cudaMalloc(&d, len));
+    CU(cudaMemcpy(d, host, len, cudaMemcpyHostToDevice));
+    *slot = d;
+    return 0;
+}
+
+static int fill_target(AbSpkTarget* d, const struct spk_target* t) {
+    memset(d, 0, sizeof(*d));
+    d->beg = t->beg; d->end = t->end; d->res = t->res; d->mass = t->mass;
+    d->code = t->code; d->cen = t->cen; d->nseg = t->ind + 1;
+    if (d->nseg > AB_MAXSEG)
+        return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "SPK target %d has %d segments (max %d)", t->code, d->nseg, AB_MAXSEG);
+    for (int s = 0; s < d->nseg; s++) { d->one[s] = t->one[s]; d->two[s] = t->two[s]; }
+    return 0;
+}
+
+/* Build the kernel-parameter view of an ephemeris on the current device. */
+static int build_ephem(const struct assist_ephem* e, AbEphem* E) {
+    int dev;
+    int rc = ensure_device(&dev);
+    if (rc) return rc;
+    if (e == NULL) return set_err(ASSIST_GPU_ERR_ARG, "ephem is NULL");
+    memset(E, 0, sizeof(*E));
+    E->jd_ref = e->jd_ref;
+    E->planets_source = e->planets_source;
+    E->AU = e->AU; E->EMRAT = e->EMRAT; E->J2E = e->J2E; E->J3E = e->J3E; E->J4E = e->J4E; E->J2SUN = e->J2SUN;
+    E->Re_eq = e->Re_eq; E->Rs_eq = e->Rs_eq; E->c_squared = e->c_squared; E->over_c_squared = e->over_c_squared;
+    for (int k = 0; k < AB_NPLANETS; k++) E->p_index[k] = -1;
+    E->emb_index = -1;
+    if (e->ascii_planets) {
+        struct ascii_s* a = e->ascii_planets;
+        if ((rc = upload_image(&a->b200_dev_image[dev], a->map, a->len))) return rc;
+        E->ascii_img = (const double*)a->b200_dev_image[dev];
+        E->a_beg = a->beg; E->a_end = a->end; E->a_inc = a->inc; E->a_cau = a->cau; E->a_cem = a->cem;
+        E->a_rec_words = (long long)(a->rec / sizeof(double));
+        E->a_nrec = (long long)(a->len / a->rec) - 2;
+        for (int p = 0; p < 15; p++) { E->a_off[p] = a->off[p]; E->a_ncf[p] = a->ncf[p]; E->a_niv[p] = a->niv[p]; }
+        for (int k = 0; k < AB_NPLANETS; k++) E->a_mass[k] = a->mass[k];
+    } else if (e->spk_planets) {
+        struct spk_s* pl = e->spk_planets;
+        if ((rc = upload_image(&pl->b200_dev_image[dev], pl->map, pl->len))) return rc;
+        E->spkp_img = (const double*)pl->b200_dev_image[dev];
+        if (pl->num > AB_MAX_PTGT)
+            return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "planet kernel has %d targets (max %d)", pl->num, AB_MAX_PTGT);
+        E->n_ptgt = pl->num;
+        for (int m = 0; m < pl->num; m++)
+            if ((rc = fill_target(&E->p_tgt[m], &pl->targets[m]))) return rc;
+        static const int naif_by_assist[AB_NPLANETS] = {10, 1, 2, 399, 301, 4, 5, 6, 7, 8, 9};
+        for (int k = 0; k < AB_NPLANETS; k++) {
+            /* precomputed index when it is consistent, else a search by NAIF code (reference src/spk.c:646-659) */
+            int idx = e->spk_target_index[k];
+            if (!(idx >= 0 && idx < pl->num && pl->targets[idx].code == naif_by_assist[k])) {
+                idx = -1;
+                for (int m = 0; m < pl->num; m++) if (pl->targets[m].code == naif_by_assist[k]) { idx = m; break; }
+            }
+            E->p_index[k] = idx;
+        }
+        int emb = e->spk_emb_index;
+        if (!(emb >= 0 && emb < pl->num && pl->targets[emb].code == 3)) {
+            emb = -1;
+            for (int m = 0; m < pl->num; m++) if (pl->targets[m].code == 3) { emb = m; break; }
+        }
+        E->emb_index = emb;
+    } else {
+        return set_err(ASSIST_ERROR_EPHEM_FILE, "ephemeris has no planets provider");
+    }
+    if (e->spk_asteroids) {
+        struct spk_s* sb = e->spk_asteroids;
+        if (sb->num > AB_MAX_AST)
+            return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "small-body kernel has %d targets (max %d in this build)", sb->num, AB_MAX_AST);
+        if ((rc = upload_image(&sb->b200_dev_image[dev], sb->map, sb->len))) return rc;
+        E->spka_img = (const double*)sb->b200_dev_image[dev];
+        E->n_ast = sb->num;
+        AbSpkTarget tg[AB_MAX_AST];
+        for (int m = 0; m < sb->num; m++)
+            if ((rc = fill_target(&tg[m], &sb->targets[m]))) return rc;
+        if (!sb->b200_dev_targets[dev]) CU(cudaMalloc(&sb->b200_dev_targets[dev], sizeof(AbSpkTarget) * AB_MAX_AST));
+        /* descriptors carry the (joinable) masses, so they are refreshed on every build */
+        CU(cudaMemcpy(sb->b200_dev_targets[dev], tg, sizeof(AbSpkTarget) * sb->num, cudaMemcpyHostToDevice));
+        E->a_tgt = (const AbSpkTarget*)sb->b200_dev_targets[dev];
+    }
+    return 0;
+}
+
+static void build_force_opts(const struct assist_gpu_options* o, int has_params, AbForceOpts* F) {
+    memset(F, 0, sizeof(*F));
+    F->forces = o->forces;
+    F->gr_eih_sources = o->gr_eih_sources < 0 ? 0 : (o->gr_eih_sources > AB_NPLANETS ? AB_NPLANETS : o->gr_eih_sources);
+    F->geocentric = o->geocentric;
+    F->has_params = has_params;
+    F->alpha = o->alpha; F->nk = o->nk; F->nm = o->nm; F->nn = o->nn; F->r0 = o->r0;
+    /* Earth pole reset to the J2000 equator, solar pole RA 286.13 Dec 63.87
+     * (reference src/forces.c:484-490, 670-676); same libm calls as the reference. */
+    const double RAe = 0.0 * M_PI / 180., Dece = 90.0 * M_PI / 180.;
+    F->e_cosa = cos(RAe); F->e_sina = sin(RAe); F->e_cosd = cos(Dece); F->e_sind = sin(Dece);
+    const double RAs = 286.13 * M_PI / 180., Decs = 63.87 * M_PI / 180.;
+    F->s_cosa = cos(RAs); F->s_sina = sin(RAs); F->s_cosd = cos(Decs); F->s_sind = sin(Decs);
+}
+
+extern "C" int assist_gpu_ephem_upload(const struct assist_ephem* ephem) {
+    AbEphem E;
+    return build_ephem(ephem, &E);
+}
+
+extern "C" int assist_gpu_ephem_nbodies(const struct assist_ephem* ephem) {
+    if (!ephem) return 0;
+    return AB_NPLANETS + (ephem->spk_asteroids ? ephem->spk_asteroids->num : 0);
+}
+
+extern "C" int assist_gpu_ephem_eval(const struct assist_ephem* ephem, int math, const double* t, int n_t,
+                                     double* out, int* status) {
+    AbEphem E;
+    int rc = build_ephem(ephem, &E);
+    if (rc) return rc;
+    if (n_t <= 0) return 0;
+    const int nb = AB_NPLANETS + E.n_ast;
+    double *d_t = nullptr, *d_out = nullptr;
+    int* d_st = nullptr;
+    CU(cudaMalloc(&d_t, sizeof(double) * n_t));
+    CU(cudaMalloc(&d_out, sizeof(double) * 10 * (size_t)n_t * nb));
+    CU(cudaMalloc(&d_st, sizeof(int) * (size_t)n_t * nb));
+    CU(cudaMemcpy(d_t, t, sizeof(double) * n_t, cudaMemcpyHostToDevice));
+    cudaError_t e = (math == ASSIST_GPU_MATH_FAST) ? ab_launch_ephem_eval_fast(E, d_t, n_t, d_out, d_st, 0)
+                                                   : ab_launch_ephem_eval_strict(E, d_t, n_t, d_out, d_st, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * 10 * (size_t)n_t * nb, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && status) e = cudaMemcpy(status, d_st, sizeof(int) * (size_t)n_t * nb, cudaMemcpyDeviceToHost);
+    cudaFree(d_t); cudaFree(d_out); cudaFree(d_st);
+    if (e != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "ephem_eval: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int assist_gpu_eval_forces(const struct assist_ephem* ephem, const struct assist_gpu_options* opt,
+                                      int n_sys, int n_var, const double* t, int t_per_system,
+                                      const double* state, const double* params, double* acc, int* status) {
+    AbEphem E;
+    int rc = build_ephem(ephem, &E);
+    if (rc) return rc;
+    if (n_var < 0 || n_var > AB_NVMAX) return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "n_var=%d (max %d)", n_var, AB_NVMAX);
+    if (n_sys <= 0) return 0;
+    AbForceOpts F;
+    build_force_opts(opt, params != NULL, &F);
+    const int K = 1 + n_var;
+    const size_t nt = t_per_system ? n_sys : 1;
+    double *d_t = nullptr, *d_state = nullptr, *d_prm = nullptr, *d_acc = nullptr;
+    int* d_st = nullptr;
+    CU(cudaMalloc(&d_t, sizeof(double) * nt));
+    CU(cudaMalloc(&d_state, sizeof(double) * 6 * (size_t)n_sys * K));
+    CU(cudaMalloc(&d_acc, sizeof(double) * 3 * (size_t)n_sys * K));
+    CU(cudaMalloc(&d_st, sizeof(int) * (size_t)n_sys));
+    if (params) {
+        CU(cudaMalloc(&d_prm, sizeof(double) * 3 * (size_t)n_sys * K));
+        CU(cudaMemcpy(d_prm, params, sizeof(double) * 3 * (size_t)n_sys * K, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(d_t, t, sizeof(double) * nt, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_state, state, sizeof(double) * 6 * (size_t)n_sys * K, cudaMemcpyHostToDevice));
+    cudaError_t e = (opt->math == ASSIST_GPU_MATH_FAST)
+        ? ab_launch_force_eval_fast(E, F, n_sys, K, d_t, t_per_system, d_state, d_prm, d_acc, d_st, 0)
+        : ab_launch_force_eval_strict(E, F, n_sys, K, d_t, t_per_system, d_state, d_prm, d_acc, d_st, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(acc, d_acc, sizeof(double) * 3 * (size_t)n_sys * K, cudaMemcpyDeviceToHost);
+    int first_err = 0;
+    if (e == cudaSuccess) {
+        int* hst = (int*)malloc(sizeof(int) * n_sys);
+        e = cudaMemcpy(hst, d_st, sizeof(int) * n_sys, cudaMemcpyDeviceToHost);
+        for (int i = 0; i < n_sys; i++) {
+            if (status) status[i] = hst[i];
+            if (hst[i] && !first_err) first_err = hst[i];
+        }
+        free(hst);
+    }
+    cudaFree(d_t); cudaFree(d_state); cudaFree(d_prm); cudaFree(d_acc); cudaFree(d_st);
+    if (e != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "eval_forces: %s", cudaGetErrorString(e));
+    if (first_err) return set_err(first_err, "%s", assist_error_messages[first_err]);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* batches                                                                  */
+/* ------------------------------------------------------------------------ */
+
+struct assist_gpu_batch {
+    const struct assist_ephem* ephem;
+    int n, nvar, K, C, mode, device;
+    struct assist_gpu_options opt;
+    AbBatch d;
+    char* block;            /* one device allocation holding every array */
+    size_t block_bytes;
+    char* snapshot;         /* device copy made by assist_gpu_batch_snapshot */
+    double* d_stage;        /* [n][K][6] AoS staging on the device */
+    double* d_stage_prm;    /* [n][K][3] */
+    double* d_out;          /* dense output staging */
+    size_t d_out_bytes;
+    cudaEvent_t ev0, ev1;
+    struct assist_gpu_stats stats;
+};
+
+__global__ void aos_to_soa_kernel(const double* __restrict__ aos, int n, int K, int width, int off, int cnt, double* __restrict__ soa) {
+    /* aos[i][j][width]; copies fields off..off+cnt-1 of body j to soa[(3*j + c) * n + i] */
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n * K) return;
+    const long long i = gid % n;
+    const int j = (int)(gid / n);
+    for (int c = 0; c < cnt; c++) soa[((long long)(3 * j + c)) * n + i] = aos[(i * K + j) * width + off + c];
+}
+
+__global__ void soa_to_aos_kernel(const double* __restrict__ soa, int n, int K, int width, int off, int cnt, double* __restrict__ aos) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n * K) return;
+    const long long i = gid % n;
+    const int j = (int)(gid / n);
+    for (int c = 0; c < cnt; c++) aos[(i * K + j) * width + off + c] = soa[((long long)(3 * j + c)) * n + i];
+}
+
+__global__ void fill_kernel(double* p, long long n, double v) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n) p[gid] = v;
+}
+
+__global__ void fill_int_kernel(int* p, long long n, int v) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n) p[gid] = v;
+}
+
+static inline int blocks_for(long long n) { return (int)((n + 255) / 256); }
+
+extern "C" assist_gpu_batch* assist_gpu_batch_create(const struct assist_ephem* ephem, int n_sys, int n_var, int mode) {
+    int dev;
+    if (ensure_device(&dev)) return NULL;
+    if (n_sys <= 0 || n_var < 0 || n_var > AB_NVMAX) {
+        set_err(ASSIST_GPU_ERR_UNSUPPORTED, "batch of %d systems with %d variational particles each (max %d) is not supported", n_sys, n_var, AB_NVMAX);
+        return NULL;
+    }
+    assist_gpu_batch* b = (assist_gpu_batch*)calloc(1, sizeof(assist_gpu_batch));
+    b->ephem = ephem; b->n = n_sys; b->nvar = n_var; b->K = 1 + n_var; b->C = 3 * b->K; b->mode = mode; b->device = dev;
+    assist_gpu_default_options(&b->opt);
+    const size_t n = n_sys, C = b->C;
+    const size_t per = C * n;                      /* doubles in one [C][n] array */
+    const size_t n_small = 12 + 42 * 1;            /* pos vel acc x0 v0 a0 csx csv ls_pos ls_vel ls_acc prm  (+ 6 seven-deep tables) */
+    (void)n_small;
+    size_t doubles = 12 * per + 42 * per + 3 * n;  /* + t dt dt_last */
+    size_t bytes = doubles * sizeof(double);
+    bytes += 4 * n * sizeof(unsigned long long);   /* counters */
+    bytes += 2 * n * sizeof(int);                  /* nv, status */
+    bytes += sizeof(AbShared) + 64;
+    if (cudaMalloc((void**)&b->block, bytes) != cudaSuccess) {
+        set_err(ASSIST_GPU_ERR_CUDA, "cudaMalloc of %zu bytes failed", bytes);
+        free(b);
+        return NULL;
+    }
+    cudaMemset(b->block, 0, bytes);
+    b->block_bytes = bytes;
+    double* p = (double*)b->block;
+    AbBatch& d = b->d;
+    d.n = n_sys; d.K = b->K; d.C = b->C; d.mode = mode;
+    d.pos = p; p += per; d.vel = p; p += per; d.acc = p; p += per;
+    d.x0 = p; p += per; d.v0 = p; p += per; d.a0 = p; p += per; d.csx = p; p += per; d.csv = p; p += per;
+    d.ls_pos = p; p += per; d.ls_vel = p; p += per; d.ls_acc = p; p += per; d.prm = p; p += per;
+    d.b = p; p += 7 * per; d.g = p; p += 7 * per; d.e = p; p += 7 * per;
+    d.csb = p; p += 7 * per; d.br = p; p += 7 * per; d.er = p; p += 7 * per;
+    d.t = p; p += n; d.dt = p; p += n; d.dt_last = p; p += n;
+    unsigned long long* q = (unsigned long long*)p;
+    d.steps = q; q += n; d.rejected = q; q += n; d.iters = q; q += n; d.evals = q; q += n;
+    d.sh = (AbShared*)q;
+    int* ip = (int*)((char*)q + ((sizeof(AbShared) + 63) / 64) * 64);
+    d.nv = ip; ip += n; d.status = ip; ip += n;
+    d.epsilon = b->opt.epsilon; d.min_dt = b->opt.min_dt; d.has_params = 0;
+    cudaMalloc((void**)&b->d_stage, sizeof(double) * 6 * n * b->K);
+    cudaMalloc((void**)&b->d_stage_prm, sizeof(double) * 3 * n * b->K);
+    cudaEventCreate(&b->ev0);
+    cudaEventCreate(&b->ev1);
+    fill_int_kernel<<<blocks_for(n), 256>>>(d.nv, n, n_var);
+    fill_int_kernel<<<blocks_for(n), 256>>>(d.status, n, -3);
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        set_err(ASSIST_GPU_ERR_CUDA, "batch initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        assist_gpu_batch_free(b);
+        return NULL;
+    }
+    return b;
+}
+
+extern "C" void assist_gpu_batch_free(assist_gpu_batch* b) {
+    if (!b) return;
+    cudaFree(b->block); cudaFree(b->snapshot); cudaFree(b->d_stage); cudaFree(b->d_stage_prm); cudaFree(b->d_out);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    free(b);
+}
+
+extern "C" int assist_gpu_batch_set_options(assist_gpu_batch* b, const struct assist_gpu_options* opt) {
+    if (!b || !opt) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    b->opt = *opt;
+    b->d.epsilon = opt->epsilon;
+    b->d.min_dt = opt->min_dt;
+    return 0;
+}
+
+static int upload_particles(assist_gpu_batch* b, const double* state) {
+    const size_t n = b->n;
+    CU(cudaMemcpy(b->d_stage, state, sizeof(double) * 6 * n * b->K, cudaMemcpyHostToDevice));
+    aos_to_soa_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d_stage, b->n, b->K, 6, 0, 3, b->d.pos);
+    aos_to_soa_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d_stage, b->n, b->K, 6, 3, 3, b->d.vel);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int assist_gpu_batch_set_state(assist_gpu_batch* b, double t0, double dt0, const double* state,
+                                          const double* params, const int* nvar_per_system) {
+    if (!b || !state) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(b->device));
+    const size_t n = b->n;
+    /* fresh IAS15 history: everything zero (REBOUND zeroes b, e, csx, csv ... on allocation) */
+    CU(cudaMemset(b->block, 0, b->block_bytes));
+    int rc = upload_particles(b, state);
+    if (rc) return rc;
+    if (params) {
+        CU(cudaMemcpy(b->d_stage_prm, params, sizeof(double) * 3 * n * b->K, cudaMemcpyHostToDevice));
+        aos_to_soa_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d_stage_prm, b->n, b->K, 3, 0, 3, b->d.prm);
+        b->d.has_params = 1;
+    } else {
+        b->d.has_params = 0;
+    }
+    if (nvar_per_system) {
+        for (size_t i = 0; i < n; i++)
+            if (nvar_per_system[i] < 0 || nvar_per_system[i] > b->nvar) return set_err(ASSIST_GPU_ERR_ARG, "nvar_per_system[%zu] out of range", i);
+        CU(cudaMemcpy(b->d.nv, nvar_per_system, sizeof(int) * n, cudaMemcpyHostToDevice));
+    } else {
+        fill_int_kernel<<<blocks_for(n), 256>>>(b->d.nv, n, b->nvar);
+    }
+    fill_kernel<<<blocks_for(n), 256>>>(b->d.t, n, t0);
+    fill_kernel<<<blocks_for(n), 256>>>(b->d.dt, n, dt0);
+    fill_int_kernel<<<blocks_for(n), 256>>>(b->d.status, n, -3);
+    AbShared sh;
+    memset(&sh, 0, sizeof(sh));
+    sh.t = t0; sh.dt = dt0; sh.status = -3;
+    CU(cudaMemcpy(b->d.sh, &sh, sizeof(sh), cudaMemcpyHostToDevice));
+    CU(cudaDeviceSynchronize());
+    memset(&b->stats, 0, sizeof(b->stats));
+    return 0;
+}
+
+extern "C" int assist_gpu_batch_update_particles(assist_gpu_batch* b, const double* state) {
+    if (!b || !state) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(b->device));
+    int rc = upload_particles(b, state);
+    if (rc) return rc;
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int assist_gpu_batch_set_time(assist_gpu_batch* b, double t, double dt) {
+    if (!b) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(b->device));
+    const size_t n = b->n;
+    fill_kernel<<<blocks_for(n), 256>>>(b->d.t, n, t);
+    fill_kernel<<<blocks_for(n), 256>>>(b->d.dt, n, dt);
+    AbShared sh;
+    CU(cudaMemcpy(&sh, b->d.sh, sizeof(sh), cudaMemcpyDeviceToHost));
+    sh.t = t; sh.dt = dt;
+    CU(cudaMemcpy(b->d.sh, &sh, sizeof(sh), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int assist_gpu_batch_snapshot(assist_gpu_batch* b) {
+    if (!b) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(b->device));
+    if (!b->snapshot) CU(cudaMalloc((void**)&b->snapshot, b->block_bytes));
+    CU(cudaMemcpy(b->snapshot, b->block, b->block_bytes, cudaMemcpyDeviceToDevice));
+    return 0;
+}
+
+extern "C" int assist_gpu_batch_restore(assist_gpu_batch* b) {
+    if (!b || !b->snapshot) return set_err(ASSIST_GPU_ERR_ARG, "no snapshot");
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(b->block, b->snapshot, b->block_bytes, cudaMemcpyDeviceToDevice, 0));
+    memset(&b->stats, 0, sizeof(b->stats));
+    return 0;
+}
+
+static int finish_launch(assist_gpu_batch* b, cudaError_t e, const char* what) {
+    if (e != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "%s launch failed: %s", what, cudaGetErrorString(e));
+    CU(cudaEventRecord(b->ev1, 0));
+    cudaError_t s = cudaEventSynchronize(b->ev1);
+    if (s != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+    b->stats.last_kernel_ms = ms;
+    b->stats.kernel_launches++;
+    return 0;
+}
+
+extern "C" int assist_gpu_batch_integrate(assist_gpu_batch* b, double t_end, int exact_finish_time, long max_steps) {
+    return ab_gpu_batch_integrate_ex(b, t_end, exact_finish_time, max_steps, 0);
+}
+
+extern "C" int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int exact_finish_time, long max_steps, int flags) {
+    if (!b) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(b->device));
+    AbEphem E;
+    int rc = build_ephem(b->ephem, &E);
+    if (rc) return rc;
+    AbForceOpts F;
+    build_force_opts(&b->opt, b->d.has_params, &F);
+    const bool fast = (b->opt.math == ASSIST_GPU_MATH_FAST);
+    cudaError_t e;
+    if (b->mode == ASSIST_GPU_PER_PARTICLE) {
+        CU(cudaEventRecord(b->ev0, 0));
+        e = fast ? ab_launch_pp_integrate_fast(E, F, b->d, t_end, exact_finish_time, 0)
+                 : ab_launch_pp_integrate_strict(E, F, b->d, t_end, exact_finish_time, 0);
+        return finish_launch(b, e, "pp_integrate");
+    }
+    /* shared step: barrier counter and reduction slots start from zero */
+    CU(cudaMemsetAsync((char*)b->d.sh + offsetof(AbShared, barrier), 0, sizeof(AbShared) - offsetof(AbShared, barrier), 0));
+    CU(cudaEventRecord(b->ev0, 0));
+    e = fast ? ab_launch_sh_integrate_fast(E, F, b->d, t_end, exact_finish_time, (long long)max_steps, flags, 0)
+             : ab_launch_sh_integrate_strict(E, F, b->d, t_end, exact_finish_time, (long long)max_steps, flags, 0);
+    rc = finish_launch(b, e, "sh_integrate");
+    if (rc) return rc;
+    AbShared sh;
+    CU(cudaMemcpy(&sh, b->d.sh, sizeof(sh), cudaMemcpyDeviceToHost));
+    if (sh.err_status) return set_err(sh.err_status, "%s", assist_error_messages[sh.err_status]);
+    return 0;
+}
+
+extern "C" int assist_gpu_batch_integrate_or_interpolate(assist_gpu_batch* b, const double* times, int n_times, double* out) {
+    if (!b || !times || !out || n_times <= 0) return set_err(ASSIST_GPU_ERR_ARG, "bad argument");
+    if (b->mode != ASSIST_GPU_PER_PARTICLE)
+        return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "batched epochs need a per-particle batch; use assist_gpu_batch_integrate + _interpolate for shared-step batches");
+    CU(cudaSetDevice(b->device));
+    AbEphem E;
+    int rc = build_ephem(b->ephem, &E);
+    if (rc) return rc;
+    AbForceOpts F;
+    build_force_opts(&b->opt, b->d.has_params, &F);
+    const size_t out_bytes = sizeof(double) * 6 * (size_t)b->n * b->K * n_times;
+    if (b->d_out_bytes < out_bytes + sizeof(double) * n_times) {
+        cudaFree(b->d_out);
+        b->d_out = nullptr; b->d_out_bytes = 0;
+        CU(cudaMalloc((void**)&b->d_out, out_bytes + sizeof(double) * n_times));
+        b->d_out_bytes = out_bytes + sizeof(double) * n_times;
+    }
+    double* d_times = (double*)((char*)b->d_out + out_bytes);
+    CU(cudaMemcpy(d_times, times, sizeof(double) * n_times, cudaMemcpyHostToDevice));
+    CU(cudaEventRecord(b->ev0, 0));
+    cudaError_t e = (b->opt.math == ASSIST_GPU_MATH_FAST) ? ab_launch_pp_dense_fast(E, F, b->d, d_times, n_times, b->d_out, 0)
+                                                          : ab_launch_pp_dense_strict(E, F, b->d, d_times, n_times, b->d_out, 0);
+    rc = finish_launch(b, e, "pp_dense");
+    if (rc) return rc;
+    CU(cudaMemcpy(out, b->d_out, out_bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int assist_gpu_batch_get_state(assist_gpu_batch* b, double* state, double* acc, double* t, double* dt,
+                                          double* dt_last_done, int* status) {
+    if (!b) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(b->device));
+    const size_t n = b->n;
+    if (state) {
+        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.pos, b->n, b->K, 6, 0, 3, b->d_stage);
+        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.vel, b->n, b->K, 6, 3, 3, b->d_stage);
+        CU(cudaMemcpy(state, b->d_stage, sizeof(double) * 6 * n * b->K, cudaMemcpyDeviceToHost));
+    }
+    if (acc) {
+        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.acc, b->n, b->K, 3, 0, 3, b->d_stage_prm);
+        CU(cudaMemcpy(acc, b->d_stage_prm, sizeof(double) * 3 * n * b->K, cudaMemcpyDeviceToHost));
+    }
+    if (b->mode == ASSIST_GPU_PER_PARTICLE) {
+        if (t) CU(cudaMemcpy(t, b->d.t, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        if (dt) CU(cudaMemcpy(dt, b->d.dt, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        if (dt_last_done) CU(cudaMemcpy(dt_last_done, b->d.dt_last, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        if (status) CU(cudaMemcpy(status, b->d.status, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    } else {
+        AbShared sh;
+        CU(cudaMemcpy(&sh, b->d.sh, sizeof(sh), cudaMemcpyDeviceToHost));
+        if (t) *t = sh.t;
+        if (dt) *dt = sh.dt;
+        if (dt_last_done) *dt_last_done = sh.dt_last;
+        if (status) *status = sh.status;
+    }
+    return 0;
+}
+
+extern "C" int ab_gpu_batch_update_params(assist_gpu_batch* b, const double* params) {
+    if (!b) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(b->device));
+    const size_t n = b->n;
+    if (params) {
+        CU(cudaMemcpy(b->d_stage_prm, params, sizeof(double) * 3 * n * b->K, cudaMemcpyHostToDevice));
+        aos_to_soa_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d_stage_prm, b->n, b->K, 3, 0, 3, b->d.prm);
+        CU(cudaGetLastError());
+        b->d.has_params = 1;
+    } else {
+        b->d.has_params = 0;
+    }
+    return 0;
+}
+
+/* state at the start of the last completed step (the reference's ax->last_state) */
+extern "C" int ab_gpu_batch_get_last_state(assist_gpu_batch* b, double* state, double* acc) {
+    if (!b) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(b->device));
+    const size_t n = b->n;
+    if (state) {
+        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.ls_pos, b->n, b->K, 6, 0, 3, b->d_stage);
+        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.ls_vel, b->n, b->K, 6, 3, 3, b->d_stage);
+        CU(cudaMemcpy(state, b->d_stage, sizeof(double) * 6 * n * b->K, cudaMemcpyDeviceToHost));
+    }
+    if (acc) {
+        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.ls_acc, b->n, b->K, 3, 0, 3, b->d_stage_prm);
+        CU(cudaMemcpy(acc, b->d_stage_prm, sizeof(double) * 3 * n * b->K, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+extern "C" int assist_gpu_batch_interpolate(assist_gpu_batch* b, double h, double* out) {
+    if (!b || !out) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    if (b->mode != ASSIST_GPU_SHARED_STEP) return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "interpolate needs a shared-step batch");
+    CU(cudaSetDevice(b->device));
+    AbShared sh;
+    CU(cudaMemcpy(&sh, b->d.sh, sizeof(sh), cudaMemcpyDeviceToHost));
+    cudaError_t e = (b->opt.math == ASSIST_GPU_MATH_FAST) ? ab_launch_sh_interpolate_fast(b->d, sh.dt_last, h, b->d_stage, 0)
+                                                          : ab_launch_sh_interpolate_strict(b->d, sh.dt_last, h, b->d_stage, 0);
+    if (e != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "interpolate: %s", cudaGetErrorString(e));
+    CU(cudaMemcpy(out, b->d_stage, sizeof(double) * 6 * (size_t)b->n * b->K, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+__global__ void sum_counters_kernel(const unsigned long long* __restrict__ c, long long n, unsigned long long* out) {
+    unsigned long long s = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += c[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+extern "C" int assist_gpu_batch_get_stats(assist_gpu_batch* b, struct assist_gpu_stats* stats) {
+    if (!b || !stats) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(b->device));
+    if (b->mode == ASSIST_GPU_PER_PARTICLE) {
+        unsigned long long* d_sum = nullptr;
+        unsigned long long h[4] = {0, 0, 0, 0};
+        CU(cudaMalloc((void**)&d_sum, sizeof(h)));
+        CU(cudaMemset(d_sum, 0, sizeof(h)));
+        const unsigned long long* src[4] = {b->d.steps, b->d.rejected, b->d.iters, b->d.evals};
+        for (int q = 0; q < 4; q++) sum_counters_kernel<<<256, 256>>>(src[q], b->n, d_sum + q);
+        CU(cudaMemcpy(h, d_sum, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(d_sum);
+        b->stats.steps = h[0]; b->stats.steps_rejected = h[1]; b->stats.pc_iterations = h[2]; b->stats.force_evals = h[3];
+    } else {
+        AbShared sh;
+        CU(cudaMemcpy(&sh, b->d.sh, sizeof(sh), cudaMemcpyDeviceToHost));
+        b->stats.steps = sh.steps; b->stats.steps_rejected = sh.rejected; b->stats.pc_iterations = sh.iters;
+        b->stats.force_evals = sh.evals * (unsigned long long)b->n;
+    }
+    *stats = b->stats;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* FP64 peak micro-benchmark (roofline denominator)                         */
+/* ------------------------------------------------------------------------ */
+
+__global__ void dfma_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" double assist_gpu_measure_fp64_peak(int iters) {
+    int dev;
+    if (ensure_device(&dev)) return -1.0;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int threads = 256, grid = sms * 8;
+    double* d = nullptr;
+    if (cudaMalloc((void**)&d, sizeof(double) * (size_t)grid * threads) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    dfma_peak_kernel<<<grid, threads>>>(d, 16);     /* warm-up */
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, 0);
+        dfma_peak_kernel<<<grid, threads>>>(d, iters);
+        cudaEventRecord(e1, 0);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8 * 16 * (double)iters * (double)grid * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d);
+    return best;
+}

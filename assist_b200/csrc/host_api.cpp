@@ -1,0 +1,477 @@
+/*
+ * host_api.cpp -- the ASSIST host API of include/assist.h ("front door").
+ *
+ * Same entry points, argument meaning and error behaviour as the reference
+ * (reference src/assist.c); what differs is what happens behind them: file
+ * providers only parse, and every evaluation / integration is a CUDA launch.
+ */
+#include <fcntl.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <vector>
+
+#include "assist.h"
+#include "assist_ephem_files.h"
+#include "assist_gpu.h"
+#include "host_internal.h"
+
+static_assert(sizeof(struct assist_ephem) == 208, "struct assist_ephem is ABI (reference assist/ephem.py:95-120)");
+static_assert(sizeof(struct assist_extras) == 112, "struct assist_extras is ABI (reference assist/extras.py:84-100)");
+static_assert(sizeof(struct reb_particle) == 128, "struct reb_particle must be REBOUND's 128-byte record");
+
+#define AB_STR2(s) #s
+#define AB_STR(s) AB_STR2(s)
+#ifndef ASSISTGITHASH
+#define ASSISTGITHASH notavailable0000000000000000000000000001
+#endif
+
+extern "C" {
+
+const char* assist_build_str = __DATE__ " " __TIME__;
+const char* assist_version_str = "1.2.0";                 /* API level of the reference this library mirrors */
+const char* assist_githash_str = AB_STR(ASSISTGITHASH);
+
+/* indices follow enum ASSIST_STATUS (reference src/assist.c:52-59); index 6 is ours */
+const char* assist_error_messages[] = {
+    "No error has occured.",
+    "The JPL planet ephemeris file has not been found.",
+    "The JPL asteroid ephemeris file has not been found. Asteroid forces have been disabled.",
+    "The requested asteroid ID has not been found.",
+    "The requested planet ID has not been found.",
+    "The requested time is outside the coverage provided by the ephemeris file.",
+    "No usable CUDA device: assist-b200 evaluates everything on the GPU and has no CPU path.",
+};
+const int assist_error_messages_N = 7;
+
+/* ---- format detection and discovery (reference src/assist.c:66-154) ------ */
+
+int assist_detect_ascii_bin_signature(int fd) {
+    /* three 6-character constant names live at 0x00FC; at least two must look like names */
+    char names[18];
+    if (pread(fd, names, sizeof(names), 0x00FC) != (ssize_t)sizeof(names)) return 0;
+    int plausible = 0;
+    for (int i = 0; i < 3; i++) {
+        const unsigned char* nm = (const unsigned char*)&names[6 * i];
+        const bool starts_alpha = (nm[0] >= 'A' && nm[0] <= 'Z') || (nm[0] >= 'a' && nm[0] <= 'z');
+        if (!starts_alpha) continue;
+        int alnum = 0;
+        bool ok = true;
+        for (int j = 0; j < 6; j++) {
+            const unsigned char c = nm[j];
+            if ((c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || (c >= '0' && c <= '9')) alnum++;
+            else if (c != ' ' && c != '\0') { ok = false; break; }
+        }
+        if (ok && alnum >= 2) plausible++;
+    }
+    return plausible >= 2;
+}
+
+ephemeris_file_format_t assist_detect_ephemeris_file_format(int fd) {
+    char magic[8];
+    const ssize_t got = pread(fd, magic, sizeof(magic), 0);
+    if (got <= 0) return FILE_FORMAT_UNKNOWN;
+    if (got >= 8 && memcmp(magic, "DAF/SPK ", 8) == 0) { lseek(fd, 0, SEEK_SET); return FILE_FORMAT_VALID_BSP; }
+    if (assist_detect_ascii_bin_signature(fd)) { lseek(fd, 0, SEEK_SET); return FILE_FORMAT_ASCII_BIN; }
+    return FILE_FORMAT_UNKNOWN;
+}
+
+int assist_discover_planets_path(char* out_path, size_t out_path_size, const char* assist_dir) {
+    if (out_path == NULL || out_path_size == 0 || assist_dir == NULL) return 0;
+    static const char* candidates[] = {"/data/de441.bsp", "/data/de440.bsp", "/data/linux_m13000p17000.441",
+                                       "/data/linux_p1550p2650.440"};
+    for (int c = 0; c < 4; c++) {
+        snprintf(out_path, out_path_size, "%s%s", assist_dir, candidates[c]);
+        if (access(out_path, R_OK) == 0) return 1;
+    }
+    return 0;
+}
+
+/* ---- ephemeris life cycle (reference src/assist.c:188-377) ---------------- */
+
+int assist_ephem_init(struct assist_ephem* ephem, char* user_planets_path, char* user_asteroids_path) {
+    ephem->jd_ref = 2451545.0;
+    ephem->spk_planets = NULL;
+    ephem->spk_asteroids = NULL;
+    ephem->ascii_planets = NULL;
+    const char* base = getenv("ASSIST_DIR");
+    char planets_path[1024], asteroids_path[1024];
+
+    if (user_planets_path == NULL) {
+        if (base == NULL) return ASSIST_ERROR_EPHEM_FILE;
+        if (!assist_discover_planets_path(planets_path, sizeof(planets_path), base))
+            snprintf(planets_path, sizeof(planets_path), "%s/data/de441.bsp", base);
+    } else {
+        snprintf(planets_path, sizeof(planets_path), "%s", user_planets_path);
+    }
+    ephemeris_file_format_t fmt = FILE_FORMAT_UNKNOWN;
+    {
+        const int fd = open(planets_path, O_RDONLY);
+        if (fd >= 0) { fmt = assist_detect_ephemeris_file_format(fd); close(fd); }
+    }
+
+    bool have_ast_path = true;
+    if (user_asteroids_path == NULL) {
+        if (base == NULL) have_ast_path = false;
+        else snprintf(asteroids_path, sizeof(asteroids_path), "%s/data/sb441-n16.bsp", base);
+    } else {
+        snprintf(asteroids_path, sizeof(asteroids_path), "%s", user_asteroids_path);
+    }
+    bool ast_missing = !have_ast_path;
+    if (have_ast_path) {
+        ephem->spk_asteroids = assist_spk_init(asteroids_path);
+        if (ephem->spk_asteroids == NULL) ast_missing = true;
+    }
+
+    if (fmt == FILE_FORMAT_VALID_BSP) {
+        ephem->spk_planets = assist_spk_init(planets_path);
+        if (ephem->spk_planets == NULL) return ASSIST_ERROR_EPHEM_FILE;
+        ephem->planets_source = FILE_FORMAT_VALID_BSP;
+        static const int naif_by_assist[] = {10, 1, 2, 399, 301, 4, 5, 6, 7, 8, 9};
+        for (int k = 0; k < ASSIST_BODY_NPLANETS; k++) {
+            struct spk_target* t = assist_spk_find_target(ephem->spk_planets, naif_by_assist[k]);
+            ephem->spk_target_index[k] = t ? (int)(t - ephem->spk_planets->targets) : -1;
+        }
+        struct spk_target* emb = assist_spk_find_target(ephem->spk_planets, 3);
+        ephem->spk_emb_index = emb ? (int)(emb - ephem->spk_planets->targets) : -1;
+        struct spk_constants_and_masses data = assist_load_spk_constants_and_masses(planets_path);
+        assist_apply_spk_constants(ephem, &data);
+        assist_spk_join_masses(ephem->spk_planets, &data.masses, ephem->EMRAT);
+        if (ephem->spk_asteroids) assist_spk_join_masses(ephem->spk_asteroids, &data.masses, ephem->EMRAT);
+        assist_free_spk_constants_and_masses(&data);
+        ephem->planets_calc = assist_spk_calc_planets_by_assist;
+    } else if (fmt == FILE_FORMAT_ASCII_BIN) {
+        ephem->ascii_planets = assist_ascii_init(planets_path);
+        if (ephem->ascii_planets == NULL) return ASSIST_ERROR_EPHEM_FILE;
+        ephem->planets_source = FILE_FORMAT_ASCII_BIN;
+        const struct ascii_s* a = ephem->ascii_planets;
+        ephem->J2E = a->J2E; ephem->J3E = a->J3E; ephem->J4E = a->J4E; ephem->J2SUN = a->J2SUN;
+        ephem->AU = a->AU; ephem->RE = a->RE; ephem->CLIGHT = a->CLIGHT; ephem->ASUN = a->ASUN;
+        ephem->EMRAT = a->cem;
+        ephem->Re_eq = ephem->RE / ephem->AU;
+        ephem->Rs_eq = ephem->ASUN / ephem->AU;
+        ephem->c_AU_per_day = (ephem->CLIGHT / ephem->AU) * 86400.0;
+        ephem->c_squared = ephem->c_AU_per_day * ephem->c_AU_per_day;
+        ephem->over_c_squared = 1.0 / ephem->c_squared;
+        ephem->planets_calc = assist_ascii_calc_from_ephem;
+        if (ephem->spk_asteroids) {
+            /* asteroid GMs come from the MAxxxx constants of the planets file (reference src/assist.c:312-333) */
+            for (int n = 0; n < ephem->spk_asteroids->num; n++) {
+                struct spk_target* tg = &ephem->spk_asteroids->targets[n];
+                if (tg->code >= 2000000) {
+                    char key[16];
+                    snprintf(key, sizeof(key), "MA%04d", tg->code - 2000000);
+                    double gm = 0.0;
+                    if (assist_ascii_find_constant(a, key, &gm)) tg->mass = gm;
+                } else if (tg->code == 399) tg->mass = a->mass[ASSIST_BODY_EARTH];
+                else if (tg->code == 301) tg->mass = a->mass[ASSIST_BODY_MOON];
+                else if (tg->code == 10) tg->mass = a->mass[ASSIST_BODY_SUN];
+            }
+        }
+    } else {
+        fprintf(stderr, "(ASSIST) Error: Failed to initialize planets ephemeris from '%s'.\n", planets_path);
+        fprintf(stderr, "(ASSIST) Supported: NAIF SPK kernels (.bsp, e.g. de440.bsp) and JPL binary ephemerides (.440/.441).\n");
+        return ASSIST_ERROR_EPHEM_FILE;
+    }
+    if (ast_missing) fprintf(stderr, "(ASSIST) %s\n", assist_error_messages[ASSIST_ERROR_AST_FILE]);
+    return ASSIST_SUCCESS;
+}
+
+void assist_ephem_free_pointers(struct assist_ephem* ephem) {
+    if (ephem->spk_planets) { assist_spk_free(ephem->spk_planets); ephem->spk_planets = NULL; }
+    if (ephem->spk_asteroids) { assist_spk_free(ephem->spk_asteroids); ephem->spk_asteroids = NULL; }
+    if (ephem->ascii_planets) { assist_ascii_free(ephem->ascii_planets); ephem->ascii_planets = NULL; }
+}
+
+void assist_ephem_free(struct assist_ephem* ephem) {
+    if (!ephem) return;
+    assist_ephem_free_pointers(ephem);
+    free(ephem);
+}
+
+struct assist_ephem* assist_ephem_create(char* user_planets_path, char* user_asteroids_path) {
+    struct assist_ephem* ephem = (struct assist_ephem*)calloc(1, sizeof(struct assist_ephem));
+    const int error = assist_ephem_init(ephem, user_planets_path, user_asteroids_path);
+    if (error != ASSIST_SUCCESS) {
+        fprintf(stderr, "(ASSIST) An error occured while trying to initialize the ephemeris structure.\n");
+        fprintf(stderr, "(ASSIST) %s\n", assist_error_messages[error]);
+        assist_ephem_free(ephem);
+        return NULL;
+    }
+    return ephem;
+}
+
+void assist_ephem_time_bounds(const struct assist_ephem* ephem, double* t_beg, double* t_end) {
+    if (ephem == NULL) return;
+    double beg = -INFINITY, end = INFINITY;
+    const struct spk_s* files[2] = {ephem->spk_planets, ephem->spk_asteroids};
+    for (int f = 0; f < 2; f++) {
+        if (!files[f]) continue;
+        for (int i = 0; i < files[f]->num; i++) {
+            if (files[f]->targets[i].beg > beg) beg = files[f]->targets[i].beg;
+            if (files[f]->targets[i].end < end) end = files[f]->targets[i].end;
+        }
+    }
+    if (ephem->spk_planets == NULL && ephem->ascii_planets != NULL) {
+        if (ephem->ascii_planets->beg > beg) beg = ephem->ascii_planets->beg;
+        if (ephem->ascii_planets->end < end) end = ephem->ascii_planets->end;
+    }
+    if (t_beg) *t_beg = beg - ephem->jd_ref;
+    if (t_end) *t_end = end - ephem->jd_ref;
+}
+
+/* ---- ephemeris queries (GPU-backed) --------------------------------------- */
+
+static int map_gpu_error(int rc) {
+    if (rc >= 0) return rc;
+    fprintf(stderr, "(ASSIST) %s\n", assist_gpu_last_error());
+    return ASSIST_ERROR_GPU;
+}
+
+/* All bodies at time t in one launch; out has nbodies*10 doubles. */
+static int eval_all_bodies(const struct assist_ephem* ephem, double t, std::vector<double>& out, std::vector<int>& st) {
+    const int nb = assist_gpu_ephem_nbodies(ephem);
+    out.resize((size_t)nb * 10);
+    st.resize(nb);
+    return assist_gpu_ephem_eval(ephem, ASSIST_GPU_MATH_STRICT, &t, 1, out.data(), st.data());
+}
+
+int assist_all_ephem(const struct assist_ephem* ephem, struct assist_ephem_cache* cache, const int i, const double t,
+                     double* const GM, double* const x, double* const y, double* const z,
+                     double* const vx, double* const vy, double* const vz,
+                     double* const ax, double* const ay, double* const az) {
+    const int nb = assist_gpu_ephem_nbodies(ephem);
+    if (i < 0) return ASSIST_ERROR_NEPHEM;
+    if (i >= nb) return (i < ASSIST_BODY_NPLANETS) ? ASSIST_ERROR_NEPHEM : (ephem->spk_asteroids ? ASSIST_ERROR_NAST : ASSIST_ERROR_AST_FILE);
+    struct assist_cache_item item;
+    bool hit = false;
+    if (cache) {
+        /* seven slots per body keyed on the exact time (reference src/forces.c:180-197) */
+        for (int s = 0; s < 7; s++) if (cache->t[7 * i + s] == t) { item = cache->items[7 * i + s]; hit = true; break; }
+    }
+    if (!hit) {
+        std::vector<double> out;
+        std::vector<int> st;
+        const int rc = eval_all_bodies(ephem, t, out, st);
+        if (rc) return map_gpu_error(rc);
+        if (st[i] != ASSIST_SUCCESS) return st[i];
+        if (cache) {
+            /* one launch produced every body: refresh the slot of each (oldest in the direction of travel) */
+            for (int b = 0; b < nb; b++) {
+                if (st[b] != ASSIST_SUCCESS) continue;
+                double* ct = cache->t + 7 * b;
+                int os = 0;
+                for (int s = 1; s < 7; s++) if ((cache->dt_sign > 0) ? (ct[s] < ct[os]) : (ct[s] > ct[os])) os = s;
+                ct[os] = t;
+                memcpy(&cache->items[7 * b + os], &out[(size_t)b * 10], sizeof(struct assist_cache_item));
+            }
+        }
+        memcpy(&item, &out[(size_t)i * 10], sizeof(item));
+    }
+    *GM = item.GM; *x = item.x; *y = item.y; *z = item.z;
+    *vx = item.vx; *vy = item.vy; *vz = item.vz; *ax = item.ax; *ay = item.ay; *az = item.az;
+    return ASSIST_SUCCESS;
+}
+
+struct reb_particle assist_get_particle_with_error(const struct assist_ephem* ephem, const int particle_id, const double t, int* error) {
+    struct reb_particle p;
+    memset(&p, 0, sizeof(p));
+    double GM = 0;
+    const int flag = assist_all_ephem(ephem, NULL, particle_id, t, &GM, &p.x, &p.y, &p.z, &p.vx, &p.vy, &p.vz, &p.ax, &p.ay, &p.az);
+    *error = flag;
+    p.m = GM;    /* GM, not mass (reference src/assist.c:509) */
+    return p;
+}
+
+struct reb_particle assist_get_particle(const struct assist_ephem* ephem, const int particle_id, const double t) {
+    int error = 0;
+    struct reb_particle p = assist_get_particle_with_error(ephem, particle_id, t, &error);
+    if (error != ASSIST_SUCCESS) {
+        fprintf(stderr, "(ASSIST) An error occured while trying to initialize particle from ephemeris data.\n");
+        fprintf(stderr, "(ASSIST) %s\n", assist_error_messages[error < assist_error_messages_N ? error : 0]);
+    }
+    return p;
+}
+
+/* planets_calc providers: same signature as the reference's function pointer */
+static enum ASSIST_STATUS planets_calc_gpu(const struct assist_ephem* ephem, double jd_ref, double jd_rel, int body,
+                                           double* GM, double* x, double* y, double* z, double* vx, double* vy, double* vz,
+                                           double* ax, double* ay, double* az) {
+    if (body < 0 || body >= ASSIST_BODY_NPLANETS) return ASSIST_ERROR_NEPHEM;
+    /* the kernels take times relative to ephem->jd_ref */
+    const double t = (jd_ref - ephem->jd_ref) + jd_rel;
+    return (enum ASSIST_STATUS)assist_all_ephem(ephem, NULL, body, t, GM, x, y, z, vx, vy, vz, ax, ay, az);
+}
+
+enum ASSIST_STATUS assist_spk_calc_planets_by_assist(const struct assist_ephem* ephem, double jd_ref, double jd_rel, int assist_body,
+                                                     double* GM, double* x, double* y, double* z, double* vx, double* vy, double* vz,
+                                                     double* ax, double* ay, double* az) {
+    if (!ephem || !ephem->spk_planets) return ASSIST_ERROR_NEPHEM;
+    return planets_calc_gpu(ephem, jd_ref, jd_rel, assist_body, GM, x, y, z, vx, vy, vz, ax, ay, az);
+}
+
+enum ASSIST_STATUS assist_ascii_calc_from_ephem(const struct assist_ephem* ephem, double jd_ref, double jd_rel, int body,
+                                                double* const GM, double* const x, double* const y, double* const z,
+                                                double* const vx, double* const vy, double* const vz,
+                                                double* const ax, double* const ay, double* const az) {
+    if (!ephem || !ephem->ascii_planets) return ASSIST_ERROR_EPHEM_FILE;
+    return planets_calc_gpu(ephem, jd_ref, jd_rel, body, GM, x, y, z, vx, vy, vz, ax, ay, az);
+}
+
+/* ---- attach / detach (reference src/assist.c:379-501) --------------------- */
+
+static void assist_extras_cleanup(struct reb_simulation* sim) {
+    struct assist_extras* assist = (struct assist_extras*)sim->extras;
+    if (assist) assist->sim = NULL;
+}
+
+void ab_host_pre_timestep_marker(struct reb_simulation* r) { (void)r; }
+
+void assist_init(struct assist_extras* assist, struct reb_simulation* sim, struct assist_ephem* ephem) {
+    assist->sim = sim;
+    assist->ephem_cache = (struct assist_ephem_cache*)calloc(1, sizeof(struct assist_ephem_cache));
+    int N_total = ASSIST_BODY_NPLANETS;
+    if (ephem->spk_asteroids) N_total += ephem->spk_asteroids->num;
+    assist->gr_eih_sources = 1;
+    assist->ephem_cache->items = (struct assist_cache_item*)calloc((size_t)N_total * 7, sizeof(struct assist_cache_item));
+    assist->ephem_cache->t = (double*)malloc((size_t)N_total * 7 * sizeof(double));
+    for (int i = 0; i < 7 * N_total; i++) assist->ephem_cache->t[i] = -1e306;
+    assist->ephem_cache->dt_sign = 1.0;
+    assist->ephem = ephem;
+    assist->particle_params = NULL;
+    assist->forces = ASSIST_FORCE_SUN | ASSIST_FORCE_PLANETS | ASSIST_FORCE_ASTEROIDS | ASSIST_FORCE_NON_GRAVITATIONAL |
+                     ASSIST_FORCE_EARTH_HARMONICS | ASSIST_FORCE_SUN_HARMONICS | ASSIST_FORCE_GR_EIH;
+    assist->last_state = NULL;
+    assist->current_state = NULL;
+    assist->alpha = 1.0; assist->nk = 0.0; assist->nm = 2.0; assist->nn = 5.093; assist->r0 = 1.0;
+
+    sim->integrator = REB_INTEGRATOR_IAS15;
+    sim->gravity = REB_GRAVITY_NONE;
+    sim->extras = assist;
+    sim->extras_cleanup = assist_extras_cleanup;
+    sim->additional_forces = assist_additional_forces;
+    sim->force_is_velocity_dependent = 1;
+    sim->ri_ias15.adaptive_mode = 1;
+}
+
+struct assist_extras* assist_attach(struct reb_simulation* sim, struct assist_ephem* ephem) {
+    if (sim == NULL) {
+        fprintf(stderr, "(ASSIST) Error: Simulation pointer passed to assist_attach was NULL.\n");
+        return NULL;
+    }
+    int should_free = 0;
+    if (ephem == NULL) {
+        ephem = assist_ephem_create(NULL, NULL);
+        if (ephem == NULL) {
+            fprintf(stderr, "(ASSIST) Error: Ephemeris pointer passed to assist_attach was NULL. Initialization with default path failed.\n");
+            return NULL;
+        }
+        should_free = 1;
+    }
+    struct assist_extras* assist = (struct assist_extras*)calloc(1, sizeof(*assist));
+    assist_init(assist, sim, ephem);
+    assist->extras_should_free_ephem = should_free;
+    return assist;
+}
+
+void assist_detach(struct reb_simulation* sim, struct assist_extras* assist) {
+    if (assist->sim) {
+        sim->extras = NULL;
+        sim->extras_cleanup = NULL;
+        sim->additional_forces = NULL;
+        sim->pre_timestep_modifications = NULL;
+        ab_host_drop_batch(sim);
+    }
+    assist->sim = NULL;
+}
+
+void assist_free_pointers(struct assist_extras* assist) {
+    if (assist->sim) { assist_detach(assist->sim, assist); assist->sim = NULL; }
+    free(assist->last_state); assist->last_state = NULL;
+    free(assist->current_state); assist->current_state = NULL;
+    if (assist->ephem_cache) {
+        free(assist->ephem_cache->items);
+        free(assist->ephem_cache->t);
+        free(assist->ephem_cache);
+        assist->ephem_cache = NULL;
+    }
+    if (assist->extras_should_free_ephem && assist->ephem) { assist_ephem_free(assist->ephem); assist->ephem = NULL; }
+}
+
+void assist_free(struct assist_extras* assist) {
+    if (!assist) return;
+    assist_free_pointers(assist);
+    free(assist);
+}
+
+void assist_error(struct assist_extras* assist, const char* const msg) {
+    if (assist->sim == NULL)
+        fprintf(stderr, "(ASSIST) Error: A Simulation is no longer attached to the ASSIST extras instance. Most likely the Simulation has been freed.\n");
+    else
+        reb_simulation_error(assist->sim, msg);
+}
+
+/* ---- dense output (reference src/assist.c:635-680) ------------------------- */
+
+static void swap_particles(struct reb_simulation* sim, struct assist_extras* ax) {
+    struct reb_particle* p = sim->particles;
+    sim->particles = ax->current_state;
+    ax->current_state = p;
+}
+
+void assist_integrate_or_interpolate(struct assist_extras* ax, double t) {
+    struct reb_simulation* sim = ax->sim;
+    sim->pre_timestep_modifications = ab_host_pre_timestep_marker;
+    sim->exact_finish_time = 0;
+
+    if (ax->current_state == NULL) {
+        ax->current_state = (struct reb_particle*)malloc(sizeof(struct reb_particle) * sim->N);
+        ax->last_state = (struct reb_particle*)malloc(sizeof(struct reb_particle) * sim->N);
+        memcpy(ax->current_state, sim->particles, sizeof(struct reb_particle) * sim->N);
+        memcpy(ax->last_state, sim->particles, sizeof(struct reb_particle) * sim->N);
+    } else {
+        swap_particles(sim, ax);
+    }
+
+    const double dts = copysign(1., sim->dt_last_done);
+    if (dts * (sim->t - sim->dt_last_done) > dts * t || dts * t > dts * sim->t || sim->dt_last_done == 0.0) {
+        reb_simulation_integrate(sim, t);
+    }
+
+    const double h = 1.0 - (sim->t - t) / sim->dt_last_done;
+    if (sim->status > 0) {
+        printf("Error: simulation exited with status %d.\n", sim->status);
+    } else if (sim->t - t == 0.) {
+        memcpy(ax->current_state, sim->particles, sizeof(struct reb_particle) * sim->N);
+    } else if (h < 0.0 || h >= 1.0 || !isnormal(h)) {
+        printf("Error: cannot interpolate beyond timestep bounds (h=%e).\n", h);
+    } else if (sim->b200_batch == NULL) {
+        printf("Error: cannot interpolate before first timestep is complete (h=%e).\n", h);
+    } else {
+        ab_host_interpolate(sim, h, ax->current_state);
+    }
+    swap_particles(sim, ax);
+}
+
+int assist_interpolate_simulation(struct reb_simulation* sim1, struct reb_simulation* sim2, double h) {
+    (void)sim1; (void)sim2; (void)h;
+    fprintf(stderr, "(ASSIST) assist_interpolate_simulation needs REBOUND SimulationArchive snapshots, which are outside the scope of assist-b200.\n");
+    return 0;
+}
+
+struct reb_simulation* assist_create_interpolated_simulation(struct reb_simulationarchive* sa, double t) {
+    (void)sa; (void)t;
+    fprintf(stderr, "(ASSIST) assist_create_interpolated_simulation needs REBOUND SimulationArchive snapshots, which are outside the scope of assist-b200.\n");
+    return NULL;
+}
+
+struct reb_simulation* assist_simulation_convert_to_rebound(const struct reb_simulation* r, const struct assist_ephem* ephem, int merge_moon) {
+    (void)r; (void)ephem; (void)merge_moon;
+    fprintf(stderr, "(ASSIST) assist_simulation_convert_to_rebound needs REBOUND's N-body gravity, which is outside the scope of assist-b200.\n");
+    return NULL;
+}
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+/* host_internal.h -- helpers shared by the host-side translation units (not part of the public ABI). */
+#ifndef AB_HOST_INTERNAL_H
+#define AB_HOST_INTERNAL_H
+
+#include "assist.h"
+#include "assist_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* extra status code: no CUDA device (message index 6 in assist_error_messages) */
+#define ASSIST_ERROR_GPU 6
+
+void ab_host_drop_batch(struct reb_simulation* r);
+void ab_host_fill_options(const struct reb_simulation* r, const struct assist_extras* ax, struct assist_gpu_options* opt);
+int ab_host_interpolate(struct reb_simulation* r, double h, struct reb_particle* dest);
+/* The hook assist_integrate_or_interpolate installs (reference src/assist.c:645, 754-758).  The GPU
+ * stepper records the state at the start of every step itself, so this is only a marker. */
+void ab_host_pre_timestep_marker(struct reb_simulation* r);
+
+/* flags: 1 = resume an interrupted integrate (keep status / last_full_dt / dt_last_done),
+ *        2 = exactly one reb_simulation_step, no exit logic (shared-step batches) */
+int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int exact_finish_time, long max_steps, int flags);
+int ab_gpu_batch_update_params(assist_gpu_batch* b, const double* params);
+int ab_gpu_batch_get_last_state(assist_gpu_batch* b, double* state, double* acc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,493 @@
+/*
+ * kernels.cu -- sm_100a kernels.  Compiled twice:
+ *   -DAB_STRICT=1 --fmad=false   namespace ab_strict : no FMA contraction, reference op order
+ *   -DAB_STRICT=0 --fmad=true    namespace ab_fast   : FMA contraction allowed
+ * The launchers at the bottom are what gpu_api.cu calls.
+ *
+ * Kernels
+ *   ephem_eval_kernel        body states for a list of times (assist_get_particle / parity)
+ *   force_eval_kernel        one force evaluation per system (assist_additional_forces / parity)
+ *   pp_integrate_kernel      per-particle-dt IAS15: each thread integrates its own system
+ *   pp_dense_kernel          same, with assist_integrate_or_interpolate semantics per epoch
+ *   sh_integrate_kernel      shared-step IAS15: persistent cooperative kernel, global reductions
+ *   sh_interpolate_kernel    dense output for the shared-step batch
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#if AB_STRICT
+#define AB_NS ab_strict
+#else
+#define AB_NS ab_fast
+#endif
+
+#include "device_types.h"
+#include "ephem_device.cuh"
+#include "forces_device.cuh"
+#include "ias15_device.cuh"
+#include "launchers.h"
+
+namespace AB_NS {
+
+/* ------------------------------------------------------------------------ */
+/* ephemeris + force evaluation kernels                                     */
+/* ------------------------------------------------------------------------ */
+
+/* out[n_t][nbodies][10], status[n_t][nbodies]; one thread per (time, body). */
+__global__ void ephem_eval_kernel(const __grid_constant__ AbEphem E, const double* __restrict__ t, int n_t,
+                                  double* __restrict__ out, int* __restrict__ status) {
+    const int nb = AB_NPLANETS + E.n_ast;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)n_t * nb) return;
+    const int it = (int)(gid / nb);
+    const int body = (int)(gid % nb);
+    const double tt = t[it];
+    double GM = 0.0, x[3] = {0, 0, 0}, v[3], a[3];
+    int flag;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (body < AB_NPLANETS) {
+        flag = ab_planet<2>(E, body, tt, &GM, x, v, a);
+    } else {
+        /* asteroid: heliocentric SPK position + Sun; velocities are not provided (src/forces.c:208-224) */
+        flag = ab_asteroid(E, body - AB_NPLANETS, tt, &GM, x);
+        if (flag == AB_OK) {
+            double GMs, xs[3], vs[3], as[3];
+            flag = ab_planet<0>(E, 0, tt, &GMs, xs, vs, as);
+            x[0] += xs[0]; x[1] += xs[1]; x[2] += xs[2];
+        }
+        v[0] = v[1] = v[2] = nan; a[0] = a[1] = a[2] = nan;
+    }
+    double* o = out + gid * 10;
+    o[0] = GM; o[1] = x[0]; o[2] = x[1]; o[3] = x[2];
+    o[4] = v[0]; o[5] = v[1]; o[6] = v[2]; o[7] = a[0]; o[8] = a[1]; o[9] = a[2];
+    status[gid] = flag;
+}
+
+/* state[n][K][6], params[n][K][3] (or null), acc[n][K][3]; one thread per system. */
+__global__ void force_eval_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F,
+                                  int n, int K, const double* __restrict__ t, int t_per_system,
+                                  const double* __restrict__ state, const double* __restrict__ params,
+                                  double* __restrict__ acc, int* __restrict__ status) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    AbSys S;
+    S.nv = K - 1;
+    for (int j = 0; j < K; j++) {
+        for (int c = 0; c < 3; c++) {
+            S.x[j][c] = state[(i * K + j) * 6 + c];
+            S.v[j][c] = state[(i * K + j) * 6 + 3 + c];
+            S.prm[j][c] = params ? params[(i * K + j) * 3 + c] : 0.0;
+        }
+    }
+    AbBodies B;
+    ab_body_states(E, F, t_per_system ? t[i] : t[0], B);
+    ab_zero_acc(S);
+    if (B.status == AB_OK) ab_forces(E, F, B, S);
+    for (int j = 0; j < K; j++)
+        for (int c = 0; c < 3; c++) acc[(i * K + j) * 3 + c] = S.a[j][c];
+    status[i] = B.status;
+}
+
+/* ------------------------------------------------------------------------ */
+/* per-particle-dt IAS15                                                    */
+/* ------------------------------------------------------------------------ */
+
+struct PPState {
+    double t, dt, dt_last;
+    int status;
+    unsigned long long steps, rejected, iters, evals;
+};
+
+/* One reb_simulation_step of system i: force evaluation at the current state, then
+ * IAS15 attempts until one is accepted.  Each thread owns its times, so the body
+ * table is evaluated per thread. */
+__device__ void pp_step(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, long long i, PPState& P) {
+    AbSys S;
+    AbBodies B;
+    ab_load_sys(Bt, i, S);
+    const int nv = S.nv;
+    ab_body_states(E, F, P.t, B);
+    if (B.status != AB_OK) { P.status = 1; Bt.status[i] = 1000 + B.status; return; }
+    ab_zero_acc(S);
+    ab_forces(E, F, B, S);
+    P.evals++;
+    ab_store_a0(Bt, i, S);
+
+    while (true) {   /* attempts */
+        ab_attempt_begin(Bt, i, nv);
+        const double t_beginning = P.t;
+        double pc_err = 1e300, pc_err_last = 2;
+        int iterations = 0;
+        while (true) {
+            if (pc_err < 1e-16) break;
+            if (iterations > 2 && pc_err_last <= pc_err) break;
+            if (iterations >= 12) break;
+            pc_err_last = pc_err;
+            pc_err = 0;
+            iterations++;
+            P.iters++;
+            double maxak = 0.0, maxb6 = 0.0;
+            for (int nn = 1; nn < 8; nn++) {
+                const double ts = t_beginning + P.dt * c_h[nn];
+                ab_predict(Bt, i, nn, P.dt, S);
+                ab_body_states(E, F, ts, B);
+                if (B.status != AB_OK) { P.status = 1; Bt.status[i] = 1000 + B.status; return; }
+                ab_zero_acc(S);
+                ab_forces(E, F, B, S);
+                P.evals++;
+                ab_update_gb(Bt, i, nn, S, maxak, maxb6);
+            }
+            pc_err = maxb6 / maxak;
+        }
+        const double dt_done = P.dt;
+        if (Bt.epsilon > 0) {
+            double maxa = 0.0, maxj = 0.0;
+            ab_dt_monitor(Bt, i, S, P.dt, maxa, maxj);
+            double dt_new = ab_dt_new(Bt.epsilon, Bt.min_dt, maxa, maxj, dt_done);
+            if (fabs(dt_new / dt_done) < 0.25) {
+                ab_restore(Bt, i, nv);
+                P.dt = dt_new;
+                if (P.dt_last != 0.) ab_predict_next(Bt, i, nv, P.dt / P.dt_last, Bt.er, Bt.br);
+                P.rejected++;
+                continue;
+            }
+            if (fabs(dt_new / dt_done) > 1.0) {
+                if (dt_new / dt_done > 1. / 0.25) dt_new = dt_done / 0.25;
+            }
+            P.dt = dt_new;
+        }
+        ab_advance(Bt, i, nv, dt_done);
+        P.t += dt_done;
+        P.dt_last = dt_done;
+        ab_predict_next(Bt, i, nv, P.dt / dt_done, Bt.e, Bt.b);
+        P.steps++;
+        return;
+    }
+}
+
+/* reb_simulation_integrate(tmax) for one system. */
+__device__ void pp_integrate_to(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, long long i, PPState& P,
+                                double tmax, int exact_finish_time) {
+    if (tmax != P.t) P.dt = copysign(P.dt, (tmax > P.t) ? 1.0 : -1.0);
+    double last_full_dt = P.dt;
+    P.dt_last = 0.;
+    P.status = -1;
+    while (ab_check_exit(P.t, P.dt, P.dt_last, P.status, tmax, exact_finish_time, last_full_dt) < 0) {
+        pp_step(E, F, Bt, i, P);
+    }
+    if (exact_finish_time == 1) P.dt = last_full_dt;
+}
+
+__device__ __forceinline__ void pp_load(const AbBatch& Bt, long long i, PPState& P) {
+    P.t = Bt.t[i]; P.dt = Bt.dt[i]; P.dt_last = Bt.dt_last[i]; P.status = Bt.status[i];
+    P.steps = Bt.steps[i]; P.rejected = Bt.rejected[i]; P.iters = Bt.iters[i]; P.evals = Bt.evals[i];
+}
+__device__ __forceinline__ void pp_store(const AbBatch& Bt, long long i, const PPState& P) {
+    Bt.t[i] = P.t; Bt.dt[i] = P.dt; Bt.dt_last[i] = P.dt_last;
+    if (Bt.status[i] < 1000) Bt.status[i] = P.status;
+    Bt.steps[i] = P.steps; Bt.rejected[i] = P.rejected; Bt.iters[i] = P.iters; Bt.evals[i] = P.evals;
+}
+
+__global__ void __launch_bounds__(AB_BLOCK)
+pp_integrate_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F,
+                    const __grid_constant__ AbBatch Bt, double tmax, int exact_finish_time) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Bt.n) return;
+    PPState P;
+    pp_load(Bt, i, P);
+    if (P.status >= 1000) return;
+    pp_integrate_to(E, F, Bt, i, P, tmax, exact_finish_time);
+    pp_store(Bt, i, P);
+}
+
+/* assist_integrate_or_interpolate(times[e]) for e = 0..n_times-1 per system
+ * (reference src/assist.c:642-680); out[n_times][n][K][6]. */
+__global__ void __launch_bounds__(AB_BLOCK)
+pp_dense_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F,
+                const __grid_constant__ AbBatch Bt, const double* __restrict__ times, int n_times,
+                double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n = Bt.n;
+    if (i >= n) return;
+    PPState P;
+    pp_load(Bt, i, P);
+    if (P.status >= 1000) return;
+    const int K = Bt.K;
+    const int nv = Bt.nv[i];
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int e = 0; e < n_times; e++) {
+        const double t = times[e];
+        double* o = out + ((long long)e * n + i) * K * 6;
+        const double dts = copysign(1., P.dt_last);
+        if (dts * (P.t - P.dt_last) > dts * t || dts * t > dts * P.t || P.dt_last == 0.0) {
+            pp_integrate_to(E, F, Bt, i, P, t, 0);
+        }
+        const double h = 1.0 - (P.t - t) / P.dt_last;
+        if (P.status > 0) {
+            for (int q = 0; q < 6 * (1 + nv); q++) o[q] = nan;
+        } else if (P.t - t == 0.) {
+            for (int j = 0; j <= nv; j++)
+                for (int c = 0; c < 3; c++) {
+                    o[6 * j + c] = AB1(Bt.pos, 3 * j + c);
+                    o[6 * j + 3 + c] = AB1(Bt.vel, 3 * j + c);
+                }
+        } else if (h < 0.0 || h >= 1.0 || !ab_isnormal(h)) {
+            for (int q = 0; q < 6 * (1 + nv); q++) o[q] = nan;
+        } else {
+            ab_interpolate(Bt, i, nv, P.dt_last, h, o);
+        }
+    }
+    pp_store(Bt, i, P);
+}
+
+/* ------------------------------------------------------------------------ */
+/* shared-step IAS15 (REBOUND semantics for one N-particle simulation)      */
+/* ------------------------------------------------------------------------ */
+
+__device__ __forceinline__ void grid_barrier(AbShared* sh, unsigned long long& phase) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        phase++;
+        __threadfence();
+        atomicAdd(&sh->barrier, 1ULL);
+        const unsigned long long target = phase * gridDim.x;
+        while (*((volatile unsigned long long*)&sh->barrier) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+/* Global max of two non-negative doubles over the whole grid. */
+__device__ void grid_max2(AbShared* sh, unsigned long long& phase, unsigned long long& rcount, double& a, double& b) {
+    __shared__ double s_a[AB_BLOCK / 32], s_b[AB_BLOCK / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmax(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_a[w] = a; s_b[w] = b; }
+    __syncthreads();
+    const int slot = (int)(rcount & 7ULL);
+    if (threadIdx.x == 0) {
+        double ma = s_a[0], mb = s_b[0];
+        for (int q = 1; q < AB_BLOCK / 32; q++) { ma = fmax(ma, s_a[q]); mb = fmax(mb, s_b[q]); }
+        atomicMax(&sh->red[slot][0], (unsigned long long)__double_as_longlong(ma));
+        atomicMax(&sh->red[slot][1], (unsigned long long)__double_as_longlong(mb));
+    }
+    grid_barrier(sh, phase);
+    a = __longlong_as_double((long long)*((volatile unsigned long long*)&sh->red[slot][0]));
+    b = __longlong_as_double((long long)*((volatile unsigned long long*)&sh->red[slot][1]));
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int z = (slot + 4) & 7;
+        sh->red[z][0] = 0ULL; sh->red[z][1] = 0ULL;
+    }
+    rcount++;
+}
+
+/* Body tables for the start of the step (slot 0) or its 7 nodes (slots 1..7),
+ * evaluated once per CTA; the threads of the CTA split the slots. */
+__device__ void sh_fill_bodies(const AbEphem& E, const AbForceOpts& F, AbBodies* sb, double t0, double dt, int first, int last) {
+    for (int s = first + (int)threadIdx.x; s <= last; s += blockDim.x) {
+        const double ts = (s == 0) ? t0 : (t0 + dt * c_h[s]);
+        ab_body_states(E, F, ts, sb[s]);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(AB_BLOCK)
+sh_integrate_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F,
+                    const __grid_constant__ AbBatch Bt, double tmax, int exact_finish_time, long long max_steps, int flags) {
+    __shared__ AbBodies sb[8];
+    AbShared* sh = Bt.sh;
+    const long long n = Bt.n;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long phase = 0, rcount = 0;
+
+    /* every thread carries the same copy of the control variables */
+    double t = sh->t, dt = sh->dt, dt_last = sh->dt_last;
+    int status = -1;
+    unsigned long long steps = 0, rejected = 0, iters = 0, evals = 0;
+    int err = 0;
+    double last_full_dt = dt;
+    const bool raw_step = (flags & 2) != 0;     /* exactly one reb_simulation_step, no exit logic */
+    if (flags & 1) {
+        /* resume an integrate() that was paused after max_steps */
+        status = sh->status;
+        last_full_dt = sh->last_full_dt;
+    } else if (!raw_step) {
+        if (tmax != t) dt = copysign(dt, (tmax > t) ? 1.0 : -1.0);
+        last_full_dt = dt;
+        dt_last = 0.;
+    }
+
+    while (raw_step || ab_check_exit(t, dt, dt_last, status, tmax, exact_finish_time, last_full_dt) < 0) {
+        /* ---- reb_simulation_step ---- */
+        sh_fill_bodies(E, F, sb, t, dt, 0, 0);
+        if (sb[0].status != AB_OK) { err = sb[0].status; status = 1; break; }
+        for (long long i = gtid; i < n; i += stride) {
+            AbSys S;
+            ab_load_sys(Bt, i, S);
+            ab_zero_acc(S);
+            ab_forces(E, F, sb[0], S);
+            ab_store_a0(Bt, i, S);
+        }
+        evals++;
+        bool accepted = false;
+        while (!accepted) {
+            sh_fill_bodies(E, F, sb, t, dt, 1, 7);
+            for (int s = 1; s < 8; s++) if (sb[s].status != AB_OK) err = sb[s].status;
+            if (err) break;
+            for (long long i = gtid; i < n; i += stride) ab_attempt_begin(Bt, i, Bt.nv[i]);
+            double pc_err = 1e300, pc_err_last = 2;
+            int iterations = 0;
+            double dmaxa = 0.0, dmaxj = 0.0;
+            while (true) {
+                if (pc_err < 1e-16) break;
+                if (iterations > 2 && pc_err_last <= pc_err) break;
+                if (iterations >= 12) break;
+                pc_err_last = pc_err;
+                pc_err = 0;
+                iterations++;
+                iters++;
+                double maxak = 0.0, maxb6 = 0.0;
+                dmaxa = 0.0; dmaxj = 0.0;
+                for (long long i = gtid; i < n; i += stride) {
+                    AbSys S;
+                    S.nv = Bt.nv[i];
+                    for (int j = 0; j <= S.nv; j++)
+                        for (int c = 0; c < 3; c++) S.prm[j][c] = Bt.has_params ? AB1(Bt.prm, 3 * j + c) : 0.0;
+                    for (int nn = 1; nn < 8; nn++) {
+                        ab_predict(Bt, i, nn, dt, S);
+                        ab_zero_acc(S);
+                        ab_forces(E, F, sb[nn], S);
+                        ab_update_gb(Bt, i, nn, S, maxak, maxb6);
+                    }
+                    /* step-size monitor uses the node-7 prediction of this (possibly last) sweep */
+                    ab_dt_monitor(Bt, i, S, dt, dmaxa, dmaxj);
+                }
+                evals += 7;
+                grid_max2(sh, phase, rcount, maxak, maxb6);
+                pc_err = maxb6 / maxak;
+            }
+            const double dt_done = dt;
+            if (Bt.epsilon > 0) {
+                grid_max2(sh, phase, rcount, dmaxa, dmaxj);
+                double dt_new = ab_dt_new(Bt.epsilon, Bt.min_dt, dmaxa, dmaxj, dt_done);
+                if (fabs(dt_new / dt_done) < 0.25) {
+                    dt = dt_new;
+                    for (long long i = gtid; i < n; i += stride) {
+                        const int nv = Bt.nv[i];
+                        ab_restore(Bt, i, nv);
+                        if (dt_last != 0.) ab_predict_next(Bt, i, nv, dt / dt_last, Bt.er, Bt.br);
+                    }
+                    rejected++;
+                    continue;
+                }
+                if (fabs(dt_new / dt_done) > 1.0) {
+                    if (dt_new / dt_done > 1. / 0.25) dt_new = dt_done / 0.25;
+                }
+                dt = dt_new;
+            }
+            for (long long i = gtid; i < n; i += stride) {
+                const int nv = Bt.nv[i];
+                ab_advance(Bt, i, nv, dt_done);
+                ab_predict_next(Bt, i, nv, dt / dt_done, Bt.e, Bt.b);
+            }
+            t += dt_done;
+            dt_last = dt_done;
+            accepted = true;
+        }
+        if (err) { status = 1; break; }
+        steps++;
+        if (raw_step) break;
+        if (max_steps > 0 && (long long)steps >= max_steps) break;
+    }
+    if (!raw_step && exact_finish_time == 1 && !err && status >= 0) dt = last_full_dt;
+
+    if (gtid == 0) {
+        sh->t = t; sh->dt = dt; sh->dt_last = dt_last; sh->last_full_dt = last_full_dt;
+        sh->status = status;
+        sh->steps += steps; sh->rejected += rejected; sh->iters += iters; sh->evals += evals;
+        sh->err_status = err;
+    }
+}
+
+/* out[n][K][6] */
+__global__ void sh_interpolate_kernel(const __grid_constant__ AbBatch Bt, double dt_last_done, double h, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Bt.n) return;
+    ab_interpolate(Bt, i, Bt.nv[i], dt_last_done, h, out + i * Bt.K * 6);
+}
+
+}  // namespace AB_NS
+
+/* ------------------------------------------------------------------------ */
+/* launchers                                                                */
+/* ------------------------------------------------------------------------ */
+#if AB_STRICT
+#define AB_LAUNCH(name) name##_strict
+#else
+#define AB_LAUNCH(name) name##_fast
+#endif
+
+using namespace AB_NS;
+
+cudaError_t AB_LAUNCH(ab_upload_constants)() {
+    cudaError_t e;
+    if ((e = cudaMemcpyToSymbol(c_h, AB_H, sizeof(AB_H))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_rr, AB_RR, sizeof(AB_RR))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_c, AB_C, sizeof(AB_C))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_d, AB_D, sizeof(AB_D))) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+cudaError_t AB_LAUNCH(ab_launch_ephem_eval)(const AbEphem& E, const double* t, int n_t, double* out, int* status, cudaStream_t st) {
+    const long long total = (long long)n_t * (AB_NPLANETS + E.n_ast);
+    const int grid = (int)((total + AB_BLOCK - 1) / AB_BLOCK);
+    ephem_eval_kernel<<<grid, AB_BLOCK, 0, st>>>(E, t, n_t, out, status);
+    return cudaGetLastError();
+}
+
+cudaError_t AB_LAUNCH(ab_launch_force_eval)(const AbEphem& E, const AbForceOpts& F, int n, int K, const double* t, int t_per_system,
+                                            const double* state, const double* params, double* acc, int* status, cudaStream_t st) {
+    const int grid = (n + AB_BLOCK - 1) / AB_BLOCK;
+    force_eval_kernel<<<grid, AB_BLOCK, 0, st>>>(E, F, n, K, t, t_per_system, state, params, acc, status);
+    return cudaGetLastError();
+}
+
+cudaError_t AB_LAUNCH(ab_launch_pp_integrate)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, double tmax, int exact, cudaStream_t st) {
+    const int grid = (Bt.n + AB_BLOCK - 1) / AB_BLOCK;
+    pp_integrate_kernel<<<grid, AB_BLOCK, 0, st>>>(E, F, Bt, tmax, exact);
+    return cudaGetLastError();
+}
+
+cudaError_t AB_LAUNCH(ab_launch_pp_dense)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const double* times, int n_times, double* out, cudaStream_t st) {
+    const int grid = (Bt.n + AB_BLOCK - 1) / AB_BLOCK;
+    pp_dense_kernel<<<grid, AB_BLOCK, 0, st>>>(E, F, Bt, times, n_times, out);
+    return cudaGetLastError();
+}
+
+cudaError_t AB_LAUNCH(ab_launch_sh_integrate)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, double tmax, int exact, long long max_steps, int flags, cudaStream_t st) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sh_integrate_kernel, AB_BLOCK, 0)) != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    int grid = (Bt.n + AB_BLOCK - 1) / AB_BLOCK;
+    const int max_grid = sms * per_sm;      /* every CTA must be resident: the kernel spins on a grid barrier */
+    if (grid > max_grid) grid = max_grid;
+    if (grid < 1) grid = 1;
+    long long ms = max_steps;
+    void* args[] = {(void*)&E, (void*)&F, (void*)&Bt, (void*)&tmax, (void*)&exact, (void*)&ms, (void*)&flags};
+    return cudaLaunchCooperativeKernel((void*)sh_integrate_kernel, dim3(grid), dim3(AB_BLOCK), args, 0, st);
+}
+
+cudaError_t AB_LAUNCH(ab_launch_sh_interpolate)(const AbBatch& Bt, double dt_last_done, double h, double* out, cudaStream_t st) {
+    const int grid = (Bt.n + AB_BLOCK - 1) / AB_BLOCK;
+    sh_interpolate_kernel<<<grid, AB_BLOCK, 0, st>>>(Bt, dt_last_done, h, out);
+    return cudaGetLastError();
+}

@@ -1,0 +1,28 @@
+/* launchers.h -- host-callable kernel launchers, one set per math variant. */
+#ifndef AB_LAUNCHERS_H
+#define AB_LAUNCHERS_H
+
+#include <cuda_runtime.h>
+#include "device_types.h"
+
+#define AB_DECLARE_LAUNCHERS(sfx)                                                                                   \
+    cudaError_t ab_upload_constants_##sfx();                                                                        \
+    cudaError_t ab_launch_ephem_eval_##sfx(const AbEphem& E, const double* t, int n_t, double* out, int* status,   \
+                                           cudaStream_t st);                                                        \
+    cudaError_t ab_launch_force_eval_##sfx(const AbEphem& E, const AbForceOpts& F, int n, int K, const double* t,  \
+                                           int t_per_system, const double* state, const double* params,            \
+                                           double* acc, int* status, cudaStream_t st);                             \
+    cudaError_t ab_launch_pp_integrate_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt,            \
+                                             double tmax, int exact, cudaStream_t st);                             \
+    cudaError_t ab_launch_pp_dense_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt,                \
+                                         const double* times, int n_times, double* out, cudaStream_t st);          \
+    cudaError_t ab_launch_sh_integrate_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt,            \
+                                             double tmax, int exact, long long max_steps, int flags,               \
+                                             cudaStream_t st);                                                     \
+    cudaError_t ab_launch_sh_interpolate_##sfx(const AbBatch& Bt, double dt_last_done, double h, double* out,      \
+                                               cudaStream_t st);
+
+AB_DECLARE_LAUNCHERS(strict)
+AB_DECLARE_LAUNCHERS(fast)
+
+#endif

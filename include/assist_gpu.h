@@ -1,0 +1,136 @@
+/*
+ * assist_gpu.h -- thin C-ABI over the sm_100a kernels (plain pointers and sizes only).
+ *
+ * These are the entry points a binding (ctypes, cgo, JNI ...) uses to drive the GPU
+ * path directly with whole populations, without going through per-particle
+ * `struct reb_particle` marshalling.  The ASSIST host API in assist.h
+ * (assist_attach / reb_simulation_integrate / assist_integrate_or_interpolate ...)
+ * is implemented on top of exactly these calls.
+ *
+ * What each call replaces in the reference:
+ *   assist_gpu_ephem_eval            assist_all_ephem            src/forces.c:175-263
+ *                                    assist_spk_target_pos       src/spk.c:492-547
+ *                                    assist_spk_calc             src/spk.c:405-481
+ *                                    assist_ascii_calc           src/ascii_ephem.c:275-384
+ *   assist_gpu_eval_forces           assist_additional_forces    src/forces.c:49-173 (+ :266-1983)
+ *   assist_gpu_batch_integrate       reb_simulation_integrate -> reb_integrator_ias15_step
+ *                                    (REBOUND; call site src/assist.c:663)
+ *   assist_gpu_batch_integrate_or_interpolate
+ *                                    assist_integrate_or_interpolate + assist_interpolate
+ *                                    src/assist.c:642-680, 556-597
+ *
+ * Layouts.  A "system" is one real particle followed by its n_var first-order
+ * variational particles (K = 1 + n_var bodies).  Host buffers are plain row-major
+ * doubles:
+ *   state  [n_sys][K][6]   x y z vx vy vz          (AU, AU/day; barycentric)
+ *   params [n_sys][K][3]   A1 A2 A3 for the real particle; dA1 dA2 dA3 for each
+ *                          variational particle (reference src/forces.c:839-841, 1030-1032)
+ *   acc    [n_sys][K][3]   ax ay az
+ * All functions return 0 on success, an ASSIST_STATUS (>0) for ephemeris errors, or
+ * a negative ASSIST_GPU_ERR_* code; assist_gpu_last_error() gives the message.
+ */
+#ifndef _ASSIST_B200_GPU_H
+#define _ASSIST_B200_GPU_H
+
+#include "assist.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum ASSIST_GPU_ERR {
+    ASSIST_GPU_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: there is NO CPU fallback */
+    ASSIST_GPU_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+    ASSIST_GPU_ERR_ARG = -3,         /* bad argument */
+    ASSIST_GPU_ERR_UNSUPPORTED = -4, /* configuration outside what the kernels implement */
+};
+
+enum ASSIST_GPU_MODE {
+    ASSIST_GPU_SHARED_STEP = 0,      /* one global dt, global convergence: REBOUND semantics for an N-particle sim */
+    ASSIST_GPU_PER_PARTICLE = 1,     /* every system steps on its own dt: one-simulation-per-particle semantics */
+};
+
+enum ASSIST_GPU_MATH {
+    ASSIST_GPU_MATH_STRICT = 0,      /* no FMA contraction, reference operation order: bit-faithful to the C build */
+    ASSIST_GPU_MATH_FAST = 1,        /* FMA contraction allowed (results agree to rounding, not bitwise) */
+};
+
+#define ASSIST_GPU_MAX_NVAR 6        /* variational particles per real particle the kernels are built for */
+
+struct assist_gpu_options {
+    int forces;                      /* ASSIST_FORCES bitmask, reference src/assist.h:76-87 */
+    int gr_eih_sources;              /* 1..11, reference src/assist.c:415 */
+    int geocentric;                  /* reference src/forces.c:57, 72-87 */
+    int math;                        /* ASSIST_GPU_MATH */
+    double alpha, nk, nm, nn, r0;    /* Marsden g(r), reference src/assist.c:434-438 */
+    double epsilon;                  /* IAS15 accuracy parameter (REBOUND default 1e-9) */
+    double min_dt;                   /* IAS15 minimum |dt| (REBOUND default 0) */
+};
+
+struct assist_gpu_stats {
+    unsigned long long steps;        /* accepted IAS15 steps, summed over systems (per-particle) or global steps (shared) */
+    unsigned long long steps_rejected;
+    unsigned long long pc_iterations;/* predictor-corrector sweeps */
+    unsigned long long force_evals;  /* force evaluations x systems */
+    unsigned long long kernel_launches;
+    double last_kernel_ms;           /* CUDA-event time of the last integrate call, on the launch stream */
+};
+
+typedef struct assist_gpu_batch assist_gpu_batch;
+
+/* ---- device management --------------------------------------------------- */
+int assist_gpu_device_count(void);
+int assist_gpu_set_device(int device);
+const char* assist_gpu_last_error(void);
+void assist_gpu_default_options(struct assist_gpu_options* opt);
+
+/* ---- ephemeris ------------------------------------------------------------ */
+/* Upload (once per device) the coefficient tables of an initialised ephemeris. */
+int assist_gpu_ephem_upload(const struct assist_ephem* ephem);
+/* Number of bodies: 11 + asteroids in the small-body file. */
+int assist_gpu_ephem_nbodies(const struct assist_ephem* ephem);
+/* out[n_t][nbodies][10] = GM x y z vx vy vz ax ay az; status[n_t][nbodies] = ASSIST_STATUS. */
+int assist_gpu_ephem_eval(const struct assist_ephem* ephem, int math, const double* t, int n_t,
+                          double* out, int* status);
+
+/* ---- one force evaluation (term-by-term parity hook) ---------------------- */
+/* t has n_sys entries when t_per_system != 0, else one entry shared by all systems. */
+int assist_gpu_eval_forces(const struct assist_ephem* ephem, const struct assist_gpu_options* opt,
+                           int n_sys, int n_var, const double* t, int t_per_system,
+                           const double* state, const double* params, double* acc, int* status);
+
+/* ---- batched IAS15 -------------------------------------------------------- */
+assist_gpu_batch* assist_gpu_batch_create(const struct assist_ephem* ephem, int n_sys, int n_var, int mode);
+void assist_gpu_batch_free(assist_gpu_batch* b);
+int assist_gpu_batch_set_options(assist_gpu_batch* b, const struct assist_gpu_options* opt);
+/* (Re)start: copies state/params from HOST memory, sets t, dt for every system, clears IAS15 history.
+ * nvar_per_system may be NULL (every system uses n_var). params may be NULL (no non-gravitational forces). */
+int assist_gpu_batch_set_state(assist_gpu_batch* b, double t0, double dt0, const double* state,
+                               const double* params, const int* nvar_per_system);
+/* Replace positions/velocities only, keeping the IAS15 history (what REBOUND does when a user
+ * edits sim->particles between two integrate calls). */
+int assist_gpu_batch_update_particles(assist_gpu_batch* b, const double* state);
+/* Keep a device-resident copy of the current state as "initial conditions"; restart from it
+ * without any host traffic (used to time the device path with inputs already in HBM). */
+int assist_gpu_batch_snapshot(assist_gpu_batch* b);
+int assist_gpu_batch_restore(assist_gpu_batch* b);
+/* reb_simulation_integrate(tmax) for every system. exact_finish_time as in REBOUND. max_steps<=0: no limit
+ * (shared-step mode only: stop after that many accepted steps). */
+int assist_gpu_batch_integrate(assist_gpu_batch* b, double t_end, int exact_finish_time, long max_steps);
+/* assist_integrate_or_interpolate for a sorted list of epochs; out[n_times][n_sys][K][6]. */
+int assist_gpu_batch_integrate_or_interpolate(assist_gpu_batch* b, const double* times, int n_times, double* out);
+/* state/acc[n_sys][K][6|3]; t, dt, dt_last_done: n_sys entries in per-particle mode, 1 in shared-step mode.
+ * Any pointer may be NULL. */
+int assist_gpu_batch_get_state(assist_gpu_batch* b, double* state, double* acc, double* t, double* dt,
+                               double* dt_last_done, int* status);
+int assist_gpu_batch_set_time(assist_gpu_batch* b, double t, double dt);
+/* Dense output inside the last completed step (shared-step mode): out[n_sys][K][6]. */
+int assist_gpu_batch_interpolate(assist_gpu_batch* b, double h, double* out);
+int assist_gpu_batch_get_stats(assist_gpu_batch* b, struct assist_gpu_stats* stats);
+/* Peak FP64 FMA rate of the current device measured with a register-resident DFMA loop (TFLOP/s). */
+double assist_gpu_measure_fp64_peak(int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

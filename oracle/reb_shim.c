@@ -601,6 +601,8 @@ static int ias15_step(struct reb_simulation* r){
             for (int k = 0; k < N; ++k){
                 particles[k].x = x0[3*k+0]; particles[k].y = x0[3*k+1]; particles[k].z = x0[3*k+2];
                 particles[k].vx = v0[3*k+0]; particles[k].vy = v0[3*k+1]; particles[k].vz = v0[3*k+2];
+                /* the retry starts from the accelerations at the beginning of the step */
+                particles[k].ax = a0[3*k+0]; particles[k].ay = a0[3*k+1]; particles[k].az = a0[3*k+2];
             }
             r->dt = dt_new;
             if (r->dt_last_done != 0.){
