@@ -79,5 +79,10 @@ def load():
     lib.assist_gpu_batch_get_stats.argtypes = [c_void_p, P(GpuStats)]
     lib.assist_gpu_measure_fp64_peak.restype = c_double
     lib.assist_gpu_measure_fp64_peak.argtypes = [c_int]
+    lib.assist_gpu_batch_get_counters.argtypes = [c_void_p, P(c_ulonglong), P(c_ulonglong), P(c_ulonglong), P(c_ulonglong)]
+    lib.assist_gpu_host_alloc.restype = c_void_p
+    lib.assist_gpu_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.assist_gpu_host_free.restype = None
+    lib.assist_gpu_host_free.argtypes = [c_void_p]
     _lib = lib
     return lib

@@ -185,6 +185,14 @@ class Batch:
         return dict(steps=s.steps, steps_rejected=s.steps_rejected, pc_iterations=s.pc_iterations,
                     force_evals=s.force_evals, kernel_launches=s.kernel_launches, last_kernel_ms=s.last_kernel_ms)
 
+    def counters(self):
+        """Per-system counters (per-particle batches): dict of uint64 arrays of length n."""
+        out = {k: np.zeros(self.n, dtype=np.uint64) for k in ("steps", "rejected", "iters", "evals")}
+        u64 = POINTER(ctypes.c_ulonglong)
+        rc = self.lib.assist_gpu_batch_get_counters(self.ptr, *[out[k].ctypes.data_as(u64) for k in ("steps", "rejected", "iters", "evals")])
+        _check(self.lib, rc, "get_counters")
+        return out
+
     def close(self):
         if self.ptr:
             self.lib.assist_gpu_batch_free(self.ptr)

@@ -7,20 +7,37 @@
 #define AB_NPLANETS 11
 #define AB_MAX_AST 16            /* asteroids held in the per-time body table */
 #define AB_MAX_BODIES (AB_NPLANETS + AB_MAX_AST)
-#define AB_MAXSEG 8              /* SPK segments per target */
+#define AB_MAXSEG 4              /* SPK segments per target */
 #define AB_MAX_PTGT 16           /* SPK targets in a planets kernel */
 #define AB_NVMAX 6               /* variational particles per system */
 #define AB_KMAX (1 + AB_NVMAX)
 #define AB_BLOCK 128
+#ifndef AB_PP_MIN_BLOCKS
+#define AB_PP_MIN_BLOCKS 3      /* resident CTAs per SM the per-particle kernels are register-budgeted for */
+#endif
 
 #define AB_SRC_SPK 0
 #define AB_SRC_ASCII 2
 
+/* One type-2 SPK segment: what the reference re-reads from the segment trailer on every
+ * evaluation (reference src/spk.c:503-517), hoisted to upload time with the same operations. */
+struct AbSpkSeg {
+    int one;             /* 1-based word address of the first record */
+    int R, P, nrec;      /* record size, coefficients per component, record count */
+    double jul_init;     /* 2451545.0 + INIT / 86400.0 */
+    double intlen_d;     /* INTLEN / 86400.0 */
+    double intlen_rd;    /* 1 / intlen_d */
+    double radius_d;     /* RADIUS / 86400.0 (all records of a type-2 segment share RADIUS) */
+    double radius_rd;    /* 1 / radius_d */
+    double radius_inv;   /* 1.0 / RADIUS */
+    int uniform;         /* 1 if every record really has the same RADIUS, else evaluate from the record */
+    int pad;
+};
+
 struct AbSpkTarget {
-    double beg, end, res, mass;
+    double beg, end, res, res_rd, mass;
     int code, cen, nseg, pad;
-    int one[AB_MAXSEG];
-    int two[AB_MAXSEG];
+    AbSpkSeg seg[AB_MAXSEG];
 };
 
 /* Everything a kernel needs to evaluate the ephemeris; passed by value (__grid_constant__). */
@@ -30,12 +47,17 @@ struct AbEphem {
     int n_ast;
     /* constants, reference src/assist.h:140-154 */
     double AU, EMRAT, J2E, J3E, J4E, J2SUN, Re_eq, Rs_eq, c_squared, over_c_squared;
+    /* unit-conversion divisors and their reciprocals (position, velocity, acceleration) */
+    double u_d[3], u_rd[3];
     /* DE binary planets */
     const double* ascii_img;
     double a_beg, a_end, a_inc, a_cau, a_cem;
     long long a_rec_words;
     long long a_nrec;
+    double a_inc_rd;
     int a_off[15], a_ncf[15], a_niv[15];
+    double a_c[15];              /* (niv*2)/inc/86400.0 per column (reference src/ascii_ephem.c:37) */
+    double a_f_earth, a_f_moon;  /* -1/(1+EMRAT), EMRAT/(1+EMRAT) (reference src/ascii_ephem.c:319-341) */
     double a_mass[AB_NPLANETS];
     /* SPK planets */
     const double* spkp_img;
@@ -43,6 +65,7 @@ struct AbEphem {
     int emb_index;
     int n_ptgt;
     AbSpkTarget p_tgt[AB_MAX_PTGT];
+    double gm[AB_MAX_BODIES];      /* GM of every body, as assist_all_ephem reports it */
     /* SPK asteroids: descriptors live in global memory */
     const double* spka_img;
     const AbSpkTarget* a_tgt;
@@ -74,6 +97,18 @@ struct AbBodies {
     int status;
 };
 
+/* Body table of one Gauss-Radau node in the common configuration (one EIH source, barycentric):
+ * same member names as AbBodies so the force routines take either. */
+struct AbNode {
+    const double* gm;               /* -> AbEphem::gm */
+    double pos[AB_MAX_BODIES][3];
+    double vel[1][3];               /* Sun */
+    double earth_acc[3];            /* unused (barycentric) */
+    double eih_term1[1];
+    double eih_ar[1][3];
+    double eih_av[1][3];
+};
+
 /* Device-side state of a batch.  Arrays are structure-of-arrays over systems:
  * element (component k, system i) lives at [k * n + i]; the seven-deep IAS15
  * tables at [(j * C + k) * n + i], C = 3 * K. */
@@ -89,7 +124,7 @@ struct AbBatch {
     double *prm;                             /* [C][n] A1 A2 A3 / dA1 dA2 dA3 */
     int *nv;                                 /* [n] variational particles in use */
     /* per-particle mode */
-    double *t, *dt, *dt_last;                /* [n] */
+    double *t, *dt, *dt_last, *last_full_dt; /* [n] */
     int *status;                             /* [n] REB_STATUS */
     /* counters: [n] in per-particle mode, [1] in shared-step mode */
     unsigned long long *steps, *rejected, *iters, *evals;

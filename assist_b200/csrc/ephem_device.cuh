@@ -10,14 +10,19 @@
  *   SPK asteroids    reference src/spk.c:405-481 (position only, literal 149597870.7)
  *   DE binary        reference src/ascii_ephem.c:27-65 (work), :275-384 (calc)
  *   body dispatch    reference src/forces.c:175-263 (assist_all_ephem: asteroid + Sun shift)
- * The T/S/U recurrences are carried in registers instead of 32-entry arrays, and
- * velocity / acceleration sums are only formed when a caller needs them (they do
- * not feed the position sums, so skipping them changes no result).
+ * Differences in HOW (not in what is computed):
+ *   - the T/S/U recurrences are carried in registers instead of 32-entry arrays, and
+ *     velocity / acceleration sums are only formed when a caller needs them;
+ *   - the per-segment trailer values (INIT, INTLEN, RSIZE, N) and every invariant
+ *     divisor are prepared once at upload time, so an evaluation needs one dependent
+ *     load (the record's MID) before the coefficient stream, and no true division
+ *     (fp_device.cuh: exact quotients from precomputed reciprocals).
  */
 #ifndef AB_EPHEM_DEVICE_CUH
 #define AB_EPHEM_DEVICE_CUH
 
 #include "device_types.h"
+#include "fp_device.cuh"
 
 #define AB_OK 0
 #define AB_ERR_EPHEM_FILE 1
@@ -28,9 +33,9 @@
 
 namespace AB_NS {
 
-__device__ __forceinline__ double ab_jul(double eph) { return 2451545.0 + eph / 86400.0; }
+__device__ __forceinline__ double ab_jul(double eph) { return 2451545.0 + AB_DIVK(eph, 86400.0); }
 
-/* Chebyshev sums for one record: NCM components, P coefficients each, argument z,
+/* Chebyshev sums for one record: 3 components, P coefficients each, argument z,
  * derivative scale c.  LEVEL 0: position, 1: +velocity, 2: +acceleration. */
 template <int LEVEL>
 __device__ __forceinline__ void ab_cheb3(const double* __restrict__ cf, int P, double z, double c,
@@ -38,7 +43,6 @@ __device__ __forceinline__ void ab_cheb3(const double* __restrict__ cf, int P, d
     double u0 = 0.0, u1 = 0.0, u2 = 0.0;
     double v0 = 0.0, v1 = 0.0, v2 = 0.0;
     double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-    /* T[p-1], T[p-2] etc. */
     double Tm1 = 0.0, Tm2 = 0.0, Sm1 = 0.0, Sm2 = 0.0, Um1 = 0.0, Um2 = 0.0;
     const double* __restrict__ cx = cf;
     const double* __restrict__ cy = cf + P;
@@ -68,20 +72,24 @@ __device__ __forceinline__ void ab_cheb3(const double* __restrict__ cf, int P, d
 /* Locate the type-2 record of `tg` that holds jd_ref + t (reference src/spk.c:501-517). */
 __device__ __forceinline__ const double* ab_spk_record(const double* __restrict__ img, const AbSpkTarget& tg,
                                                        double jd_ref, double t, int* P, double* z, double* c) {
-    int n = (int)((jd_ref + t - tg.beg) / tg.res);
+    int n = (int)ab_divc(jd_ref + t - tg.beg, tg.res, tg.res_rd);
     if (n > tg.nseg - 1) n = tg.nseg - 1;       /* jd == end: the reference indexes one past; stay in the last segment */
     if (n < 0) n = 0;
-    const double* val = img + tg.two[n] - 1;
-    const int R = (int)__ldg(val - 1);
-    *P = (R - 2) / 3;
-    int b = (int)(((jd_ref - ab_jul(__ldg(val - 3))) + t) / (__ldg(val - 2) / 86400.0));
-    const int nrec = (int)__ldg(val);
-    if (b > nrec - 1) b = nrec - 1;
+    const AbSpkSeg& sg = tg.seg[n];
+    *P = sg.P;
+    int b = (int)ab_divc((jd_ref - sg.jul_init) + t, sg.intlen_d, sg.intlen_rd);
+    if (b > sg.nrec - 1) b = sg.nrec - 1;
     if (b < 0) b = 0;
-    const double* rec = img + (tg.one[n] - 1) + (long long)b * R;
-    const double radius = __ldg(rec + 1);
-    *z = ((jd_ref - ab_jul(__ldg(rec))) + t) / (radius / 86400.0);
-    *c = 1.0 / radius;
+    const double* rec = img + (sg.one - 1) + (long long)b * sg.R;
+    const double mid = __ldg(rec);
+    if (sg.uniform) {
+        *z = ab_divc((jd_ref - ab_jul(mid)) + t, sg.radius_d, sg.radius_rd);
+        *c = sg.radius_inv;
+    } else {
+        const double radius = __ldg(rec + 1);
+        *z = ((jd_ref - ab_jul(mid)) + t) / AB_DIVK(radius, 86400.0);
+        *c = 1.0 / radius;
+    }
     return rec + 2;
 }
 
@@ -96,7 +104,6 @@ __device__ __forceinline__ void ab_spk_target_pos(const double* __restrict__ img
 /* Planet (body < 11) from an SPK kernel, reference src/spk.c:550-610, 632-693. */
 template <int LEVEL>
 __device__ int ab_spk_planet(const AbEphem& E, int body, double t, double* GM, double x[3], double v[3], double a[3]) {
-    const int naif[AB_NPLANETS] = {10, 1, 2, 399, 301, 4, 5, 6, 7, 8, 9};
     const double jd_ref = E.jd_ref;
     double u[3], uv[3] = {0, 0, 0}, uw[3] = {0, 0, 0};
     const int idx = E.p_index[body];
@@ -105,8 +112,7 @@ __device__ int ab_spk_planet(const AbEphem& E, int body, double t, double* GM, d
         if (jd_ref + t < tg.beg || jd_ref + t > tg.end) return AB_ERR_COVERAGE;
         *GM = tg.mass;
         ab_spk_target_pos<LEVEL>(E.spkp_img, tg, jd_ref, t, u, uv, uw);
-        const int code = naif[body];
-        if (code == 301 || code == 399) {
+        if (body == 3 || body == 4) {           /* NAIF 399 / 301 are given relative to the EMB */
             if (E.emb_index < 0) return AB_ERR_NEPHEM;
             double e[3], ev[3] = {0, 0, 0}, ew[3] = {0, 0, 0};
             ab_spk_target_pos<LEVEL>(E.spkp_img, E.p_tgt[E.emb_index], jd_ref, t, e, ev, ew);
@@ -125,26 +131,24 @@ __device__ int ab_spk_planet(const AbEphem& E, int body, double t, double* GM, d
     } else {
         return AB_ERR_NEPHEM;
     }
-    const double au = E.AU;
-    const double seconds_per_day = 86400.;
+    /* km, km/s, km/s^2 -> AU, AU/day, AU/day^2: divisors au, au/86400, au/86400^2 */
     for (int i = 0; i < 3; i++) {
-        x[i] = u[i] / au;
-        if (LEVEL >= 1) v[i] = uv[i] / (au / seconds_per_day);
-        if (LEVEL >= 2) a[i] = uw[i] / (au / (seconds_per_day * seconds_per_day));
+        x[i] = ab_divc(u[i], E.u_d[0], E.u_rd[0]);
+        if (LEVEL >= 1) v[i] = ab_divc(uv[i], E.u_d[1], E.u_rd[1]);
+        if (LEVEL >= 2) a[i] = ab_divc(uw[i], E.u_d[2], E.u_rd[2]);
     }
     return AB_OK;
 }
 
 /* One column of a DE-binary record, reference src/ascii_ephem.c:27-65. */
 template <int LEVEL>
-__device__ __forceinline__ void ab_ascii_work(const double* __restrict__ Pcol, int ncm, int ncf, int niv,
-                                              double t0, double t1, double u[3], double v[3], double w[3]) {
+__device__ __forceinline__ void ab_ascii_work(const double* __restrict__ Pcol, int ncf, int niv, double c,
+                                              double t0, double u[3], double v[3], double w[3]) {
     const double tt = t0 * (double)niv;
     const int b = (int)tt;
     const double frac = tt - (double)b;            /* == fmod(tt, 1.0) for tt >= 0, exactly */
     const double z = 2.0 * frac - 1.0;
-    const double c = (double)(niv * 2) / t1 / 86400.0;
-    ab_cheb3<LEVEL>(Pcol + ncf * (b * ncm), ncf, z, c, u, v, w);
+    ab_cheb3<LEVEL>(Pcol + ncf * (b * 3), ncf, z, c, u, v, w);
 }
 
 /* Planet (body < 11) from a DE-binary file, reference src/ascii_ephem.c:275-384. */
@@ -153,25 +157,24 @@ __device__ int ab_ascii_planet(const AbEphem& E, int body, double t, double* GM,
     const double jd_ref = E.jd_ref;
     *GM = E.a_mass[body];
     if (jd_ref + t < E.a_beg || jd_ref + t > E.a_end) return AB_ERR_COVERAGE;
-    long long blk = (long long)(unsigned int)((jd_ref + t - E.a_beg) / E.a_inc);
+    long long blk = (long long)(unsigned int)ab_divc(jd_ref + t - E.a_beg, E.a_inc, E.a_inc_rd);
     if (blk > E.a_nrec - 1) blk = E.a_nrec - 1;    /* jd == end */
     const double* z = E.ascii_img + (blk + 2) * E.a_rec_words;
-    const double tr = ((jd_ref - E.a_beg - (double)blk * E.a_inc) + t) / E.a_inc;
+    const double tr = ab_divc((jd_ref - E.a_beg - (double)blk * E.a_inc) + t, E.a_inc, E.a_inc_rd);
     /* ASCII_* column of each ASSIST body */
-    const int col_of[AB_NPLANETS] = {10, 0, 1, 2, 2, 3, 4, 5, 6, 7, 8};
+    const int col = (body == 0) ? 10 : (body <= 3 ? body - 1 : (body == 4 ? 2 : body - 2));
     double u[3], uv[3] = {0, 0, 0}, uw[3] = {0, 0, 0};
-    const int col = col_of[body];
-    ab_ascii_work<LEVEL>(z + E.a_off[col], 3, E.a_ncf[col], E.a_niv[col], tr, E.a_inc, u, uv, uw);
+    ab_ascii_work<LEVEL>(z + E.a_off[col], E.a_ncf[col], E.a_niv[col], E.a_c[col], tr, u, uv, uw);
     if (body == 3 || body == 4) {
         double l[3], lv[3] = {0, 0, 0}, lw[3] = {0, 0, 0};
-        ab_ascii_work<LEVEL>(z + E.a_off[9], 3, E.a_ncf[9], E.a_niv[9], tr, E.a_inc, l, lv, lw);
-        const double f = (body == 3) ? (-1.0 / (1.0 + E.a_cem)) : (E.a_cem / (1.0 + E.a_cem));
+        ab_ascii_work<LEVEL>(z + E.a_off[9], E.a_ncf[9], E.a_niv[9], E.a_c[9], tr, l, lv, lw);
+        const double f = (body == 3) ? E.a_f_earth : E.a_f_moon;
         for (int i = 0; i < 3; i++) { u[i] += l[i] * f; uv[i] += lv[i] * f; uw[i] += lw[i] * f; }
     }
     for (int i = 0; i < 3; i++) {
-        x[i] = u[i] / E.a_cau;
-        if (LEVEL >= 1) v[i] = uv[i] / (E.a_cau / 86400.);
-        if (LEVEL >= 2) a[i] = uw[i] / (E.a_cau / (86400. * 86400.));
+        x[i] = ab_divc(u[i], E.u_d[0], E.u_rd[0]);
+        if (LEVEL >= 1) v[i] = ab_divc(uv[i], E.u_d[1], E.u_rd[1]);
+        if (LEVEL >= 2) a[i] = ab_divc(uw[i], E.u_d[2], E.u_rd[2]);
     }
     return AB_OK;
 }
@@ -183,7 +186,7 @@ __device__ __forceinline__ int ab_planet(const AbEphem& E, int body, double t, d
 }
 
 /* Heliocentric asteroid position in AU, reference src/spk.c:405-481. */
-__device__ int ab_asteroid(const AbEphem& E, int m, double t, double* GM, double x[3]) {
+__device__ __forceinline__ int ab_asteroid(const AbEphem& E, int m, double t, double* GM, double x[3]) {
     if (E.spka_img == nullptr) return AB_ERR_AST_FILE;
     if (m < 0 || m >= E.n_ast) return AB_ERR_NAST;
     const AbSpkTarget& tg = E.a_tgt[m];
@@ -194,7 +197,7 @@ __device__ int ab_asteroid(const AbEphem& E, int m, double t, double* GM, double
     const double* cf = ab_spk_record(E.spka_img, tg, jd_ref, t, &P, &z, &c);
     double u[3], dv[3], dw[3];
     ab_cheb3<0>(cf, P, z, c, u, dv, dw);
-    x[0] = u[0] / 149597870.7; x[1] = u[1] / 149597870.7; x[2] = u[2] / 149597870.7;
+    x[0] = AB_DIVK(u[0], 149597870.7); x[1] = AB_DIVK(u[1], 149597870.7); x[2] = AB_DIVK(u[2], 149597870.7);
     return AB_OK;
 }
 
@@ -220,17 +223,15 @@ __device__ void ab_body_states(const AbEphem& E, const AbForceOpts& F, double t,
         }
         if (flag != AB_OK && status == AB_OK) status = flag;
     }
-    const bool need_ast = (F.forces & 0x04) != 0 || true;   /* variational direct term ignores the mask (src/forces.c:359) */
-    if (need_ast) {
-        for (int m = 0; m < E.n_ast; m++) {
-            double x[3];
-            int flag = ab_asteroid(E, m, t, &B.gm[AB_NPLANETS + m], x);
-            if (flag != AB_OK && status == AB_OK) status = flag;
-            /* heliocentric -> barycentric, reference src/forces.c:213-219 */
-            B.pos[AB_NPLANETS + m][0] = x[0] + B.pos[0][0];
-            B.pos[AB_NPLANETS + m][1] = x[1] + B.pos[0][1];
-            B.pos[AB_NPLANETS + m][2] = x[2] + B.pos[0][2];
-        }
+    /* asteroids are always needed: the variational direct term ignores the force mask (src/forces.c:359) */
+    for (int m = 0; m < E.n_ast; m++) {
+        double x[3];
+        int flag = ab_asteroid(E, m, t, &B.gm[AB_NPLANETS + m], x);
+        if (flag != AB_OK && status == AB_OK) status = flag;
+        /* heliocentric -> barycentric, reference src/forces.c:213-219 */
+        B.pos[AB_NPLANETS + m][0] = x[0] + B.pos[0][0];
+        B.pos[AB_NPLANETS + m][1] = x[1] + B.pos[0][1];
+        B.pos[AB_NPLANETS + m][2] = x[2] + B.pos[0][2];
     }
     if (need_eih && status == AB_OK) {
         for (int j = 0; j < ns; j++) {
@@ -248,9 +249,10 @@ __device__ void ab_body_states(const AbEphem& E, const AbForceOpts& F, double t,
                 term1 += GMk / _rjk;
                 const double fac = GMk / (rjk2 * _rjk);
                 arx -= fac * dxjk; ary -= fac * dyjk; arz -= fac * dzjk;
-                avx -= GMk * dxjk / (_rjk * _rjk * _rjk);
-                avy -= GMk * dyjk / (_rjk * _rjk * _rjk);
-                avz -= GMk * dzjk / (_rjk * _rjk * _rjk);
+                const AbDivisor r3(_rjk * _rjk * _rjk);
+                avx -= r3(GMk * dxjk);
+                avy -= r3(GMk * dyjk);
+                avz -= r3(GMk * dzjk);
             }
             B.eih_term1[j] = term1;
             B.eih_ar[j][0] = arx; B.eih_ar[j][1] = ary; B.eih_ar[j][2] = arz;
@@ -258,6 +260,187 @@ __device__ void ab_body_states(const AbEphem& E, const AbForceOpts& F, double t,
         }
     }
     B.status = status;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Node tables: the body states of one IAS15 step, evaluated once.
+ *
+ * Within a step the force routine is called at the same 8 times (start of step + 7 Gauss-Radau
+ * nodes) in every predictor-corrector sweep.  The reference memoises them in a 7-slot cache
+ * keyed on the time (src/forces.c:180-197, 227-261); here a thread fills its 8 node tables in
+ * one go.  The Chebyshev recurrences of the 8 times are independent, so they are run side by
+ * side (8-way instruction-level parallelism on a latency-bound FP64 chain), and a coefficient
+ * record shared by several nodes is read through L1 once.  Values are the same as those of the
+ * one-time routines above: each sum sees the same operands in the same order.
+ * ------------------------------------------------------------------------------------------ */
+#define AB_NT 8
+
+/* position sums (km) of one series at AB_NT arguments; cf[k] points at the X coefficients */
+__device__ __forceinline__ void ab_cheb_pos_multi(const double* const* cf, int P, const double* z, double (*u)[3]) {
+    double T1[AB_NT], T2[AB_NT], a0[AB_NT], a1[AB_NT], a2[AB_NT];
+#pragma unroll
+    for (int k = 0; k < AB_NT; k++) {
+        /* p = 0 (T = 1) and p = 1 (T = z) */
+        const double* c = cf[k];
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        s0 += __ldg(c) * 1.0; s1 += __ldg(c + P) * 1.0; s2 += __ldg(c + 2 * P) * 1.0;
+        s0 += __ldg(c + 1) * z[k]; s1 += __ldg(c + P + 1) * z[k]; s2 += __ldg(c + 2 * P + 1) * z[k];
+        a0[k] = s0; a1[k] = s1; a2[k] = s2;
+        T2[k] = 1.0; T1[k] = z[k];
+    }
+    for (int p = 2; p < P; p++) {
+#pragma unroll
+        for (int k = 0; k < AB_NT; k++) {
+            const double T = 2.0 * z[k] * T1[k] - T2[k];
+            const double* c = cf[k] + p;
+            a0[k] += __ldg(c) * T; a1[k] += __ldg(c + P) * T; a2[k] += __ldg(c + 2 * P) * T;
+            T2[k] = T1[k]; T1[k] = T;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < AB_NT; k++) { u[k][0] = a0[k]; u[k][1] = a1[k]; u[k][2] = a2[k]; }
+}
+
+/* one SPK target at AB_NT times (positions in km) */
+__device__ __noinline__ void ab_spk_pos_multi(const double* __restrict__ img, const AbSpkTarget& tg, double jd_ref,
+                                              const double* t, double (*u)[3]) {
+    const double* cf[AB_NT];
+    double z[AB_NT];
+    int P0 = 0;
+    bool same = true;
+#pragma unroll
+    for (int k = 0; k < AB_NT; k++) {
+        int P; double c;
+        cf[k] = ab_spk_record(img, tg, jd_ref, t[k], &P, &z[k], &c);
+        if (k == 0) P0 = P; else same = same && (P == P0);
+    }
+    if (same) {
+        ab_cheb_pos_multi(cf, P0, z, u);
+    } else {   /* nodes in segments with different record sizes: one at a time */
+        for (int k = 0; k < AB_NT; k++) {
+            double dv[3], dw[3];
+            ab_spk_target_pos<0>(img, tg, jd_ref, t[k], u[k], dv, dw);
+        }
+    }
+}
+
+/* one DE-binary column at AB_NT times (positions in km) */
+__device__ __noinline__ void ab_ascii_pos_multi(const AbEphem& E, int col, const double* t, double (*u)[3]) {
+    const double* cf[AB_NT];
+    double z[AB_NT];
+    const int ncf = E.a_ncf[col], niv = E.a_niv[col];
+#pragma unroll
+    for (int k = 0; k < AB_NT; k++) {
+        long long blk = (long long)(unsigned int)ab_divc(E.jd_ref + t[k] - E.a_beg, E.a_inc, E.a_inc_rd);
+        if (blk > E.a_nrec - 1) blk = E.a_nrec - 1;
+        const double* rec = E.ascii_img + (blk + 2) * E.a_rec_words;
+        const double tr = ab_divc((E.jd_ref - E.a_beg - (double)blk * E.a_inc) + t[k], E.a_inc, E.a_inc_rd);
+        const double tt = tr * (double)niv;
+        const int b = (int)tt;
+        z[k] = 2.0 * (tt - (double)b) - 1.0;
+        cf[k] = rec + E.a_off[col] + ncf * (b * 3);
+    }
+    ab_cheb_pos_multi(cf, ncf, z, u);
+}
+
+/* Fill the AB_NT node tables of a step for the common configuration: one EIH source (the Sun),
+ * barycentric.  Returns an ASSIST status. */
+__device__ __noinline__ int ab_fill_nodes(const AbEphem& E, const AbForceOpts& F, const double* t, AbNode* nodes) {
+    const double jd_ref = E.jd_ref;
+    /* coverage (reference src/spk.c:563-565, 416-418; src/ascii_ephem.c:294-295) */
+    for (int k = 0; k < AB_NT; k++) {
+        const double jd = jd_ref + t[k];
+        if (E.planets_source == AB_SRC_ASCII) {
+            if (jd < E.a_beg || jd > E.a_end) return AB_ERR_COVERAGE;
+        } else {
+            for (int b = 0; b < AB_NPLANETS; b++) {
+                const int idx = E.p_index[b];
+                if (idx < 0) { if (b != 3) return AB_ERR_NEPHEM; continue; }
+                if (jd < E.p_tgt[idx].beg || jd > E.p_tgt[idx].end) return AB_ERR_COVERAGE;
+            }
+        }
+        for (int m = 0; m < E.n_ast; m++)
+            if (jd < E.a_tgt[m].beg || jd > E.a_tgt[m].end) return AB_ERR_COVERAGE;
+    }
+    double u[AB_NT][3];
+    if (E.planets_source == AB_SRC_ASCII) {
+        double emb[AB_NT][3], lun[AB_NT][3];
+        ab_ascii_pos_multi(E, 2, t, emb);
+        ab_ascii_pos_multi(E, 9, t, lun);
+        for (int b = 0; b < AB_NPLANETS; b++) {
+            if (b == 3 || b == 4) {
+                const double f = (b == 3) ? E.a_f_earth : E.a_f_moon;
+                for (int k = 0; k < AB_NT; k++)
+                    for (int c = 0; c < 3; c++) nodes[k].pos[b][c] = ab_divc(emb[k][c] + lun[k][c] * f, E.u_d[0], E.u_rd[0]);
+            } else {
+                const int col = (b == 0) ? 10 : (b <= 2 ? b - 1 : b - 2);
+                ab_ascii_pos_multi(E, col, t, u);
+                for (int k = 0; k < AB_NT; k++)
+                    for (int c = 0; c < 3; c++) nodes[k].pos[b][c] = ab_divc(u[k][c], E.u_d[0], E.u_rd[0]);
+            }
+        }
+    } else {
+        double emb[AB_NT][3];
+        bool have_emb = false;
+        for (int b = 0; b < AB_NPLANETS; b++) {
+            const int idx = E.p_index[b];
+            if (idx < 0 || ((b == 3 || b == 4) && E.emb_index < 0)) {
+                /* rare layouts (no 399 target): the one-time routine knows the fallbacks */
+                for (int k = 0; k < AB_NT; k++) {
+                    double GM, v[3], a[3];
+                    const int flag = ab_spk_planet<0>(E, b, t[k], &GM, nodes[k].pos[b], v, a);
+                    if (flag != AB_OK) return flag;
+                }
+                continue;
+            }
+            ab_spk_pos_multi(E.spkp_img, E.p_tgt[idx], jd_ref, t, u);
+            if (b == 3 || b == 4) {
+                if (!have_emb) { ab_spk_pos_multi(E.spkp_img, E.p_tgt[E.emb_index], jd_ref, t, emb); have_emb = true; }
+                for (int k = 0; k < AB_NT; k++)
+                    for (int c = 0; c < 3; c++) u[k][c] += emb[k][c];
+            }
+            for (int k = 0; k < AB_NT; k++)
+                for (int c = 0; c < 3; c++) nodes[k].pos[b][c] = ab_divc(u[k][c], E.u_d[0], E.u_rd[0]);
+        }
+    }
+    /* Sun velocity (non-grav, simple GR and the EIH source) */
+    for (int k = 0; k < AB_NT; k++) {
+        double GM, x[3], a[3];
+        const int flag = ab_planet<1>(E, 0, t[k], &GM, x, nodes[k].vel[0], a);
+        if (flag != AB_OK) return flag;
+    }
+    /* asteroids: heliocentric SPK position / 149597870.7 + Sun */
+    for (int m = 0; m < E.n_ast; m++) {
+        ab_spk_pos_multi(E.spka_img, E.a_tgt[m], jd_ref, t, u);
+        for (int k = 0; k < AB_NT; k++)
+            for (int c = 0; c < 3; c++)
+                nodes[k].pos[AB_NPLANETS + m][c] = AB_DIVK(u[k][c], 149597870.7) + nodes[k].pos[0][c];
+    }
+    /* particle-independent EIH sums for source 0 */
+    const bool need_eih = (F.forces & 0x40) != 0;
+    for (int k = 0; k < AB_NT; k++) {
+        AbNode& N = nodes[k];
+        N.gm = E.gm;
+        if (!need_eih) continue;
+        double term1 = 0.0, arx = 0.0, ary = 0.0, arz = 0.0, avx = 0.0, avy = 0.0, avz = 0.0;
+        for (int q = 1; q < AB_NPLANETS; q++) {
+            const double GMk = E.gm[q];
+            const double dxjk = N.pos[0][0] - N.pos[q][0];
+            const double dyjk = N.pos[0][1] - N.pos[q][1];
+            const double dzjk = N.pos[0][2] - N.pos[q][2];
+            const double rjk2 = dxjk * dxjk + dyjk * dyjk + dzjk * dzjk;
+            const double _rjk = sqrt(rjk2);
+            term1 += GMk / _rjk;
+            const double fac = GMk / (rjk2 * _rjk);
+            arx -= fac * dxjk; ary -= fac * dyjk; arz -= fac * dzjk;
+            const AbDivisor r3(_rjk * _rjk * _rjk);
+            avx -= r3(GMk * dxjk); avy -= r3(GMk * dyjk); avz -= r3(GMk * dzjk);
+        }
+        N.eih_term1[0] = term1;
+        N.eih_ar[0][0] = arx; N.eih_ar[0][1] = ary; N.eih_ar[0][2] = arz;
+        N.eih_av[0][0] = avx; N.eih_av[0][1] = avy; N.eih_av[0][2] = avz;
+    }
+    return AB_OK;
 }
 
 }  // namespace AB_NS

@@ -24,21 +24,26 @@
 #define AB_FORCES_DEVICE_CUH
 
 #include "device_types.h"
+#include "fp_device.cuh"
 
 namespace AB_NS {
 
 /* Positions/velocities/accelerations of one system in registers/local memory. */
-struct AbSys {
-    double x[AB_KMAX][3];
-    double v[AB_KMAX][3];
-    double a[AB_KMAX][3];
-    double prm[AB_KMAX][3];
-    int nv;
+template <int KM>
+struct AbSysT {
+    double x[KM][3];
+    double v[KM][3];
+    double a[KM][3];
+    double prm[KM][3];
+    int nv_;
+    /* KM == 1 means "no variational particles": the count is a compile-time zero so that
+     * every array index is static and the state lives in registers */
+    __device__ __forceinline__ int nv() const { return (KM == 1) ? 0 : nv_; }
 };
 
 /* 3x6 Jacobian applied to every variational particle of the system. */
 #define AB_APPLY_J36(S, dxdx, dxdy, dxdz, dxdvx, dxdvy, dxdvz, dydx, dydy, dydz, dydvx, dydvy, dydvz, dzdx, dzdy, dzdz, dzdvx, dzdvy, dzdvz) \
-    for (int vv = 1; vv <= (S).nv; vv++) {                                                             \
+    for (int vv = 1; vv <= (S).nv(); vv++) {                                                             \
         const double ddx = (S).x[vv][0], ddy = (S).x[vv][1], ddz = (S).x[vv][2];                     \
         const double ddvx = (S).v[vv][0], ddvy = (S).v[vv][1], ddvz = (S).v[vv][2];                  \
         const double dax = ddx * dxdx + ddy * dxdy + ddz * dxdz + ddvx * dxdvx + ddvy * dxdvy + ddvz * dxdvz; \
@@ -48,7 +53,8 @@ struct AbSys {
     }
 
 /* ---- Marsden non-gravitational term, reference src/forces.c:774-1057 ------- */
-__device__ void ab_force_nongrav(const AbForceOpts& F, const AbBodies& B, AbSys& S,
+template <int KM, class BT>
+__device__ void ab_force_nongrav(const AbForceOpts& F, const BT& B, AbSysT<KM>& S,
                                  double xo, double yo, double zo, double vxo, double vyo, double vzo) {
     if (!F.has_params) return;
     const double A1 = S.prm[0][0], A2 = S.prm[0][1], A3 = S.prm[0][2];
@@ -84,7 +90,7 @@ __device__ void ab_force_nongrav(const AbForceOpts& F, const AbBodies& B, AbSys&
     S.a[0][1] += A1 * g * dy / r + A2 * g * ty / _t + A3 * g * hy / h;
     S.a[0][2] += A1 * g * dz / r + A2 * g * tz / _t + A3 * g * hz / h;
 
-    if (S.nv == 0) return;
+    if (S.nv() == 0) return;
 
     const double r3 = r * r * r;
     const double v2 = dvx * dvx + dvy * dvy + dvz * dvz;
@@ -147,7 +153,7 @@ __device__ void ab_force_nongrav(const AbForceOpts& F, const AbBodies& B, AbSys&
     const double dydvz = A1 * (0.) + A2 * g * (-dz * dy / _t - tzt3 * r2 * ty) + A3 * g * (-dx / h - hyh3 * (r2 * dvz - dz * rdotv));
     const double dzdvy = A1 * (0.) + A2 * g * (-dy * dz / _t - tyt3 * r2 * tz) + A3 * g * (dx / h - hzh3 * (r2 * dvy - dy * rdotv));
 
-    for (int vv = 1; vv <= S.nv; vv++) {
+    for (int vv = 1; vv <= S.nv(); vv++) {
         const double ddx = S.x[vv][0], ddy = S.x[vv][1], ddz = S.x[vv][2];
         const double ddvx = S.v[vv][0], ddvy = S.v[vv][1], ddvz = S.v[vv][2];
         const double dA1 = S.prm[vv][0], dA2 = S.prm[vv][1], dA3 = S.prm[vv][2];
@@ -162,7 +168,8 @@ __device__ void ab_force_nongrav(const AbForceOpts& F, const AbBodies& B, AbSys&
 }
 
 /* ---- Earth J2/J3/J4, reference src/forces.c:435-642 ------------------------ */
-__device__ void ab_force_earth_harmonics(const AbEphem& E, const AbForceOpts& F, const AbBodies& B, AbSys& S,
+template <int KM, class BT>
+__device__ void ab_force_earth_harmonics(const AbEphem& E, const AbForceOpts& F, const BT& B, AbSysT<KM>& S,
                                          double xo, double yo, double zo) {
     const double GMearth = B.gm[3];
     const double xr = B.pos[3][0], yr = B.pos[3][1], zr = B.pos[3][2];
@@ -174,28 +181,29 @@ __device__ void ab_force_earth_harmonics(const AbEphem& E, const AbForceOpts& F,
     double dz = S.x[0][2] + (zo - zr);
     const double r2 = dx * dx + dy * dy + dz * dz;
     const double r = sqrt(r2);
+    const AbDivisor dr2(r2), dr(r);   /* every /r2 and /r below is an exact quotient from one reciprocal */
 
     double dxp = -dx * sina + dy * cosa;
     double dyp = -dx * cosa * sind - dy * sina * sind + dz * cosd;
     double dzp = dx * cosa * cosd + dy * sina * cosd + dz * sind;
     dx = dxp; dy = dyp; dz = dzp;
 
-    const double costheta2 = dz * dz / r2;
-    const double J2e_prefac = 3. * J2e * Re_eq * Re_eq / r2 / r2 / r / 2.;
+    const double costheta2 = dr2(dz * dz);
+    const double J2e_prefac = dr(dr2(dr2(3. * J2e * Re_eq * Re_eq))) / 2.;
     const double J2e_fac = 5. * costheta2 - 1.;
 
     double resx = GMearth * J2e_prefac * J2e_fac * dx;
     double resy = GMearth * J2e_prefac * J2e_fac * dy;
     double resz = GMearth * J2e_prefac * (J2e_fac - 2.) * dz;
 
-    const double J3e_prefac = 5. * J3e * Re_eq * Re_eq * Re_eq / r2 / r2 / r / 2.;
+    const double J3e_prefac = dr(dr2(dr2(5. * J3e * Re_eq * Re_eq * Re_eq))) / 2.;
     const double J3e_fac = 3. - 7. * costheta2;
 
-    resx += -GMearth * J3e_prefac * (1. / r2) * J3e_fac * dx * dz;
-    resy += -GMearth * J3e_prefac * (1. / r2) * J3e_fac * dy * dz;
+    resx += -GMearth * J3e_prefac * dr2(1.) * J3e_fac * dx * dz;
+    resy += -GMearth * J3e_prefac * dr2(1.) * J3e_fac * dy * dz;
     resz += -GMearth * J3e_prefac * (6. * costheta2 - 7. * costheta2 * costheta2 - 0.6);
 
-    const double J4e_prefac = 5. * J4e * Re_eq * Re_eq * Re_eq * Re_eq / r2 / r2 / r2 / r / 8.;
+    const double J4e_prefac = dr(dr2(dr2(dr2(5. * J4e * Re_eq * Re_eq * Re_eq * Re_eq)))) / 8.;
     const double J4e_fac = 63. * costheta2 * costheta2 - 42. * costheta2 + 3.;
 
     resx += GMearth * J4e_prefac * J4e_fac * dx;
@@ -208,27 +216,27 @@ __device__ void ab_force_earth_harmonics(const AbEphem& E, const AbForceOpts& F,
 
     S.a[0][0] += resxp; S.a[0][1] += resyp; S.a[0][2] += reszp;
 
-    if (S.nv == 0) return;
+    if (S.nv() == 0) return;
 
     const double J2e_fac2 = 7. * costheta2 - 1.;
     const double J2e_fac3 = 35. * costheta2 * costheta2 - 30. * costheta2 + 3.;
 
-    const double dxdx = GMearth * J2e_prefac * (J2e_fac - 5. * J2e_fac2 * dx * dx / r2);
-    const double dydy = GMearth * J2e_prefac * (J2e_fac - 5. * J2e_fac2 * dy * dy / r2);
+    const double dxdx = GMearth * J2e_prefac * (J2e_fac - dr2(5. * J2e_fac2 * dx * dx));
+    const double dydy = GMearth * J2e_prefac * (J2e_fac - dr2(5. * J2e_fac2 * dy * dy));
     const double dzdz = GMearth * J2e_prefac * (-1.) * J2e_fac3;
-    const double dxdy = GMearth * J2e_prefac * (-5.) * J2e_fac2 * dx * dy / r2;
-    const double dydz = GMearth * J2e_prefac * (-5.) * (J2e_fac2 - 2.) * dy * dz / r2;
-    const double dxdz = GMearth * J2e_prefac * (-5.) * (J2e_fac2 - 2.) * dx * dz / r2;
+    const double dxdy = dr2(GMearth * J2e_prefac * (-5.) * J2e_fac2 * dx * dy);
+    const double dydz = dr2(GMearth * J2e_prefac * (-5.) * (J2e_fac2 - 2.) * dy * dz);
+    const double dxdz = dr2(GMearth * J2e_prefac * (-5.) * (J2e_fac2 - 2.) * dx * dz);
 
-    const double costheta = dz / r;
-    const double J3e_fac2 = 21 * (-3. * costheta2 + 1.) / r2;
-    const double J3e_fac3 = 3 * (-21. * costheta2 * costheta2 + 14. * costheta2 - 1.) / r2;
-    const double J3e_fac4 = (-63. * costheta2 * costheta2 + 70. * costheta2 - 15.) * costheta / r;
+    const double costheta = dr(dz);
+    const double J3e_fac2 = dr2(21 * (-3. * costheta2 + 1.));
+    const double J3e_fac3 = dr2(3 * (-21. * costheta2 * costheta2 + 14. * costheta2 - 1.));
+    const double J3e_fac4 = dr((-63. * costheta2 * costheta2 + 70. * costheta2 - 15.) * costheta);
 
-    const double dxdxJ3 = GMearth * J3e_prefac * costheta * (J3e_fac2 * dx * dx - J3e_fac) / r;
-    const double dydyJ3 = GMearth * J3e_prefac * costheta * (J3e_fac2 * dy * dy - J3e_fac) / r;
+    const double dxdxJ3 = dr(GMearth * J3e_prefac * costheta * (J3e_fac2 * dx * dx - J3e_fac));
+    const double dydyJ3 = dr(GMearth * J3e_prefac * costheta * (J3e_fac2 * dy * dy - J3e_fac));
     const double dzdzJ3 = GMearth * J3e_prefac * J3e_fac4;
-    const double dxdyJ3 = GMearth * J3e_prefac * J3e_fac2 * costheta * dx * dy / r;
+    const double dxdyJ3 = dr(GMearth * J3e_prefac * J3e_fac2 * costheta * dx * dy);
     const double dydzJ3 = GMearth * J3e_prefac * J3e_fac3 * dy;
     const double dxdzJ3 = GMearth * J3e_prefac * J3e_fac3 * dx;
 
@@ -236,14 +244,14 @@ __device__ void ab_force_earth_harmonics(const AbEphem& E, const AbForceOpts& F,
     const double J4e_fac3 = 33. * costheta2 * costheta2 - 30. * costheta2 + 5.;
     const double J4e_fac4 = 231. * costheta2 * costheta2 * costheta2 - 315. * costheta2 * costheta2 + 105. * costheta2 - 5.;
 
-    const double dxdxJ4 = GMearth * J4e_prefac * (J4e_fac - 21. * J4e_fac2 * dx * dx / r2);
-    const double dydyJ4 = GMearth * J4e_prefac * (J4e_fac - 21. * J4e_fac2 * dy * dy / r2);
+    const double dxdxJ4 = GMearth * J4e_prefac * (J4e_fac - dr2(21. * J4e_fac2 * dx * dx));
+    const double dydyJ4 = GMearth * J4e_prefac * (J4e_fac - dr2(21. * J4e_fac2 * dy * dy));
     const double dzdzJ4 = GMearth * J4e_prefac * (-3.) * J4e_fac4;
-    const double dxdyJ4 = GMearth * J4e_prefac * (-21.) * J4e_fac2 * dx * dy / r2;
-    const double dydzJ4 = GMearth * J4e_prefac * (-21.) * J4e_fac3 * dy * dz / r2;
-    const double dxdzJ4 = GMearth * J4e_prefac * (-21.) * J4e_fac3 * dx * dz / r2;
+    const double dxdyJ4 = dr2(GMearth * J4e_prefac * (-21.) * J4e_fac2 * dx * dy);
+    const double dydzJ4 = dr2(GMearth * J4e_prefac * (-21.) * J4e_fac3 * dy * dz);
+    const double dxdzJ4 = dr2(GMearth * J4e_prefac * (-21.) * J4e_fac3 * dx * dz);
 
-    for (int vv = 1; vv <= S.nv; vv++) {
+    for (int vv = 1; vv <= S.nv(); vv++) {
         const double ddx = S.x[vv][0], ddy = S.x[vv][1], ddz = S.x[vv][2];
         double ddxp = -ddx * sina + ddy * cosa;
         double ddyp = -ddx * cosa * sind - ddy * sina * sind + ddz * cosd;
@@ -270,7 +278,8 @@ __device__ void ab_force_earth_harmonics(const AbEphem& E, const AbForceOpts& F,
 }
 
 /* ---- solar J2, reference src/forces.c:644-772 ------------------------------ */
-__device__ void ab_force_solar_j2(const AbEphem& E, const AbForceOpts& F, const AbBodies& B, AbSys& S,
+template <int KM, class BT>
+__device__ void ab_force_solar_j2(const AbEphem& E, const AbForceOpts& F, const BT& B, AbSysT<KM>& S,
                                   double xo, double yo, double zo) {
     const double GMsun = B.gm[0];
     const double xr = B.pos[0][0], yr = B.pos[0][1], zr = B.pos[0][2];
@@ -282,14 +291,15 @@ __device__ void ab_force_solar_j2(const AbEphem& E, const AbForceOpts& F, const 
     double dz = S.x[0][2] + (zo - zr);
     const double r2 = dx * dx + dy * dy + dz * dz;
     const double r = sqrt(r2);
+    const AbDivisor dr2(r2), dr(r);
 
     double dxp = -dx * sina + dy * cosa;
     double dyp = -dx * cosa * sind - dy * sina * sind + dz * cosd;
     double dzp = dx * cosa * cosd + dy * sina * cosd + dz * sind;
     dx = dxp; dy = dyp; dz = dzp;
 
-    const double costheta2 = dz * dz / r2;
-    const double J2s_prefac = 3. * J2s * Rs_eq * Rs_eq / r2 / r2 / r / 2.;
+    const double costheta2 = dr2(dz * dz);
+    const double J2s_prefac = dr(dr2(dr2(3. * J2s * Rs_eq * Rs_eq))) / 2.;
     const double J2s_fac = 5. * costheta2 - 1.;
     const double J2s_fac2 = 7. * costheta2 - 1.;
     const double J2s_fac3 = 35. * costheta2 * costheta2 - 30. * costheta2 + 3.;
@@ -304,16 +314,16 @@ __device__ void ab_force_solar_j2(const AbEphem& E, const AbForceOpts& F, const 
 
     S.a[0][0] += resxp; S.a[0][1] += resyp; S.a[0][2] += reszp;
 
-    if (S.nv == 0) return;
+    if (S.nv() == 0) return;
 
-    const double dxdx = GMsun * J2s_prefac * (J2s_fac - 5. * J2s_fac2 * dx * dx / r2);
-    const double dydy = GMsun * J2s_prefac * (J2s_fac - 5. * J2s_fac2 * dy * dy / r2);
+    const double dxdx = GMsun * J2s_prefac * (J2s_fac - dr2(5. * J2s_fac2 * dx * dx));
+    const double dydy = GMsun * J2s_prefac * (J2s_fac - dr2(5. * J2s_fac2 * dy * dy));
     const double dzdz = GMsun * J2s_prefac * (-1.) * J2s_fac3;
-    const double dxdy = GMsun * J2s_prefac * (-5.) * J2s_fac2 * dx * dy / r2;
-    const double dydz = GMsun * J2s_prefac * (-5.) * (J2s_fac2 - 2.) * dy * dz / r2;
-    const double dxdz = GMsun * J2s_prefac * (-5.) * (J2s_fac2 - 2.) * dx * dz / r2;
+    const double dxdy = dr2(GMsun * J2s_prefac * (-5.) * J2s_fac2 * dx * dy);
+    const double dydz = dr2(GMsun * J2s_prefac * (-5.) * (J2s_fac2 - 2.) * dy * dz);
+    const double dxdz = dr2(GMsun * J2s_prefac * (-5.) * (J2s_fac2 - 2.) * dx * dz);
 
-    for (int vv = 1; vv <= S.nv; vv++) {
+    for (int vv = 1; vv <= S.nv(); vv++) {
         double ddx = S.x[vv][0], ddy = S.x[vv][1], ddz = S.x[vv][2];
         double ddxp = -ddx * sina + ddy * cosa;
         double ddyp = -ddx * cosa * sind - ddy * sina * sind + ddz * cosd;
@@ -333,7 +343,8 @@ __device__ void ab_force_solar_j2(const AbEphem& E, const AbForceOpts& F, const 
 }
 
 /* ---- potential GR (Nobili & Roxburgh), reference src/forces.c:1059-1161 ---- */
-__device__ void ab_force_potential_gr(const AbEphem& E, const AbBodies& B, AbSys& S, double xo, double yo, double zo) {
+template <int KM, class BT>
+__device__ void ab_force_potential_gr(const AbEphem& E, const BT& B, AbSysT<KM>& S, double xo, double yo, double zo) {
     const double C2 = E.c_squared;
     const double GMsun = B.gm[0];
     const double px = S.x[0][0] + (xo - B.pos[0][0]);
@@ -343,7 +354,7 @@ __device__ void ab_force_potential_gr(const AbEphem& E, const AbBodies& B, AbSys
     const double r = sqrt(r2);
     const double prefac = -6.0 * GMsun * GMsun / (C2 * r2 * r2);
     S.a[0][0] += prefac * px; S.a[0][1] += prefac * py; S.a[0][2] += prefac * pz;
-    if (S.nv == 0) return;
+    if (S.nv() == 0) return;
     const double dxdx = prefac + -4.0 * prefac * (px / r) * (px / r);
     const double dxdy = -4.0 * prefac * (px / r) * (py / r);
     const double dxdz = -4.0 * prefac * (px / r) * (pz / r);
@@ -353,7 +364,7 @@ __device__ void ab_force_potential_gr(const AbEphem& E, const AbBodies& B, AbSys
     const double dzdx = -4.0 * prefac * (pz / r) * (px / r);
     const double dzdy = -4.0 * prefac * (pz / r) * (py / r);
     const double dzdz = prefac + -4.0 * prefac * (pz / r) * (pz / r);
-    for (int vv = 1; vv <= S.nv; vv++) {
+    for (int vv = 1; vv <= S.nv(); vv++) {
         const double ddx = S.x[vv][0], ddy = S.x[vv][1], ddz = S.x[vv][2];
         const double dax = ddx * dxdx + ddy * dxdy + ddz * dxdz;
         const double day = ddx * dydx + ddy * dydy + ddz * dydz;
@@ -363,7 +374,8 @@ __device__ void ab_force_potential_gr(const AbEphem& E, const AbBodies& B, AbSys
 }
 
 /* ---- simple GR (Damour & Deruelle), reference src/forces.c:1163-1286 ------- */
-__device__ void ab_force_simple_gr(const AbEphem& E, const AbBodies& B, AbSys& S,
+template <int KM, class BT>
+__device__ void ab_force_simple_gr(const AbEphem& E, const BT& B, AbSysT<KM>& S,
                                    double xo, double yo, double zo, double vxo, double vyo, double vzo) {
     const double C2 = E.c_squared;
     const double GMsun = B.gm[0];
@@ -383,7 +395,7 @@ __device__ void ab_force_simple_gr(const AbEphem& E, const AbBodies& B, AbSys& S
     S.a[0][0] += prefac * (A * px + Bq * pvx);
     S.a[0][1] += prefac * (A * py + Bq * pvy);
     S.a[0][2] += prefac * (A * pz + Bq * pvz);
-    if (S.nv == 0) return;
+    if (S.nv() == 0) return;
 
     const double dpdr = -3.0 * prefac / r;
     const double dxdx = dpdr * px / r * (A * px + Bq * pvx) + prefac * (A - px * (px / r) * 4.0 * GMsun / (r * r) + 4.0 * pvx * pvx);
@@ -412,7 +424,8 @@ __device__ void ab_force_simple_gr(const AbEphem& E, const AbBodies& B, AbSys& S
 }
 
 /* ---- Einstein-Infeld-Hoffman, reference src/forces.c:1288-1983 ------------- */
-__device__ void ab_force_eih(const AbEphem& E, const AbForceOpts& F, const AbBodies& B, AbSys& S,
+template <int KM, class BT>
+__device__ void ab_force_eih(const AbEphem& E, const AbForceOpts& F, const BT& B, AbSysT<KM>& S,
                              double xo, double yo, double zo, double vxo, double vyo, double vzo,
                              double axo, double ayo, double azo) {
     const double over_C2 = E.over_c_squared;
@@ -493,7 +506,7 @@ __device__ void ab_force_eih(const AbEphem& E, const AbForceOpts& F, const AbBod
         S.a[0][2] += term7z_sum * over_C2 + term8z_sum * over_C2;
     }
 
-    if (S.nv == 0) return;
+    if (S.nv() == 0) return;
 
     /* variational particles, src/forces.c:1508-1982 */
     double dterm0dx_sum = 0.0, dterm0dy_sum = 0.0, dterm0dz_sum = 0.0;
@@ -678,7 +691,8 @@ __device__ void ab_force_eih(const AbEphem& E, const AbForceOpts& F, const AbBod
 }
 
 /* ---- direct Newtonian terms, reference src/forces.c:266-433 ---------------- */
-__device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const AbBodies& B, AbSys& S,
+template <int KM, class BT>
+__device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT& B, AbSysT<KM>& S,
                                 double xo, double yo, double zo) {
     const int order[AB_NPLANETS] = {10, 4, 5, 1, 9, 8, 3, 2, 7, 6, 0};
     const int ast_num = E.n_ast;
@@ -701,7 +715,7 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const Ab
             S.a[0][1] -= prefac * dy;
             S.a[0][2] -= prefac * dz;
         }
-        if (S.nv > 0) {
+        if (S.nv() > 0) {
             /* no force-mask check here, as in the reference (src/forces.c:359) */
             const double r3inv = 1. / (r2 * _r);
             const double r5inv = 3. * r3inv / r2;
@@ -711,7 +725,7 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const Ab
             const double dxdy = dx * dy * r5inv;
             const double dxdz = dx * dz * r5inv;
             const double dydz = dy * dz * r5inv;
-            for (int vv = 1; vv <= S.nv; vv++) {
+            for (int vv = 1; vv <= S.nv(); vv++) {
                 const double ddx = S.x[vv][0], ddy = S.x[vv][1], ddz = S.x[vv][2];
                 const double dax = ddx * dxdx + ddy * dxdy + ddz * dxdz;
                 const double day = ddx * dxdy + ddy * dydy + ddz * dydz;
@@ -726,7 +740,8 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const Ab
 
 /* ---- dispatcher, reference src/forces.c:49-173 ----------------------------- */
 /* S.a must be zero on entry (REBOUND zeroes accelerations before the plug-in runs). */
-__device__ void ab_forces(const AbEphem& E, const AbForceOpts& F, const AbBodies& B, AbSys& S) {
+template <int KM, class BT>
+__device__ void ab_forces(const AbEphem& E, const AbForceOpts& F, const BT& B, AbSysT<KM>& S) {
     double xo = 0.0, yo = 0.0, zo = 0.0, vxo = 0.0, vyo = 0.0, vzo = 0.0, axo = 0.0, ayo = 0.0, azo = 0.0;
     if (F.geocentric == 1) {
         xo = B.pos[3][0]; yo = B.pos[3][1]; zo = B.pos[3][2];

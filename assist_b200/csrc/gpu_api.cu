@@ -55,8 +55,10 @@ static int ensure_device(int* dev_out) {
     CU(cudaGetDevice(&dev));
     if (dev < 0 || dev >= ASSIST_B200_MAX_DEVICES) return set_err(ASSIST_GPU_ERR_ARG, "device index %d out of range", dev);
     if (!g_const_uploaded[dev]) {
-        CU(ab_upload_constants_strict());
-        CU(ab_upload_constants_fast());
+        CU(ab_upload_constants_strict_tu0()); CU(ab_upload_constants_strict_tu1());
+        CU(ab_upload_constants_strict_tu2()); CU(ab_upload_constants_strict_tu3());
+        CU(ab_upload_constants_fast_tu0()); CU(ab_upload_constants_fast_tu1());
+        CU(ab_upload_constants_fast_tu2()); CU(ab_upload_constants_fast_tu3());
         g_const_uploaded[dev] = true;
     }
     *dev_out = dev;
@@ -95,13 +97,38 @@ static int upload_image(void** slot, const void* host, size_t len) {
     return 0;
 }
 
-static int fill_target(AbSpkTarget* d, const struct spk_target* t) {
+static int fill_target(AbSpkTarget* d, const struct spk_target* t, const struct spk_s* file) {
     memset(d, 0, sizeof(*d));
-    d->beg = t->beg; d->end = t->end; d->res = t->res; d->mass = t->mass;
+    d->beg = t->beg; d->end = t->end; d->res = t->res; d->res_rd = 1.0 / t->res; d->mass = t->mass;
     d->code = t->code; d->cen = t->cen; d->nseg = t->ind + 1;
     if (d->nseg > AB_MAXSEG)
         return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "SPK target %d has %d segments (max %d)", t->code, d->nseg, AB_MAXSEG);
-    for (int s = 0; s < d->nseg; s++) { d->one[s] = t->one[s]; d->two[s] = t->two[s]; }
+    const double* img = (const double*)file->map;
+    const size_t words = file->len / sizeof(double);
+    for (int s = 0; s < d->nseg; s++) {
+        /* segment trailer [INIT, INTLEN, RSIZE, N]; `two` addresses its last word (reference src/spk.c:503-510) */
+        if (t->two[s] < 4 || (size_t)t->two[s] > words || t->one[s] < 1)
+            return set_err(ASSIST_GPU_ERR_ARG, "SPK target %d: segment addresses out of range", t->code);
+        const double* val = img + t->two[s] - 1;
+        AbSpkSeg* sg = &d->seg[s];
+        sg->one = t->one[s];
+        sg->R = (int)val[-1];
+        sg->P = (sg->R - 2) / 3;
+        sg->nrec = (int)val[0];
+        if (sg->P < 2 || sg->P >= 32 || sg->nrec < 1)
+            return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "SPK target %d: not a type-2 Chebyshev segment", t->code);
+        sg->jul_init = 2451545.0 + val[-3] / 86400.0;
+        sg->intlen_d = val[-2] / 86400.0;
+        sg->intlen_rd = 1.0 / sg->intlen_d;
+        const double* rec0 = img + (t->one[s] - 1);
+        const double radius = rec0[1];
+        sg->radius_d = radius / 86400.0;
+        sg->radius_rd = 1.0 / sg->radius_d;
+        sg->radius_inv = 1.0 / radius;
+        sg->uniform = 1;
+        for (int b = 1; b < sg->nrec; b++)
+            if (rec0[(size_t)b * sg->R + 1] != radius) { sg->uniform = 0; break; }
+    }
     return 0;
 }
 
@@ -123,19 +150,30 @@ static int build_ephem(const struct assist_ephem* e, AbEphem* E) {
         if ((rc = upload_image(&a->b200_dev_image[dev], a->map, a->len))) return rc;
         E->ascii_img = (const double*)a->b200_dev_image[dev];
         E->a_beg = a->beg; E->a_end = a->end; E->a_inc = a->inc; E->a_cau = a->cau; E->a_cem = a->cem;
+        E->a_inc_rd = 1.0 / a->inc;
+        E->a_f_earth = -1.0 / (1.0 + a->cem);
+        E->a_f_moon = a->cem / (1.0 + a->cem);
+        E->u_d[0] = a->cau; E->u_d[1] = a->cau / 86400.; E->u_d[2] = a->cau / (86400. * 86400.);
         E->a_rec_words = (long long)(a->rec / sizeof(double));
         E->a_nrec = (long long)(a->len / a->rec) - 2;
-        for (int p = 0; p < 15; p++) { E->a_off[p] = a->off[p]; E->a_ncf[p] = a->ncf[p]; E->a_niv[p] = a->niv[p]; }
+        for (int p = 0; p < 15; p++) {
+            E->a_off[p] = a->off[p]; E->a_ncf[p] = a->ncf[p]; E->a_niv[p] = a->niv[p];
+            E->a_c[p] = (double)(a->niv[p] * 2) / a->inc / 86400.0;
+        }
         for (int k = 0; k < AB_NPLANETS; k++) E->a_mass[k] = a->mass[k];
     } else if (e->spk_planets) {
         struct spk_s* pl = e->spk_planets;
         if ((rc = upload_image(&pl->b200_dev_image[dev], pl->map, pl->len))) return rc;
         E->spkp_img = (const double*)pl->b200_dev_image[dev];
+        {
+            const double au = e->AU, seconds_per_day = 86400.;
+            E->u_d[0] = au; E->u_d[1] = au / seconds_per_day; E->u_d[2] = au / (seconds_per_day * seconds_per_day);
+        }
         if (pl->num > AB_MAX_PTGT)
             return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "planet kernel has %d targets (max %d)", pl->num, AB_MAX_PTGT);
         E->n_ptgt = pl->num;
         for (int m = 0; m < pl->num; m++)
-            if ((rc = fill_target(&E->p_tgt[m], &pl->targets[m]))) return rc;
+            if ((rc = fill_target(&E->p_tgt[m], &pl->targets[m], pl))) return rc;
         static const int naif_by_assist[AB_NPLANETS] = {10, 1, 2, 399, 301, 4, 5, 6, 7, 8, 9};
         for (int k = 0; k < AB_NPLANETS; k++) {
             /* precomputed index when it is consistent, else a search by NAIF code (reference src/spk.c:646-659) */
@@ -155,6 +193,7 @@ static int build_ephem(const struct assist_ephem* e, AbEphem* E) {
     } else {
         return set_err(ASSIST_ERROR_EPHEM_FILE, "ephemeris has no planets provider");
     }
+    for (int q = 0; q < 3; q++) E->u_rd[q] = 1.0 / E->u_d[q];
     if (e->spk_asteroids) {
         struct spk_s* sb = e->spk_asteroids;
         if (sb->num > AB_MAX_AST)
@@ -164,11 +203,16 @@ static int build_ephem(const struct assist_ephem* e, AbEphem* E) {
         E->n_ast = sb->num;
         AbSpkTarget tg[AB_MAX_AST];
         for (int m = 0; m < sb->num; m++)
-            if ((rc = fill_target(&tg[m], &sb->targets[m]))) return rc;
+            if ((rc = fill_target(&tg[m], &sb->targets[m], sb))) return rc;
         if (!sb->b200_dev_targets[dev]) CU(cudaMalloc(&sb->b200_dev_targets[dev], sizeof(AbSpkTarget) * AB_MAX_AST));
         /* descriptors carry the (joinable) masses, so they are refreshed on every build */
         CU(cudaMemcpy(sb->b200_dev_targets[dev], tg, sizeof(AbSpkTarget) * sb->num, cudaMemcpyHostToDevice));
         E->a_tgt = (const AbSpkTarget*)sb->b200_dev_targets[dev];
+        for (int m = 0; m < sb->num; m++) E->gm[AB_NPLANETS + m] = sb->targets[m].mass;
+    }
+    for (int k = 0; k < AB_NPLANETS; k++) {
+        if (e->ascii_planets) E->gm[k] = e->ascii_planets->mass[k];
+        else E->gm[k] = (E->p_index[k] >= 0) ? E->p_tgt[E->p_index[k]].mass : 0.0;   /* Earth-from-EMB fallback reports GM = 0 */
     }
     return 0;
 }
@@ -282,9 +326,31 @@ struct assist_gpu_batch {
     double* d_stage_prm;    /* [n][K][3] */
     double* d_out;          /* dense output staging */
     size_t d_out_bytes;
+    int* d_active[2];       /* ping-pong lists of systems still integrating */
+    int* d_count;           /* length of the list being built */
+    long long step_cap;     /* accepted steps per system per launch (per-particle mode) */
     cudaEvent_t ev0, ev1;
     struct assist_gpu_stats stats;
 };
+
+/* Append the systems of `in` (or 0..n_in-1) whose integrate() has not returned yet to `out`. */
+__global__ void compact_active_kernel(const int* __restrict__ status, const int* __restrict__ in, int n_in,
+                                      int* __restrict__ out, int* __restrict__ count) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = -1;
+    bool act = false;
+    if (tid < n_in) {
+        i = in ? in[tid] : tid;
+        act = status[i] < 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, act);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (act) out[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
 
 __global__ void aos_to_soa_kernel(const double* __restrict__ aos, int n, int K, int width, int off, int cnt, double* __restrict__ soa) {
     /* aos[i][j][width]; copies fields off..off+cnt-1 of body j to soa[(3*j + c) * n + i] */
@@ -329,7 +395,7 @@ extern "C" assist_gpu_batch* assist_gpu_batch_create(const struct assist_ephem* 
     const size_t per = C * n;                      /* doubles in one [C][n] array */
     const size_t n_small = 12 + 42 * 1;            /* pos vel acc x0 v0 a0 csx csv ls_pos ls_vel ls_acc prm  (+ 6 seven-deep tables) */
     (void)n_small;
-    size_t doubles = 12 * per + 42 * per + 3 * n;  /* + t dt dt_last */
+    size_t doubles = 12 * per + 42 * per + 4 * n;  /* + t dt dt_last last_full_dt */
     size_t bytes = doubles * sizeof(double);
     bytes += 4 * n * sizeof(unsigned long long);   /* counters */
     bytes += 2 * n * sizeof(int);                  /* nv, status */
@@ -349,7 +415,7 @@ extern "C" assist_gpu_batch* assist_gpu_batch_create(const struct assist_ephem* 
     d.ls_pos = p; p += per; d.ls_vel = p; p += per; d.ls_acc = p; p += per; d.prm = p; p += per;
     d.b = p; p += 7 * per; d.g = p; p += 7 * per; d.e = p; p += 7 * per;
     d.csb = p; p += 7 * per; d.br = p; p += 7 * per; d.er = p; p += 7 * per;
-    d.t = p; p += n; d.dt = p; p += n; d.dt_last = p; p += n;
+    d.t = p; p += n; d.dt = p; p += n; d.dt_last = p; p += n; d.last_full_dt = p; p += n;
     unsigned long long* q = (unsigned long long*)p;
     d.steps = q; q += n; d.rejected = q; q += n; d.iters = q; q += n; d.evals = q; q += n;
     d.sh = (AbShared*)q;
@@ -358,6 +424,13 @@ extern "C" assist_gpu_batch* assist_gpu_batch_create(const struct assist_ephem* 
     d.epsilon = b->opt.epsilon; d.min_dt = b->opt.min_dt; d.has_params = 0;
     cudaMalloc((void**)&b->d_stage, sizeof(double) * 6 * n * b->K);
     cudaMalloc((void**)&b->d_stage_prm, sizeof(double) * 3 * n * b->K);
+    cudaMalloc((void**)&b->d_active[0], sizeof(int) * n);
+    cudaMalloc((void**)&b->d_active[1], sizeof(int) * n);
+    cudaMalloc((void**)&b->d_count, sizeof(int));
+    {
+        const char* cap = getenv("ASSIST_B200_STEP_CAP");
+        b->step_cap = cap ? atoll(cap) : 32;
+    }
     cudaEventCreate(&b->ev0);
     cudaEventCreate(&b->ev1);
     fill_int_kernel<<<blocks_for(n), 256>>>(d.nv, n, n_var);
@@ -373,6 +446,7 @@ extern "C" assist_gpu_batch* assist_gpu_batch_create(const struct assist_ephem* 
 extern "C" void assist_gpu_batch_free(assist_gpu_batch* b) {
     if (!b) return;
     cudaFree(b->block); cudaFree(b->snapshot); cudaFree(b->d_stage); cudaFree(b->d_stage_prm); cudaFree(b->d_out);
+    cudaFree(b->d_active[0]); cudaFree(b->d_active[1]); cudaFree(b->d_count);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     free(b);
@@ -495,10 +569,35 @@ extern "C" int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int 
     const bool fast = (b->opt.math == ASSIST_GPU_MATH_FAST);
     cudaError_t e;
     if (b->mode == ASSIST_GPU_PER_PARTICLE) {
+        /* Every launch advances each running system by at most step_cap accepted steps; the systems
+         * whose integrate() has not returned are then packed into a dense list and relaunched.  This
+         * keeps the lanes of a warp busy although step counts differ by 10x between particles. */
+        const bool k1 = (b->K == 1);
         CU(cudaEventRecord(b->ev0, 0));
-        e = fast ? ab_launch_pp_integrate_fast(E, F, b->d, t_end, exact_finish_time, 0)
-                 : ab_launch_pp_integrate_strict(E, F, b->d, t_end, exact_finish_time, 0);
-        return finish_launch(b, e, "pp_integrate");
+        const int* list = NULL;
+        int n_active = b->n, resume = 0, which = 0;
+        unsigned long long launches = 0;
+        while (true) {
+            if (k1) e = fast ? ab_launch_pp_integrate_k1_fast(E, F, b->d, t_end, exact_finish_time, resume, b->step_cap, list, n_active, 0)
+                             : ab_launch_pp_integrate_k1_strict(E, F, b->d, t_end, exact_finish_time, resume, b->step_cap, list, n_active, 0);
+            else e = fast ? ab_launch_pp_integrate_kv_fast(E, F, b->d, t_end, exact_finish_time, resume, b->step_cap, list, n_active, 0)
+                          : ab_launch_pp_integrate_kv_strict(E, F, b->d, t_end, exact_finish_time, resume, b->step_cap, list, n_active, 0);
+            if (e != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "pp_integrate launch failed: %s", cudaGetErrorString(e));
+            launches++;
+            if (b->step_cap <= 0) break;
+            CU(cudaMemsetAsync(b->d_count, 0, sizeof(int), 0));
+            compact_active_kernel<<<(n_active + 255) / 256, 256>>>(b->d.status, list, n_active, b->d_active[which], b->d_count);
+            int count = 0;
+            CU(cudaMemcpy(&count, b->d_count, sizeof(int), cudaMemcpyDeviceToHost));
+            if (count == 0) break;
+            if (launches > 4000000ULL) return set_err(ASSIST_GPU_ERR_CUDA, "per-particle integration did not finish after %llu launches", launches);
+            list = b->d_active[which];
+            n_active = count;
+            which ^= 1;
+            resume = 1;
+        }
+        b->stats.kernel_launches += 2 * launches - 2;   /* integrate launches + compaction kernels (finish_launch adds one) */
+        return finish_launch(b, cudaSuccess, "pp_integrate");
     }
     /* shared step: barrier counter and reduction slots start from zero */
     CU(cudaMemsetAsync((char*)b->d.sh + offsetof(AbShared, barrier), 0, sizeof(AbShared) - offsetof(AbShared, barrier), 0));
@@ -533,8 +632,12 @@ extern "C" int assist_gpu_batch_integrate_or_interpolate(assist_gpu_batch* b, co
     double* d_times = (double*)((char*)b->d_out + out_bytes);
     CU(cudaMemcpy(d_times, times, sizeof(double) * n_times, cudaMemcpyHostToDevice));
     CU(cudaEventRecord(b->ev0, 0));
-    cudaError_t e = (b->opt.math == ASSIST_GPU_MATH_FAST) ? ab_launch_pp_dense_fast(E, F, b->d, d_times, n_times, b->d_out, 0)
-                                                          : ab_launch_pp_dense_strict(E, F, b->d, d_times, n_times, b->d_out, 0);
+    const bool fastm = (b->opt.math == ASSIST_GPU_MATH_FAST);
+    cudaError_t e;
+    if (b->K == 1) e = fastm ? ab_launch_pp_dense_k1_fast(E, F, b->d, d_times, n_times, b->d_out, 0)
+                             : ab_launch_pp_dense_k1_strict(E, F, b->d, d_times, n_times, b->d_out, 0);
+    else e = fastm ? ab_launch_pp_dense_kv_fast(E, F, b->d, d_times, n_times, b->d_out, 0)
+                   : ab_launch_pp_dense_kv_strict(E, F, b->d, d_times, n_times, b->d_out, 0);
     rc = finish_launch(b, e, "pp_dense");
     if (rc) return rc;
     CU(cudaMemcpy(out, b->d_out, out_bytes, cudaMemcpyDeviceToHost));
@@ -689,4 +792,37 @@ extern "C" double assist_gpu_measure_fp64_peak(int iters) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d);
     return best;
+}
+
+/* ------------------------------------------------------------------------ */
+/* pinned host buffers (for callers that want asynchronous-speed H2D/D2H)    */
+/* ------------------------------------------------------------------------ */
+
+extern "C" void* assist_gpu_host_alloc(size_t bytes) {
+    int dev;
+    if (ensure_device(&dev)) return NULL;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        set_err(ASSIST_GPU_ERR_CUDA, "cudaHostAlloc(%zu) failed", bytes);
+        return NULL;
+    }
+    return p;
+}
+
+extern "C" void assist_gpu_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+/* Per-system counters of a per-particle batch (each array n_sys long; any may be NULL). */
+extern "C" int assist_gpu_batch_get_counters(assist_gpu_batch* b, unsigned long long* steps, unsigned long long* rejected,
+                                             unsigned long long* iters, unsigned long long* evals) {
+    if (!b) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    if (b->mode != ASSIST_GPU_PER_PARTICLE) return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "per-system counters need a per-particle batch");
+    CU(cudaSetDevice(b->device));
+    const size_t bytes = sizeof(unsigned long long) * (size_t)b->n;
+    if (steps) CU(cudaMemcpy(steps, b->d.steps, bytes, cudaMemcpyDeviceToHost));
+    if (rejected) CU(cudaMemcpy(rejected, b->d.rejected, bytes, cudaMemcpyDeviceToHost));
+    if (iters) CU(cudaMemcpy(iters, b->d.iters, bytes, cudaMemcpyDeviceToHost));
+    if (evals) CU(cudaMemcpy(evals, b->d.evals, bytes, cudaMemcpyDeviceToHost));
+    return 0;
 }

@@ -17,14 +17,16 @@
 
 #include "device_types.h"
 #include "ias15_constants.h"
+#include "fp_device.cuh"
 #include "forces_device.cuh"
 
 namespace AB_NS {
 
-__constant__ double c_h[8];
-__constant__ double c_rr[28];
-__constant__ double c_c[21];
-__constant__ double c_d[21];
+static __constant__ double c_h[8];
+static __constant__ double c_rr[28];
+static __constant__ double c_rri[28];   /* RN(1/rr[k]) for exact division by rr[k] (fp_device.cuh) */
+static __constant__ double c_c[21];
+static __constant__ double c_d[21];
 
 #define AB1(arr, k) (arr)[(long long)(k) * n + i]
 #define AB7(arr, j, k) (arr)[((long long)(j) * C + (k)) * n + i]
@@ -49,16 +51,17 @@ __device__ double ab_sqrt7(double a) {
     double x = 1.;
     for (int k = 0; k < 20; k++) {
         double x6 = x * x * x * x * x * x;
-        x += (a / x6 - x) / 7.;
+        x += AB_DIVK(a / x6 - x, 7.);
     }
     return x * scale;
 }
 
 /* Load particles of system i into registers. */
-__device__ __forceinline__ void ab_load_sys(const AbBatch& Bt, long long i, AbSys& S) {
+template <int KM>
+__device__ __forceinline__ void ab_load_sys(const AbBatch& Bt, long long i, AbSysT<KM>& S) {
     const long long n = Bt.n;
-    S.nv = Bt.nv[i];
-    for (int j = 0; j <= S.nv; j++) {
+    S.nv_ = Bt.nv[i];
+    for (int j = 0; j <= S.nv(); j++) {
         for (int c = 0; c < 3; c++) {
             S.x[j][c] = AB1(Bt.pos, 3 * j + c);
             S.v[j][c] = AB1(Bt.vel, 3 * j + c);
@@ -67,15 +70,17 @@ __device__ __forceinline__ void ab_load_sys(const AbBatch& Bt, long long i, AbSy
     }
 }
 
-__device__ __forceinline__ void ab_zero_acc(AbSys& S) {
-    for (int j = 0; j <= S.nv; j++) { S.a[j][0] = 0.0; S.a[j][1] = 0.0; S.a[j][2] = 0.0; }
+template <int KM>
+__device__ __forceinline__ void ab_zero_acc(AbSysT<KM>& S) {
+    for (int j = 0; j <= S.nv(); j++) { S.a[j][0] = 0.0; S.a[j][1] = 0.0; S.a[j][2] = 0.0; }
 }
 
 /* Start of a reb_simulation_step: accelerations at the current state become a0 and
  * the dense-output anchor (last_state) is taken. */
-__device__ __forceinline__ void ab_store_a0(const AbBatch& Bt, long long i, const AbSys& S) {
+template <int KM>
+__device__ __forceinline__ void ab_store_a0(const AbBatch& Bt, long long i, const AbSysT<KM>& S) {
     const long long n = Bt.n;
-    for (int j = 0; j <= S.nv; j++) {
+    for (int j = 0; j <= S.nv(); j++) {
         for (int c = 0; c < 3; c++) {
             const int k = 3 * j + c;
             AB1(Bt.acc, k) = S.a[j][c];
@@ -109,20 +114,39 @@ __device__ void ab_attempt_begin(const AbBatch& Bt, long long i, int nv) {
 }
 
 /* Predict positions and velocities of every body of system i at node n. */
-__device__ void ab_predict(const AbBatch& Bt, long long i, int nn, double dt, AbSys& S) {
+template <int KM>
+__device__ void ab_predict(const AbBatch& Bt, long long i, int nn, double dt, AbSysT<KM>& S) {
     const long long n = Bt.n;
     const int C = Bt.C;
     const double h = c_h[nn];
-    for (int j = 0; j <= S.nv; j++) {
+    for (int j = 0; j <= S.nv(); j++) {
         for (int c = 0; c < 3; c++) {
             const int k = 3 * j + c;
             const double b0 = AB7(Bt.b, 0, k), b1 = AB7(Bt.b, 1, k), b2 = AB7(Bt.b, 2, k), b3 = AB7(Bt.b, 3, k);
             const double b4 = AB7(Bt.b, 4, k), b5 = AB7(Bt.b, 5, k), b6 = AB7(Bt.b, 6, k);
             const double x0 = AB1(Bt.x0, k), v0 = AB1(Bt.v0, k), a0 = AB1(Bt.a0, k);
             const double csx = AB1(Bt.csx, k), csv = AB1(Bt.csv, k);
-            const double xk = -csx + ((((((((b6 * 7. * h / 9. + b5) * 3. * h / 4. + b4) * 5. * h / 7. + b3) * 2. * h / 3. + b2) * 3. * h / 5. + b1) * h / 2. + b0) * h / 3. + a0) * dt * h / 2. + v0) * dt * h;
+            /* position series, nested exactly as REBOUND writes it:
+             * ((((((((b6*7h/9 + b5)*3h/4 + b4)*5h/7 + b3)*2h/3 + b2)*3h/5 + b1)*h/2 + b0)*h/3 + a0)*dt*h/2 + v0)*dt*h */
+            double px = AB_DIVK(b6 * 7. * h, 9.) + b5;
+            px = px * 3. * h / 4. + b4;
+            px = AB_DIVK(px * 5. * h, 7.) + b3;
+            px = AB_DIVK(px * 2. * h, 3.) + b2;
+            px = AB_DIVK(px * 3. * h, 5.) + b1;
+            px = px * h / 2. + b0;
+            px = AB_DIVK(px * h, 3.) + a0;
+            px = px * dt * h / 2. + v0;
+            const double xk = -csx + px * dt * h;
             S.x[j][c] = xk + x0;
-            const double vk = -csv + (((((((b6 * 7. * h / 8. + b5) * 6. * h / 7. + b4) * 5. * h / 6. + b3) * 4. * h / 5. + b2) * 3. * h / 4. + b1) * 2. * h / 3. + b0) * h / 2. + a0) * dt * h;
+            /* velocity series: (((((((b6*7h/8 + b5)*6h/7 + b4)*5h/6 + b3)*4h/5 + b2)*3h/4 + b1)*2h/3 + b0)*h/2 + a0)*dt*h */
+            double pv = b6 * 7. * h / 8. + b5;
+            pv = AB_DIVK(pv * 6. * h, 7.) + b4;
+            pv = AB_DIVK(pv * 5. * h, 6.) + b3;
+            pv = AB_DIVK(pv * 4. * h, 5.) + b2;
+            pv = pv * 3. * h / 4. + b1;
+            pv = AB_DIVK(pv * 2. * h, 3.) + b0;
+            pv = pv * h / 2. + a0;
+            const double vk = -csv + pv * dt * h;
             S.v[j][c] = vk + v0;
         }
     }
@@ -130,10 +154,11 @@ __device__ void ab_predict(const AbBatch& Bt, long long i, int nn, double dt, Ab
 
 /* Improve g and b from the accelerations at node n.  At node 7 also returns the
  * largest |a| and |change of b6| over the components (convergence monitor). */
-__device__ void ab_update_gb(const AbBatch& Bt, long long i, int nn, const AbSys& S, double& maxak, double& maxb6) {
+template <int KM>
+__device__ void ab_update_gb(const AbBatch& Bt, long long i, int nn, const AbSysT<KM>& S, double& maxak, double& maxb6) {
     const long long n = Bt.n;
     const int C = Bt.C;
-    for (int j = 0; j <= S.nv; j++) {
+    for (int j = 0; j <= S.nv(); j++) {
         for (int c = 0; c < 3; c++) {
             const int k = 3 * j + c;
             const double at = S.a[j][c];
@@ -144,7 +169,7 @@ __device__ void ab_update_gb(const AbBatch& Bt, long long i, int nn, const AbSys
             switch (nn) {
                 case 1: {
                     tmp = AB7(Bt.g, 0, k);
-                    const double gn = gk / c_rr[0];
+                    const double gn = ab_divc(gk, c_rr[0], c_rri[0]);
                     AB7(Bt.g, 0, k) = gn;
                     double b0 = AB7(Bt.b, 0, k), cs0 = AB7(Bt.csb, 0, k);
                     ab_add_cs(b0, cs0, gn - tmp);
@@ -153,7 +178,7 @@ __device__ void ab_update_gb(const AbBatch& Bt, long long i, int nn, const AbSys
                 case 2: {
                     tmp = AB7(Bt.g, 1, k);
                     g0 = AB7(Bt.g, 0, k);
-                    const double gn = (gk / c_rr[1] - g0) / c_rr[2];
+                    const double gn = ab_divc(ab_divc(gk, c_rr[1], c_rri[1]) - g0, c_rr[2], c_rri[2]);
                     AB7(Bt.g, 1, k) = gn;
                     tmp = gn - tmp;
                     double b0 = AB7(Bt.b, 0, k), cs0 = AB7(Bt.csb, 0, k);
@@ -166,7 +191,7 @@ __device__ void ab_update_gb(const AbBatch& Bt, long long i, int nn, const AbSys
                 case 3: {
                     tmp = AB7(Bt.g, 2, k);
                     g0 = AB7(Bt.g, 0, k); g1 = AB7(Bt.g, 1, k);
-                    const double gn = ((gk / c_rr[3] - g0) / c_rr[4] - g1) / c_rr[5];
+                    const double gn = ab_divc(ab_divc(ab_divc(gk, c_rr[3], c_rri[3]) - g0, c_rr[4], c_rri[4]) - g1, c_rr[5], c_rri[5]);
                     AB7(Bt.g, 2, k) = gn;
                     tmp = gn - tmp;
                     double b0 = AB7(Bt.b, 0, k), cs0 = AB7(Bt.csb, 0, k);
@@ -182,7 +207,7 @@ __device__ void ab_update_gb(const AbBatch& Bt, long long i, int nn, const AbSys
                 case 4: {
                     tmp = AB7(Bt.g, 3, k);
                     g0 = AB7(Bt.g, 0, k); g1 = AB7(Bt.g, 1, k); g2 = AB7(Bt.g, 2, k);
-                    const double gn = (((gk / c_rr[6] - g0) / c_rr[7] - g1) / c_rr[8] - g2) / c_rr[9];
+                    const double gn = ab_divc(ab_divc(ab_divc(ab_divc(gk, c_rr[6], c_rri[6]) - g0, c_rr[7], c_rri[7]) - g1, c_rr[8], c_rri[8]) - g2, c_rr[9], c_rri[9]);
                     AB7(Bt.g, 3, k) = gn;
                     tmp = gn - tmp;
                     double b0 = AB7(Bt.b, 0, k), cs0 = AB7(Bt.csb, 0, k);
@@ -201,7 +226,7 @@ __device__ void ab_update_gb(const AbBatch& Bt, long long i, int nn, const AbSys
                 case 5: {
                     tmp = AB7(Bt.g, 4, k);
                     g0 = AB7(Bt.g, 0, k); g1 = AB7(Bt.g, 1, k); g2 = AB7(Bt.g, 2, k); g3 = AB7(Bt.g, 3, k);
-                    const double gn = ((((gk / c_rr[10] - g0) / c_rr[11] - g1) / c_rr[12] - g2) / c_rr[13] - g3) / c_rr[14];
+                    const double gn = ab_divc(ab_divc(ab_divc(ab_divc(ab_divc(gk, c_rr[10], c_rri[10]) - g0, c_rr[11], c_rri[11]) - g1, c_rr[12], c_rri[12]) - g2, c_rr[13], c_rri[13]) - g3, c_rr[14], c_rri[14]);
                     AB7(Bt.g, 4, k) = gn;
                     tmp = gn - tmp;
                     double b0 = AB7(Bt.b, 0, k), cs0 = AB7(Bt.csb, 0, k);
@@ -223,7 +248,7 @@ __device__ void ab_update_gb(const AbBatch& Bt, long long i, int nn, const AbSys
                 case 6: {
                     tmp = AB7(Bt.g, 5, k);
                     g0 = AB7(Bt.g, 0, k); g1 = AB7(Bt.g, 1, k); g2 = AB7(Bt.g, 2, k); g3 = AB7(Bt.g, 3, k); g4 = AB7(Bt.g, 4, k);
-                    const double gn = (((((gk / c_rr[15] - g0) / c_rr[16] - g1) / c_rr[17] - g2) / c_rr[18] - g3) / c_rr[19] - g4) / c_rr[20];
+                    const double gn = ab_divc(ab_divc(ab_divc(ab_divc(ab_divc(ab_divc(gk, c_rr[15], c_rri[15]) - g0, c_rr[16], c_rri[16]) - g1, c_rr[17], c_rri[17]) - g2, c_rr[18], c_rri[18]) - g3, c_rr[19], c_rri[19]) - g4, c_rr[20], c_rri[20]);
                     AB7(Bt.g, 5, k) = gn;
                     tmp = gn - tmp;
                     double b0 = AB7(Bt.b, 0, k), cs0 = AB7(Bt.csb, 0, k);
@@ -249,7 +274,7 @@ __device__ void ab_update_gb(const AbBatch& Bt, long long i, int nn, const AbSys
                     tmp = AB7(Bt.g, 6, k);
                     g0 = AB7(Bt.g, 0, k); g1 = AB7(Bt.g, 1, k); g2 = AB7(Bt.g, 2, k); g3 = AB7(Bt.g, 3, k);
                     g4 = AB7(Bt.g, 4, k); g5 = AB7(Bt.g, 5, k);
-                    const double gn = ((((((gk / c_rr[21] - g0) / c_rr[22] - g1) / c_rr[23] - g2) / c_rr[24] - g3) / c_rr[25] - g4) / c_rr[26] - g5) / c_rr[27];
+                    const double gn = ab_divc(ab_divc(ab_divc(ab_divc(ab_divc(ab_divc(ab_divc(gk, c_rr[21], c_rri[21]) - g0, c_rr[22], c_rri[22]) - g1, c_rr[23], c_rri[23]) - g2, c_rr[24], c_rri[24]) - g3, c_rr[25], c_rri[25]) - g4, c_rr[26], c_rri[26]) - g5, c_rr[27], c_rri[27]);
                     AB7(Bt.g, 6, k) = gn;
                     tmp = gn - tmp;
                     double b0 = AB7(Bt.b, 0, k), cs0 = AB7(Bt.csb, 0, k);
@@ -285,7 +310,8 @@ __device__ void ab_update_gb(const AbBatch& Bt, long long i, int nn, const AbSys
 
 /* Step-size monitor of one system: largest |a| and |b6| of the REAL particle,
  * unless its acceleration is slowly varying.  S holds the node-7 prediction. */
-__device__ void ab_dt_monitor(const AbBatch& Bt, long long i, const AbSys& S, double dt, double& maxa, double& maxj) {
+template <int KM>
+__device__ void ab_dt_monitor(const AbBatch& Bt, long long i, const AbSysT<KM>& S, double dt, double& maxa, double& maxj) {
     const long long n = Bt.n;
     const int C = Bt.C;
     const double v2 = S.v[0][0] * S.v[0][0] + S.v[0][1] * S.v[0][1] + S.v[0][2] * S.v[0][2];
@@ -372,21 +398,21 @@ __device__ void ab_advance(const AbBatch& Bt, long long i, int nv, double dt_don
         double x0 = AB1(Bt.x0, k), v0 = AB1(Bt.v0, k);
         const double a0 = AB1(Bt.a0, k);
         double csx = AB1(Bt.csx, k), csv = AB1(Bt.csv, k);
-        ab_add_cs(x0, csx, b6 / 72. * dt_done * dt_done);
-        ab_add_cs(x0, csx, b5 / 56. * dt_done * dt_done);
-        ab_add_cs(x0, csx, b4 / 42. * dt_done * dt_done);
-        ab_add_cs(x0, csx, b3 / 30. * dt_done * dt_done);
-        ab_add_cs(x0, csx, b2 / 20. * dt_done * dt_done);
-        ab_add_cs(x0, csx, b1 / 12. * dt_done * dt_done);
-        ab_add_cs(x0, csx, b0 / 6. * dt_done * dt_done);
+        ab_add_cs(x0, csx, AB_DIVK(b6, 72.) * dt_done * dt_done);
+        ab_add_cs(x0, csx, AB_DIVK(b5, 56.) * dt_done * dt_done);
+        ab_add_cs(x0, csx, AB_DIVK(b4, 42.) * dt_done * dt_done);
+        ab_add_cs(x0, csx, AB_DIVK(b3, 30.) * dt_done * dt_done);
+        ab_add_cs(x0, csx, AB_DIVK(b2, 20.) * dt_done * dt_done);
+        ab_add_cs(x0, csx, AB_DIVK(b1, 12.) * dt_done * dt_done);
+        ab_add_cs(x0, csx, AB_DIVK(b0, 6.) * dt_done * dt_done);
         ab_add_cs(x0, csx, a0 / 2. * dt_done * dt_done);
         ab_add_cs(x0, csx, v0 * dt_done);
         ab_add_cs(v0, csv, b6 / 8. * dt_done);
-        ab_add_cs(v0, csv, b5 / 7. * dt_done);
-        ab_add_cs(v0, csv, b4 / 6. * dt_done);
-        ab_add_cs(v0, csv, b3 / 5. * dt_done);
+        ab_add_cs(v0, csv, AB_DIVK(b5, 7.) * dt_done);
+        ab_add_cs(v0, csv, AB_DIVK(b4, 6.) * dt_done);
+        ab_add_cs(v0, csv, AB_DIVK(b3, 5.) * dt_done);
         ab_add_cs(v0, csv, b2 / 4. * dt_done);
-        ab_add_cs(v0, csv, b1 / 3. * dt_done);
+        ab_add_cs(v0, csv, AB_DIVK(b1, 3.) * dt_done);
         ab_add_cs(v0, csv, b0 / 2. * dt_done);
         ab_add_cs(v0, csv, a0 * dt_done);
         AB1(Bt.x0, k) = x0; AB1(Bt.v0, k) = v0; AB1(Bt.csx, k) = csx; AB1(Bt.csv, k) = csv;
@@ -406,20 +432,20 @@ __device__ void ab_interpolate(const AbBatch& Bt, long long i, int nv, double dt
     double s[9], sv[8];
     s[0] = dt_last_done * h;
     s[1] = s[0] * s[0] / 2.;
-    s[2] = s[1] * h / 3.;
+    s[2] = AB_DIVK(s[1] * h, 3.);
     s[3] = s[2] * h / 2.;
-    s[4] = 3. * s[3] * h / 5.;
-    s[5] = 2. * s[4] * h / 3.;
-    s[6] = 5. * s[5] * h / 7.;
+    s[4] = AB_DIVK(3. * s[3] * h, 5.);
+    s[5] = AB_DIVK(2. * s[4] * h, 3.);
+    s[6] = AB_DIVK(5. * s[5] * h, 7.);
     s[7] = 3. * s[6] * h / 4.;
-    s[8] = 7. * s[7] * h / 9.;
+    s[8] = AB_DIVK(7. * s[7] * h, 9.);
     sv[0] = dt_last_done * h;
     sv[1] = sv[0] * h / 2.;
-    sv[2] = 2. * sv[1] * h / 3.;
+    sv[2] = AB_DIVK(2. * sv[1] * h, 3.);
     sv[3] = 3. * sv[2] * h / 4.;
-    sv[4] = 4. * sv[3] * h / 5.;
-    sv[5] = 5. * sv[4] * h / 6.;
-    sv[6] = 6. * sv[5] * h / 7.;
+    sv[4] = AB_DIVK(4. * sv[3] * h, 5.);
+    sv[5] = AB_DIVK(5. * sv[4] * h, 6.);
+    sv[6] = AB_DIVK(6. * sv[5] * h, 7.);
     sv[7] = 7. * sv[6] * h / 8.;
     for (int j = 0; j <= nv; j++) {
         for (int c = 0; c < 3; c++) {
@@ -436,6 +462,7 @@ __device__ void ab_interpolate(const AbBatch& Bt, long long i, int nv, double dt
 /* reb_check_exit: decides whether integrate() goes on; may shorten dt for the last step. */
 __device__ int ab_check_exit(double t, double& dt, double dt_last, int& status, double tmax, int exact_finish_time, double& last_full_dt) {
     const double dtsign = copysign(1., dt);
+    if (!(dt == dt) || !(t == t)) status = 1;      /* NaN step or time: stop instead of spinning forever */
     if (status >= 0) {
         /* exit now */
     } else if (exact_finish_time == 1) {

@@ -1,27 +1,32 @@
 /*
- * kernels.cu -- sm_100a kernels.  Compiled twice:
+ * kernels.cu -- sm_100a kernels.  Compiled once per (math variant, translation unit):
  *   -DAB_STRICT=1 --fmad=false   namespace ab_strict : no FMA contraction, reference op order
  *   -DAB_STRICT=0 --fmad=true    namespace ab_fast   : FMA contraction allowed
+ *   -DAB_TU=0  ephem_eval_kernel, force_eval_kernel     (assist_get_particle / assist_additional_forces / parity)
+ *   -DAB_TU=1  pp_* kernels for systems without variational particles (state in registers)
+ *   -DAB_TU=2  pp_* kernels for systems with up to AB_NVMAX variational particles
+ *   -DAB_TU=3  sh_* kernels: shared-step IAS15 (persistent cooperative kernel) + dense output
  * The launchers at the bottom are what gpu_api.cu calls.
- *
- * Kernels
- *   ephem_eval_kernel        body states for a list of times (assist_get_particle / parity)
- *   force_eval_kernel        one force evaluation per system (assist_additional_forces / parity)
- *   pp_integrate_kernel      per-particle-dt IAS15: each thread integrates its own system
- *   pp_dense_kernel          same, with assist_integrate_or_interpolate semantics per epoch
- *   sh_integrate_kernel      shared-step IAS15: persistent cooperative kernel, global reductions
- *   sh_interpolate_kernel    dense output for the shared-step batch
  */
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 
-#if AB_STRICT
-#define AB_NS ab_strict
-#else
-#define AB_NS ab_fast
+#ifndef AB_TU
+#error "AB_TU must be defined"
 #endif
+#define AB_CAT3_(a, b, c) a##_##b##_tu##c
+#define AB_CAT3(a, b, c) AB_CAT3_(a, b, c)
+#define AB_CAT2_(a, b) a##_##b
+#define AB_CAT2(a, b) AB_CAT2_(a, b)
+#if AB_STRICT
+#define AB_SFX strict
+#else
+#define AB_SFX fast
+#endif
+/* one namespace per (variant, translation unit): device helpers defined in headers stay private to it */
+#define AB_NS AB_CAT3(ab, AB_SFX, AB_TU)
 
 #include "device_types.h"
 #include "ephem_device.cuh"
@@ -31,6 +36,16 @@
 
 namespace AB_NS {
 
+/* Out-of-line copies keep one instance of the two big routines per kernel. */
+__device__ __noinline__ void ab_body_states_ol(const AbEphem& E, const AbForceOpts& F, double t, AbBodies& B) {
+    ab_body_states(E, F, t, B);
+}
+template <int KM, class BT>
+__device__ __noinline__ void ab_forces_ol(const AbEphem& E, const AbForceOpts& F, const BT& B, AbSysT<KM>& S) {
+    ab_forces<KM, BT>(E, F, B, S);
+}
+
+#if AB_TU == 0
 /* ------------------------------------------------------------------------ */
 /* ephemeris + force evaluation kernels                                     */
 /* ------------------------------------------------------------------------ */
@@ -72,8 +87,8 @@ __global__ void force_eval_kernel(const __grid_constant__ AbEphem E, const __gri
                                   double* __restrict__ acc, int* __restrict__ status) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    AbSys S;
-    S.nv = K - 1;
+    AbSysT<AB_KMAX> S;
+    S.nv_ = K - 1;
     for (int j = 0; j < K; j++) {
         for (int c = 0; c < 3; c++) {
             S.x[j][c] = state[(i * K + j) * 6 + c];
@@ -82,20 +97,27 @@ __global__ void force_eval_kernel(const __grid_constant__ AbEphem E, const __gri
         }
     }
     AbBodies B;
-    ab_body_states(E, F, t_per_system ? t[i] : t[0], B);
+    ab_body_states_ol(E, F, t_per_system ? t[i] : t[0], B);
     ab_zero_acc(S);
-    if (B.status == AB_OK) ab_forces(E, F, B, S);
+    if (B.status == AB_OK) ab_forces_ol<AB_KMAX, AbBodies>(E, F, B, S);
     for (int j = 0; j < K; j++)
         for (int c = 0; c < 3; c++) acc[(i * K + j) * 3 + c] = S.a[j][c];
     status[i] = B.status;
 }
+#endif  /* AB_TU == 0 */
 
+#if AB_TU == 1 || AB_TU == 2
 /* ------------------------------------------------------------------------ */
 /* per-particle-dt IAS15                                                    */
 /* ------------------------------------------------------------------------ */
+#if AB_TU == 1
+#define PP_KM 1
+#else
+#define PP_KM AB_KMAX
+#endif
 
 struct PPState {
-    double t, dt, dt_last;
+    double t, dt, dt_last, last_full_dt;
     int status;
     unsigned long long steps, rejected, iters, evals;
 };
@@ -103,15 +125,16 @@ struct PPState {
 /* One reb_simulation_step of system i: force evaluation at the current state, then
  * IAS15 attempts until one is accepted.  Each thread owns its times, so the body
  * table is evaluated per thread. */
+template <int KM>
 __device__ void pp_step(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, long long i, PPState& P) {
-    AbSys S;
+    AbSysT<KM> S;
     AbBodies B;
     ab_load_sys(Bt, i, S);
-    const int nv = S.nv;
-    ab_body_states(E, F, P.t, B);
+    const int nv = S.nv();
+    ab_body_states_ol(E, F, P.t, B);
     if (B.status != AB_OK) { P.status = 1; Bt.status[i] = 1000 + B.status; return; }
     ab_zero_acc(S);
-    ab_forces(E, F, B, S);
+    ab_forces_ol<KM, AbBodies>(E, F, B, S);
     P.evals++;
     ab_store_a0(Bt, i, S);
 
@@ -132,10 +155,10 @@ __device__ void pp_step(const AbEphem& E, const AbForceOpts& F, const AbBatch& B
             for (int nn = 1; nn < 8; nn++) {
                 const double ts = t_beginning + P.dt * c_h[nn];
                 ab_predict(Bt, i, nn, P.dt, S);
-                ab_body_states(E, F, ts, B);
+                ab_body_states_ol(E, F, ts, B);
                 if (B.status != AB_OK) { P.status = 1; Bt.status[i] = 1000 + B.status; return; }
                 ab_zero_acc(S);
-                ab_forces(E, F, B, S);
+                ab_forces_ol<KM, AbBodies>(E, F, B, S);
                 P.evals++;
                 ab_update_gb(Bt, i, nn, S, maxak, maxb6);
             }
@@ -167,44 +190,130 @@ __device__ void pp_step(const AbEphem& E, const AbForceOpts& F, const AbBatch& B
     }
 }
 
-/* reb_simulation_integrate(tmax) for one system. */
-__device__ void pp_integrate_to(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, long long i, PPState& P,
-                                double tmax, int exact_finish_time) {
-    if (tmax != P.t) P.dt = copysign(P.dt, (tmax > P.t) ? 1.0 : -1.0);
-    double last_full_dt = P.dt;
-    P.dt_last = 0.;
-    P.status = -1;
-    while (ab_check_exit(P.t, P.dt, P.dt_last, P.status, tmax, exact_finish_time, last_full_dt) < 0) {
-        pp_step(E, F, Bt, i, P);
+/* The same step for the common configuration (one EIH source, barycentric): the body tables of
+ * the 8 times of the step are evaluated once, side by side (ab_fill_nodes), and every
+ * predictor-corrector sweep reuses them -- what the reference's 7-slot time cache does. */
+template <int KM>
+__device__ void pp_step_nodes(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, long long i, PPState& P) {
+    AbSysT<KM> S;
+    AbNode nodes[AB_NT];
+    double times[AB_NT];
+    ab_load_sys(Bt, i, S);
+    const int nv = S.nv();
+    bool have_a0 = false;
+    while (true) {   /* attempts */
+        const double t_beginning = P.t;
+        times[0] = t_beginning;
+        for (int nn = 1; nn < 8; nn++) times[nn] = t_beginning + P.dt * c_h[nn];
+        const int flag = ab_fill_nodes(E, F, times, nodes);
+        if (flag != AB_OK) { P.status = 1; Bt.status[i] = 1000 + flag; return; }
+        if (!have_a0) {
+            ab_zero_acc(S);
+            ab_forces_ol<KM, AbNode>(E, F, nodes[0], S);
+            P.evals++;
+            ab_store_a0(Bt, i, S);
+            have_a0 = true;
+        }
+        ab_attempt_begin(Bt, i, nv);
+        double pc_err = 1e300, pc_err_last = 2;
+        int iterations = 0;
+        while (true) {
+            if (pc_err < 1e-16) break;
+            if (iterations > 2 && pc_err_last <= pc_err) break;
+            if (iterations >= 12) break;
+            pc_err_last = pc_err;
+            pc_err = 0;
+            iterations++;
+            P.iters++;
+            double maxak = 0.0, maxb6 = 0.0;
+            for (int nn = 1; nn < 8; nn++) {
+                ab_predict(Bt, i, nn, P.dt, S);
+                ab_zero_acc(S);
+                ab_forces_ol<KM, AbNode>(E, F, nodes[nn], S);
+                P.evals++;
+                ab_update_gb(Bt, i, nn, S, maxak, maxb6);
+            }
+            pc_err = maxb6 / maxak;
+        }
+        const double dt_done = P.dt;
+        if (Bt.epsilon > 0) {
+            double maxa = 0.0, maxj = 0.0;
+            ab_dt_monitor(Bt, i, S, P.dt, maxa, maxj);
+            double dt_new = ab_dt_new(Bt.epsilon, Bt.min_dt, maxa, maxj, dt_done);
+            if (fabs(dt_new / dt_done) < 0.25) {
+                ab_restore(Bt, i, nv);
+                P.dt = dt_new;
+                if (P.dt_last != 0.) ab_predict_next(Bt, i, nv, P.dt / P.dt_last, Bt.er, Bt.br);
+                P.rejected++;
+                continue;
+            }
+            if (fabs(dt_new / dt_done) > 1.0) {
+                if (dt_new / dt_done > 1. / 0.25) dt_new = dt_done / 0.25;
+            }
+            P.dt = dt_new;
+        }
+        ab_advance(Bt, i, nv, dt_done);
+        P.t += dt_done;
+        P.dt_last = dt_done;
+        ab_predict_next(Bt, i, nv, P.dt / dt_done, Bt.e, Bt.b);
+        P.steps++;
+        return;
     }
-    if (exact_finish_time == 1) P.dt = last_full_dt;
+}
+
+/* reb_simulation_integrate(tmax) for one system, at most `step_cap` steps in this call.
+ * Returns true when integrate() has returned (status >= 0), false when it was paused. */
+template <int KM>
+__device__ bool pp_integrate_to(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, long long i, PPState& P,
+                                double tmax, int exact_finish_time, bool resume, long long step_cap) {
+    if (!resume) {
+        if (tmax != P.t) P.dt = copysign(P.dt, (tmax > P.t) ? 1.0 : -1.0);
+        P.last_full_dt = P.dt;
+        P.dt_last = 0.;
+        P.status = -1;
+    }
+    long long done = 0;
+    while (true) {
+        if (step_cap > 0 && done >= step_cap) return false;
+        if (ab_check_exit(P.t, P.dt, P.dt_last, P.status, tmax, exact_finish_time, P.last_full_dt) >= 0) break;
+        if (F.gr_eih_sources == 1 && !F.geocentric) pp_step_nodes<KM>(E, F, Bt, i, P);
+        else pp_step<KM>(E, F, Bt, i, P);
+        done++;
+    }
+    if (exact_finish_time == 1) P.dt = P.last_full_dt;
+    return true;
 }
 
 __device__ __forceinline__ void pp_load(const AbBatch& Bt, long long i, PPState& P) {
-    P.t = Bt.t[i]; P.dt = Bt.dt[i]; P.dt_last = Bt.dt_last[i]; P.status = Bt.status[i];
+    P.t = Bt.t[i]; P.dt = Bt.dt[i]; P.dt_last = Bt.dt_last[i]; P.last_full_dt = Bt.last_full_dt[i]; P.status = Bt.status[i];
     P.steps = Bt.steps[i]; P.rejected = Bt.rejected[i]; P.iters = Bt.iters[i]; P.evals = Bt.evals[i];
 }
 __device__ __forceinline__ void pp_store(const AbBatch& Bt, long long i, const PPState& P) {
-    Bt.t[i] = P.t; Bt.dt[i] = P.dt; Bt.dt_last[i] = P.dt_last;
+    Bt.t[i] = P.t; Bt.dt[i] = P.dt; Bt.dt_last[i] = P.dt_last; Bt.last_full_dt[i] = P.last_full_dt;
     if (Bt.status[i] < 1000) Bt.status[i] = P.status;
     Bt.steps[i] = P.steps; Bt.rejected[i] = P.rejected; Bt.iters[i] = P.iters; Bt.evals[i] = P.evals;
 }
 
-__global__ void __launch_bounds__(AB_BLOCK)
+/* Thread -> system through an optional list of still-running systems, so that a relaunch
+ * packs the stragglers into full warps. */
+__global__ void __launch_bounds__(AB_BLOCK, AB_PP_MIN_BLOCKS)
 pp_integrate_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F,
-                    const __grid_constant__ AbBatch Bt, double tmax, int exact_finish_time) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= Bt.n) return;
+                    const __grid_constant__ AbBatch Bt, double tmax, int exact_finish_time, int resume,
+                    long long step_cap, const int* __restrict__ active, int n_active) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_active) return;
+    const long long i = active ? active[tid] : tid;
     PPState P;
     pp_load(Bt, i, P);
     if (P.status >= 1000) return;
-    pp_integrate_to(E, F, Bt, i, P, tmax, exact_finish_time);
+    if (resume && P.status >= 0) return;
+    pp_integrate_to<PP_KM>(E, F, Bt, i, P, tmax, exact_finish_time, resume != 0, step_cap);
     pp_store(Bt, i, P);
 }
 
 /* assist_integrate_or_interpolate(times[e]) for e = 0..n_times-1 per system
  * (reference src/assist.c:642-680); out[n_times][n][K][6]. */
-__global__ void __launch_bounds__(AB_BLOCK)
+__global__ void __launch_bounds__(AB_BLOCK, AB_PP_MIN_BLOCKS)
 pp_dense_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F,
                 const __grid_constant__ AbBatch Bt, const double* __restrict__ times, int n_times,
                 double* __restrict__ out) {
@@ -222,7 +331,7 @@ pp_dense_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbFor
         double* o = out + ((long long)e * n + i) * K * 6;
         const double dts = copysign(1., P.dt_last);
         if (dts * (P.t - P.dt_last) > dts * t || dts * t > dts * P.t || P.dt_last == 0.0) {
-            pp_integrate_to(E, F, Bt, i, P, t, 0);
+            pp_integrate_to<PP_KM>(E, F, Bt, i, P, t, 0, false, 0);
         }
         const double h = 1.0 - (P.t - t) / P.dt_last;
         if (P.status > 0) {
@@ -241,7 +350,9 @@ pp_dense_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbFor
     }
     pp_store(Bt, i, P);
 }
+#endif  /* AB_TU == 1 || AB_TU == 2 */
 
+#if AB_TU == 3
 /* ------------------------------------------------------------------------ */
 /* shared-step IAS15 (REBOUND semantics for one N-particle simulation)      */
 /* ------------------------------------------------------------------------ */
@@ -291,15 +402,14 @@ __device__ void grid_max2(AbShared* sh, unsigned long long& phase, unsigned long
 __device__ void sh_fill_bodies(const AbEphem& E, const AbForceOpts& F, AbBodies* sb, double t0, double dt, int first, int last) {
     for (int s = first + (int)threadIdx.x; s <= last; s += blockDim.x) {
         const double ts = (s == 0) ? t0 : (t0 + dt * c_h[s]);
-        ab_body_states(E, F, ts, sb[s]);
+        ab_body_states_ol(E, F, ts, sb[s]);
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(AB_BLOCK)
-sh_integrate_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F,
-                    const __grid_constant__ AbBatch Bt, double tmax, int exact_finish_time, long long max_steps, int flags) {
-    __shared__ AbBodies sb[8];
+template <int KM>
+__device__ void sh_integrate_body(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, AbBodies* sb,
+                                  double tmax, int exact_finish_time, long long max_steps, int flags) {
     AbShared* sh = Bt.sh;
     const long long n = Bt.n;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -328,10 +438,10 @@ sh_integrate_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ A
         sh_fill_bodies(E, F, sb, t, dt, 0, 0);
         if (sb[0].status != AB_OK) { err = sb[0].status; status = 1; break; }
         for (long long i = gtid; i < n; i += stride) {
-            AbSys S;
+            AbSysT<KM> S;
             ab_load_sys(Bt, i, S);
             ab_zero_acc(S);
-            ab_forces(E, F, sb[0], S);
+            ab_forces_ol<KM, AbBodies>(E, F, sb[0], S);
             ab_store_a0(Bt, i, S);
         }
         evals++;
@@ -340,7 +450,7 @@ sh_integrate_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ A
             sh_fill_bodies(E, F, sb, t, dt, 1, 7);
             for (int s = 1; s < 8; s++) if (sb[s].status != AB_OK) err = sb[s].status;
             if (err) break;
-            for (long long i = gtid; i < n; i += stride) ab_attempt_begin(Bt, i, Bt.nv[i]);
+            for (long long i = gtid; i < n; i += stride) ab_attempt_begin(Bt, i, (KM == 1) ? 0 : Bt.nv[i]);
             double pc_err = 1e300, pc_err_last = 2;
             int iterations = 0;
             double dmaxa = 0.0, dmaxj = 0.0;
@@ -355,14 +465,14 @@ sh_integrate_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ A
                 double maxak = 0.0, maxb6 = 0.0;
                 dmaxa = 0.0; dmaxj = 0.0;
                 for (long long i = gtid; i < n; i += stride) {
-                    AbSys S;
-                    S.nv = Bt.nv[i];
-                    for (int j = 0; j <= S.nv; j++)
+                    AbSysT<KM> S;
+                    S.nv_ = Bt.nv[i];
+                    for (int j = 0; j <= S.nv(); j++)
                         for (int c = 0; c < 3; c++) S.prm[j][c] = Bt.has_params ? AB1(Bt.prm, 3 * j + c) : 0.0;
                     for (int nn = 1; nn < 8; nn++) {
                         ab_predict(Bt, i, nn, dt, S);
                         ab_zero_acc(S);
-                        ab_forces(E, F, sb[nn], S);
+                        ab_forces_ol<KM, AbBodies>(E, F, sb[nn], S);
                         ab_update_gb(Bt, i, nn, S, maxak, maxb6);
                     }
                     /* step-size monitor uses the node-7 prediction of this (possibly last) sweep */
@@ -379,7 +489,7 @@ sh_integrate_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ A
                 if (fabs(dt_new / dt_done) < 0.25) {
                     dt = dt_new;
                     for (long long i = gtid; i < n; i += stride) {
-                        const int nv = Bt.nv[i];
+                        const int nv = (KM == 1) ? 0 : Bt.nv[i];
                         ab_restore(Bt, i, nv);
                         if (dt_last != 0.) ab_predict_next(Bt, i, nv, dt / dt_last, Bt.er, Bt.br);
                     }
@@ -392,7 +502,7 @@ sh_integrate_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ A
                 dt = dt_new;
             }
             for (long long i = gtid; i < n; i += stride) {
-                const int nv = Bt.nv[i];
+                const int nv = (KM == 1) ? 0 : Bt.nv[i];
                 ab_advance(Bt, i, nv, dt_done);
                 ab_predict_next(Bt, i, nv, dt / dt_done, Bt.e, Bt.b);
             }
@@ -415,67 +525,95 @@ sh_integrate_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ A
     }
 }
 
+__global__ void __launch_bounds__(AB_BLOCK)
+sh_integrate_kernel_k1(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F,
+                       const __grid_constant__ AbBatch Bt, double tmax, int exact_finish_time, long long max_steps, int flags) {
+    __shared__ AbBodies sb[8];
+    sh_integrate_body<1>(E, F, Bt, sb, tmax, exact_finish_time, max_steps, flags);
+}
+
+__global__ void __launch_bounds__(AB_BLOCK)
+sh_integrate_kernel_kv(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F,
+                       const __grid_constant__ AbBatch Bt, double tmax, int exact_finish_time, long long max_steps, int flags) {
+    __shared__ AbBodies sb[8];
+    sh_integrate_body<AB_KMAX>(E, F, Bt, sb, tmax, exact_finish_time, max_steps, flags);
+}
+
 /* out[n][K][6] */
 __global__ void sh_interpolate_kernel(const __grid_constant__ AbBatch Bt, double dt_last_done, double h, double* __restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Bt.n) return;
     ab_interpolate(Bt, i, Bt.nv[i], dt_last_done, h, out + i * Bt.K * 6);
 }
+#endif  /* AB_TU == 3 */
 
 }  // namespace AB_NS
 
 /* ------------------------------------------------------------------------ */
 /* launchers                                                                */
 /* ------------------------------------------------------------------------ */
-#if AB_STRICT
-#define AB_LAUNCH(name) name##_strict
-#else
-#define AB_LAUNCH(name) name##_fast
-#endif
-
 using namespace AB_NS;
 
-cudaError_t AB_LAUNCH(ab_upload_constants)() {
+/* every translation unit has its own copy of the IAS15 tables in constant memory */
+cudaError_t AB_CAT3(ab_upload_constants, AB_SFX, AB_TU)() {
     cudaError_t e;
     if ((e = cudaMemcpyToSymbol(c_h, AB_H, sizeof(AB_H))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_rr, AB_RR, sizeof(AB_RR))) != cudaSuccess) return e;
+    double rri[28];
+    for (int k = 0; k < 28; k++) rri[k] = 1.0 / AB_RR[k];
+    if ((e = cudaMemcpyToSymbol(c_rri, rri, sizeof(rri))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_c, AB_C, sizeof(AB_C))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_d, AB_D, sizeof(AB_D))) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
-cudaError_t AB_LAUNCH(ab_launch_ephem_eval)(const AbEphem& E, const double* t, int n_t, double* out, int* status, cudaStream_t st) {
+#if AB_TU == 0
+cudaError_t AB_CAT2(ab_launch_ephem_eval, AB_SFX)(const AbEphem& E, const double* t, int n_t, double* out, int* status, cudaStream_t st) {
     const long long total = (long long)n_t * (AB_NPLANETS + E.n_ast);
     const int grid = (int)((total + AB_BLOCK - 1) / AB_BLOCK);
     ephem_eval_kernel<<<grid, AB_BLOCK, 0, st>>>(E, t, n_t, out, status);
     return cudaGetLastError();
 }
 
-cudaError_t AB_LAUNCH(ab_launch_force_eval)(const AbEphem& E, const AbForceOpts& F, int n, int K, const double* t, int t_per_system,
-                                            const double* state, const double* params, double* acc, int* status, cudaStream_t st) {
+cudaError_t AB_CAT2(ab_launch_force_eval, AB_SFX)(const AbEphem& E, const AbForceOpts& F, int n, int K, const double* t, int t_per_system,
+                                                  const double* state, const double* params, double* acc, int* status, cudaStream_t st) {
     const int grid = (n + AB_BLOCK - 1) / AB_BLOCK;
     force_eval_kernel<<<grid, AB_BLOCK, 0, st>>>(E, F, n, K, t, t_per_system, state, params, acc, status);
     return cudaGetLastError();
 }
+#endif
 
-cudaError_t AB_LAUNCH(ab_launch_pp_integrate)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, double tmax, int exact, cudaStream_t st) {
-    const int grid = (Bt.n + AB_BLOCK - 1) / AB_BLOCK;
-    pp_integrate_kernel<<<grid, AB_BLOCK, 0, st>>>(E, F, Bt, tmax, exact);
+#if AB_TU == 1 || AB_TU == 2
+#if AB_TU == 1
+#define PP_NAME(x) AB_CAT2(x##_k1, AB_SFX)
+#else
+#define PP_NAME(x) AB_CAT2(x##_kv, AB_SFX)
+#endif
+cudaError_t PP_NAME(ab_launch_pp_integrate)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, double tmax, int exact, int resume,
+                                            long long step_cap, const int* active, int n_active, cudaStream_t st) {
+    const int grid = (n_active + AB_BLOCK - 1) / AB_BLOCK;
+    if (grid < 1) return cudaSuccess;
+    pp_integrate_kernel<<<grid, AB_BLOCK, 0, st>>>(E, F, Bt, tmax, exact, resume, step_cap, active, n_active);
     return cudaGetLastError();
 }
 
-cudaError_t AB_LAUNCH(ab_launch_pp_dense)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const double* times, int n_times, double* out, cudaStream_t st) {
+cudaError_t PP_NAME(ab_launch_pp_dense)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const double* times, int n_times, double* out, cudaStream_t st) {
     const int grid = (Bt.n + AB_BLOCK - 1) / AB_BLOCK;
     pp_dense_kernel<<<grid, AB_BLOCK, 0, st>>>(E, F, Bt, times, n_times, out);
     return cudaGetLastError();
 }
+#endif
 
-cudaError_t AB_LAUNCH(ab_launch_sh_integrate)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, double tmax, int exact, long long max_steps, int flags, cudaStream_t st) {
+#if AB_TU == 3
+cudaError_t AB_CAT2(ab_launch_sh_integrate, AB_SFX)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, double tmax, int exact, long long max_steps, int flags, cudaStream_t st) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e;
+    void* kern = (Bt.K == 1) ? (void*)sh_integrate_kernel_k1 : (void*)sh_integrate_kernel_kv;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sh_integrate_kernel, AB_BLOCK, 0)) != cudaSuccess) return e;
+    if (Bt.K == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sh_integrate_kernel_k1, AB_BLOCK, 0);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sh_integrate_kernel_kv, AB_BLOCK, 0);
+    if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     int grid = (Bt.n + AB_BLOCK - 1) / AB_BLOCK;
     const int max_grid = sms * per_sm;      /* every CTA must be resident: the kernel spins on a grid barrier */
@@ -483,11 +621,12 @@ cudaError_t AB_LAUNCH(ab_launch_sh_integrate)(const AbEphem& E, const AbForceOpt
     if (grid < 1) grid = 1;
     long long ms = max_steps;
     void* args[] = {(void*)&E, (void*)&F, (void*)&Bt, (void*)&tmax, (void*)&exact, (void*)&ms, (void*)&flags};
-    return cudaLaunchCooperativeKernel((void*)sh_integrate_kernel, dim3(grid), dim3(AB_BLOCK), args, 0, st);
+    return cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(AB_BLOCK), args, 0, st);
 }
 
-cudaError_t AB_LAUNCH(ab_launch_sh_interpolate)(const AbBatch& Bt, double dt_last_done, double h, double* out, cudaStream_t st) {
+cudaError_t AB_CAT2(ab_launch_sh_interpolate, AB_SFX)(const AbBatch& Bt, double dt_last_done, double h, double* out, cudaStream_t st) {
     const int grid = (Bt.n + AB_BLOCK - 1) / AB_BLOCK;
     sh_interpolate_kernel<<<grid, AB_BLOCK, 0, st>>>(Bt, dt_last_done, h, out);
     return cudaGetLastError();
 }
+#endif

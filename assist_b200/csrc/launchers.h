@@ -6,16 +6,25 @@
 #include "device_types.h"
 
 #define AB_DECLARE_LAUNCHERS(sfx)                                                                                   \
-    cudaError_t ab_upload_constants_##sfx();                                                                        \
+    cudaError_t ab_upload_constants_##sfx##_tu0();                                                                  \
+    cudaError_t ab_upload_constants_##sfx##_tu1();                                                                  \
+    cudaError_t ab_upload_constants_##sfx##_tu2();                                                                  \
+    cudaError_t ab_upload_constants_##sfx##_tu3();                                                                  \
     cudaError_t ab_launch_ephem_eval_##sfx(const AbEphem& E, const double* t, int n_t, double* out, int* status,   \
                                            cudaStream_t st);                                                        \
     cudaError_t ab_launch_force_eval_##sfx(const AbEphem& E, const AbForceOpts& F, int n, int K, const double* t,  \
                                            int t_per_system, const double* state, const double* params,            \
                                            double* acc, int* status, cudaStream_t st);                             \
-    cudaError_t ab_launch_pp_integrate_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt,            \
-                                             double tmax, int exact, cudaStream_t st);                             \
-    cudaError_t ab_launch_pp_dense_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt,                \
-                                         const double* times, int n_times, double* out, cudaStream_t st);          \
+    cudaError_t ab_launch_pp_integrate_k1_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt,         \
+                                                double tmax, int exact, int resume, long long step_cap,            \
+                                                const int* active, int n_active, cudaStream_t st);                 \
+    cudaError_t ab_launch_pp_integrate_kv_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt,         \
+                                                double tmax, int exact, int resume, long long step_cap,            \
+                                                const int* active, int n_active, cudaStream_t st);                 \
+    cudaError_t ab_launch_pp_dense_k1_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt,             \
+                                            const double* times, int n_times, double* out, cudaStream_t st);       \
+    cudaError_t ab_launch_pp_dense_kv_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt,             \
+                                            const double* times, int n_times, double* out, cudaStream_t st);       \
     cudaError_t ab_launch_sh_integrate_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt,            \
                                              double tmax, int exact, long long max_steps, int flags,               \
                                              cudaStream_t st);                                                     \

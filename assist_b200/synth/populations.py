@@ -62,8 +62,44 @@ def _to_bary(helio):
     return helio + _sun_state()[None, :]
 
 
+def _planet_positions(t0_jd=T0_JD):
+    """Barycentric positions (AU) and Hill radii (AU) of the nine planet barycentres at t0."""
+    m = SolarSystemModel()
+    pos, hill = [], []
+    for name, el in m.planets.items():
+        pos.append(m.position(name, np.array([t0_jd]))[:, 0] / AU_KM)
+        hill.append(el["a"] * (el["gm"] / (3.0 * GMS)) ** (1.0 / 3.0))
+    return np.array(pos), np.array(hill)
+
+
+def _outside_hill_spheres(state, factor=3.0):
+    """True for particles that start farther than `factor` Hill radii from every planet.
+
+    Random orbital elements occasionally put a particle INSIDE a planet's Hill sphere with a
+    small relative velocity, i.e. on a satellite orbit (period ~ hours).  Such an object is not
+    a heliocentric small body; it is rejected at generation time (documented in DESIGN.md)."""
+    pos, hill = _planet_positions()
+    d = np.linalg.norm(state[:, None, :3] - pos[None, :, :], axis=-1)
+    return np.all(d > factor * hill[None, :], axis=1)
+
+
+def _filtered(gen, n, seed):
+    """Draw from gen(m, seed) until n particles pass the Hill-sphere filter (deterministic)."""
+    out = np.empty((0, 6))
+    k = 0
+    while out.shape[0] < n:
+        cand = gen(n - out.shape[0] + 64, seed + 7919 * k)
+        out = np.concatenate([out, cand[_outside_hill_spheres(cand)]], axis=0)
+        k += 1
+    return out[:n]
+
+
 def main_belt(n, seed=20261702):
     """C2 / C4: a~U[2.1,3.3], e~Rayleigh(0.1) clipped 0.3, i~Rayleigh(8 deg)."""
+    return _filtered(_main_belt_raw, n, seed)
+
+
+def _main_belt_raw(n, seed):
     rng = np.random.default_rng(seed)
     a = rng.uniform(2.1, 3.3, n)
     e = np.clip(rng.rayleigh(0.1, n), 0.0, 0.3)
@@ -74,6 +110,10 @@ def main_belt(n, seed=20261702):
 
 def neo(n, seed=20261703):
     """NEO part of C3: a~U[0.8,2.5], e~U[0.2,0.7], q<1.3, i~Rayleigh(12 deg)."""
+    return _filtered(_neo_raw, n, seed)
+
+
+def _neo_raw(n, seed):
     rng = np.random.default_rng(seed)
     a = np.empty(n); e = np.empty(n)
     filled = 0

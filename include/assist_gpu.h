@@ -127,6 +127,12 @@ int assist_gpu_batch_set_time(assist_gpu_batch* b, double t, double dt);
 /* Dense output inside the last completed step (shared-step mode): out[n_sys][K][6]. */
 int assist_gpu_batch_interpolate(assist_gpu_batch* b, double h, double* out);
 int assist_gpu_batch_get_stats(assist_gpu_batch* b, struct assist_gpu_stats* stats);
+/* Per-system counters of a per-particle batch (each array n_sys long; any may be NULL). */
+int assist_gpu_batch_get_counters(assist_gpu_batch* b, unsigned long long* steps, unsigned long long* rejected,
+                                  unsigned long long* iters, unsigned long long* evals);
+/* Page-locked host memory for state / output buffers (cudaHostAlloc). */
+void* assist_gpu_host_alloc(size_t bytes);
+void assist_gpu_host_free(void* p);
 /* Peak FP64 FMA rate of the current device measured with a register-resident DFMA loop (TFLOP/s). */
 double assist_gpu_measure_fp64_peak(int iters);
 

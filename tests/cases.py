@@ -1,0 +1,66 @@
+"""Seeded test cases shared by the golden generator and the parity tests."""
+import numpy as np
+
+from assist_b200.synth import populations
+
+T0 = populations.T0
+
+# times relative to jd_ref: inside, near both ends of coverage, on record boundaries (8455.5+200.0 hits a
+# 16-day and an 8-day boundary of the synthetic files), and one negative
+EPHEM_TIMES = np.array([T0, T0 + 17.3, T0 - 1234.56789, T0 + 3000.25, -10000.0, T0 + 200.0, T0 + 199.99999, 13455.0, -10544.5])
+
+FORCE_T = T0 + 3.7
+# name, mask, gr_eih_sources, geocentric
+FORCE_TERMS = [
+    ("sun", 0x01, 1, 0), ("planets", 0x02, 1, 0), ("asteroids", 0x04, 1, 0), ("nongrav", 0x08, 1, 0),
+    ("earth_harm", 0x10, 1, 0), ("sun_harm", 0x20, 1, 0), ("eih1", 0x40, 1, 0), ("eih11", 0x40, 11, 0),
+    ("gr_simple", 0x80, 1, 0), ("gr_potential", 0x100, 1, 0), ("default", 0x7F, 1, 0), ("all11", 0x7F, 11, 0),
+    ("geocentric", 0x7F, 1, 1),
+]
+
+PP_DAYS = 400.0
+VAR_DAYS = 200.0
+SH_DAYS = 300.0
+DENSE_TIMES = T0 - 10.0 * np.arange(1, 40)
+
+
+def force_case(n=64):
+    """Systems with 6 variational particles (random variations) and non-zero A1..A3 / dA."""
+    st6 = populations.neo_mba_mix(n, seed=5)
+    state = populations.with_variations(st6, 6)
+    rng = np.random.default_rng(3)
+    state[:, 1:, :] += 0.1 * rng.standard_normal(state[:, 1:, :].shape)
+    params = np.zeros((n, 7, 3))
+    params[:, 0, :] = [1e-9, -2e-10, 3e-11]
+    params[:, 1:, :] = rng.standard_normal((n, 6, 3))
+    # a few particles without non-gravitational parameters (reference skips them, src/forces.c:861)
+    params[::7, 0, :] = 0.0
+    return state, params
+
+
+def pp_case(n=16):
+    return populations.neo_mba_mix(n, seed=11)
+
+
+def var_case(n=8):
+    return populations.with_variations(populations.main_belt(n, seed=13), 6)
+
+
+def shared_case(n=40):
+    return populations.main_belt(n, seed=17)
+
+
+def shared_var_case():
+    """Two real particles, the first with two variational particles, the second with one
+    (layout of reference unit_tests/variational_spk/problem.c, extended)."""
+    st = populations.main_belt(2, seed=23)
+    out = np.zeros((2, 3, 6))
+    out[:, 0, :] = st
+    out[0, 1, 0] = 1.0
+    out[0, 2, 4] = 1.0
+    out[1, 1, 2] = 1.0
+    return out
+
+
+def comet_case(n=6):
+    return populations.comets(n, seed=19)

@@ -1,0 +1,187 @@
+"""CPU tests of the ORACLE: the reference's own C code (oracle/_ref) driven by the IAS15
+restatement (oracle/reb_shim.c), pinned against the committed golden vectors and against
+the data-independent invariants of the reference's own test-suite."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+import refharness as rh
+from conftest import ROOT, planets_path, relerr
+from assist_b200.cstructs import Particle
+from assist_b200.synth import populations
+
+AU_M = 149597870700.0
+
+
+@pytest.fixture(scope="module")
+def reph(ref, paths, fmt):
+    return rh.open_ephem(ref, planets_path(paths, fmt), paths["asteroids_bsp"])
+
+
+def test_ias15_constants_are_derived_and_pinned(tmp_path):
+    """gen_ias15_constants.py asserts the published h[] and the SURVEY App. A known doubles."""
+    out = tmp_path / "c.h"
+    subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "gen_ias15_constants.py"), str(out), "T"], check=True)
+    txt = out.read_text()
+    assert txt.count("0x") == 78
+    # the committed headers of the oracle and of the product hold the same numbers
+    a = open(os.path.join(ROOT, "oracle", "ias15_constants.h")).read().replace("ORC_", "X_")
+    b = open(os.path.join(ROOT, "assist_b200", "csrc", "ias15_constants.h")).read().replace("AB_", "X_")
+    assert a == b
+
+
+def test_reference_reproduces_golden(ref, reph, fmt, golden):
+    """The golden files are exactly what the reference build produces today (bit for bit)."""
+    g = golden[fmt]
+    out, st = rh.all_bodies(ref, reph, cases.EPHEM_TIMES)
+    assert np.array_equal(np.nan_to_num(out, nan=-7), np.nan_to_num(g["ephem"], nan=-7))
+    assert np.array_equal(st, g["ephem_status"])
+    state, params = cases.force_case()
+    for name, mask, src, geo in cases.FORCE_TERMS:
+        a = rh.forces(ref, reph, cases.FORCE_T, state, params, forces=mask, gr_eih_sources=src, geocentric=geo)
+        assert np.array_equal(a, g["force_" + name]), name
+    fin, ts, _, cnt = rh.integrate_each(ref, reph, cases.T0, cases.pp_case(), cases.T0 + cases.PP_DAYS, forces=0x7F)
+    assert np.array_equal(fin, g["pp_final"]) and np.array_equal(ts, g["pp_t"])
+    assert cnt["steps"] == g["pp_counts"][0]
+
+
+def test_ephemeris_formats_agree(ref, paths):
+    """SPK and DE-binary providers hold the same Chebyshev data: same states (reference
+    unit_tests/apophis_drift checks the same thing on real files)."""
+    a = rh.open_ephem(ref, paths["planets_bsp"], paths["asteroids_bsp"])
+    b = rh.open_ephem(ref, paths["de440"], paths["asteroids_bsp"])
+    oa, _ = rh.all_bodies(ref, a, cases.EPHEM_TIMES[:4])
+    ob, _ = rh.all_bodies(ref, b, cases.EPHEM_TIMES[:4])
+    assert np.allclose(oa[:, :, :4], ob[:, :, :4], rtol=0, atol=1e-14)
+    assert a.contents.AU == b.contents.AU and a.contents.EMRAT == b.contents.EMRAT
+    assert a.contents.over_c_squared == b.contents.over_c_squared
+
+
+def test_time_bounds_and_coverage_error(ref, reph):
+    tb, te = ctypes.c_double(), ctypes.c_double()
+    ref.assist_ephem_time_bounds(reph, tb, te)
+    assert (tb.value, te.value) == (-10544.5, 13455.5)
+    err = ctypes.c_int(0)
+    ref.assist_get_particle_with_error(reph, 0, 20000.0, err)
+    assert err.value == 5      # ASSIST_ERROR_COVERAGE
+
+
+def test_invariant_cache_on_off_bit_identical(ref, reph):
+    """reference unit_tests/ephem_cache/problem.c: the 7-slot cache must not change a single bit."""
+    st = np.array([[3.3388753502614090e+00, -9.1765182678903168e-01, -5.0385906775843303e-01,
+                    2.8056633153049852e-03, 7.5504086883996860e-03, 2.9800282074358684e-03]])
+    for direction in (1, -1):
+        res = []
+        for use_cache in (False, True):
+            s = rh.Sim(ref, reph, cases.T0, st)
+            if not use_cache:
+                s.ax.contents.ephem_cache = None
+            s.integrate(cases.T0 + direction * 1000)
+            assert s.t == cases.T0 + direction * 1000
+            res.append(s.state())
+            s.close()
+        assert np.array_equal(res[0], res[1])
+
+
+def test_invariant_roundtrip_fixed_step(ref, reph):
+    """reference unit_tests/roundtrip_spk/problem.c: dt = 10, epsilon = 0, out and back."""
+    x0 = np.array([3.3388753502614090e+00, -9.1765182678903168e-01, -5.0385906775843303e-01,
+                   2.8056633153049852e-03, 7.5504086883996860e-03, 2.9800282074358684e-03])
+    for trange, tol_m in ((100, 1e-4), (1000, 1e-3), (4000, 5e-3)):       # the synthetic files end 5000 d after T0
+        s = rh.Sim(ref, reph, cases.T0, x0[None, :], epsilon=0.0, dt0=10.0)
+        count = 0
+        while s.t < cases.T0 + trange:
+            ref.reb_simulation_step(s.r)
+            count += 1
+        s.r.contents.dt *= -1
+        for _ in range(count):
+            ref.reb_simulation_step(s.r)
+        assert s.t == cases.T0
+        d = np.linalg.norm(s.state()[0, 0, :3] - x0[:3]) * AU_M
+        assert d < tol_m, (trange, d)
+        s.close()
+
+
+def test_invariant_roundtrip_adaptive(ref, reph):
+    """reference unit_tests/roundtrip_adaptive_spk/problem.c: three particles, adaptive, out and back."""
+    base = np.array([3.3388753502614090e+00, -9.1765182678903168e-01, -5.0385906775843303e-01,
+                     5.22000300435103972568e-03, 6.56760310074497024591e-03, 2.44038701006633581073e-03])
+    st = np.tile(base, (3, 1))
+    st[:, 3] += np.arange(3) / 1e4
+    for trange, tol_m in ((100, 1e-2), (1000, 5e-2), (4000, 1e-1)):
+        s = rh.Sim(ref, reph, cases.T0, st)
+        s.integrate(cases.T0 + trange)
+        s.integrate(cases.T0)
+        assert s.t == cases.T0
+        d = np.mean(np.linalg.norm(s.state()[:, 0, :3] - st[:, :3], axis=1)) * AU_M
+        assert d < tol_m, (trange, d)
+        s.close()
+
+
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_invariant_onthefly_interpolation(ref, reph, sign):
+    """reference unit_tests/onthefly_(backwards_)interpolation: dense output equals direct integration to 2e-13 AU."""
+    st = np.array([[-2.724183384883979E+00, -3.523994546329214E-02, 9.036596202793466E-02,
+                    -1.374545432301129E-04, -1.027075301472321E-02, -4.195690627695180E-03]])
+    step = 40.0 if sign > 0 else 10.0
+    ts = cases.T0 + sign * step * np.arange(1, 21)
+    s1 = rh.Sim(ref, reph, cases.T0, st)
+    direct = []
+    for t in ts:
+        s1.integrate(t)
+        direct.append(s1.state()[0, 0, 0])
+    s2 = rh.Sim(ref, reph, cases.T0, st)
+    interp = [s2.integrate_or_interpolate(t)[0, 0, 0] for t in ts]
+    assert np.max(np.abs(np.array(direct) - np.array(interp))) < 2e-13
+    s1.close(); s2.close()
+
+
+def test_invariant_variational_vs_finite_difference(ref, reph):
+    """reference unit_tests/variational_spk/problem.c: variational particle vs 10 m shadow particle, 1e-5."""
+    p0 = np.array([-2.724183384883979E+00, -3.523994546329214E-02, 9.036596202793466E-02,
+                   -1.374545432301129E-04, -1.027075301472321E-02, -4.195690627695180E-03])
+    dx = 10.0 / AU_M
+    lib = ref
+    r = lib.reb_simulation_create()
+    ax = lib.assist_attach(r, reph)
+    r.contents.t = cases.T0
+    lib.reb_simulation_add(r, Particle(x=p0[0], y=p0[1], z=p0[2], vx=p0[3], vy=p0[4], vz=p0[5]))
+    lib.reb_simulation_add(r, Particle(x=p0[0] + dx, y=p0[1], z=p0[2], vx=p0[3], vy=p0[4], vz=p0[5]))
+    var = lib.reb_simulation_add_variation_1st_order(r, 0)
+    r.contents.particles[var].x = 1.0
+    for span in (1.0, 100.0):
+        lib.reb_simulation_integrate(r, r.contents.t + span)
+        P = r.contents.particles
+        d1 = P[1].x - P[0].x
+        d2 = P[var].x * dx
+        assert abs((d1 - d2) / d1) < 1e-5
+    lib.assist_free(ax)
+    lib.reb_simulation_free(r)
+
+
+def test_gr_moves_orbit_by_about_100m(ref, reph):
+    """reference assist/test/test_forces.py:58: dropping GR_EIH moves a main-belt orbit ~100 m in 60 d."""
+    st = np.array([[-2.724183384883979E+00, -3.523994546329214E-02, 9.036596202793466E-02,
+                    -1.374545432301129E-04, -1.027075301472321E-02, -4.195690627695180E-03]])
+    out = []
+    for mask in (0x7F, 0x7F & ~0x40):
+        s = rh.Sim(ref, reph, cases.T0, st, forces=mask)
+        s.integrate(cases.T0 + 60.0)
+        out.append(s.state()[0, 0, :3])
+        s.close()
+    d = np.linalg.norm(out[0] - out[1]) * AU_M
+    assert 50.0 < d < 200.0, d
+
+
+def test_min_dt_clamp_and_c1_counts(golden):
+    """C1 (Apophis-like, 11 EIH sources, non-grav, min_dt 1e-3) completed and stayed finite."""
+    for tag in ("bsp", "440"):
+        g = golden[tag]
+        assert np.isfinite(g["c1_final"]).all()
+        assert g["c1_t"][0] == cases.T0 + 3652.5
+        assert g["c1_counts"][0] > 100

@@ -1,0 +1,332 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the oracle.
+
+Oracle = the committed golden vectors (tests/golden/*.npz, generated from the reference's own
+C code) and, when it travelled to the box, the reference build itself (oracle/_ref).
+
+Tolerances (north star): every force term <= 1e-14 relative; integrated positions <= 1e-12 AU.
+The strict math variant is additionally required to be BIT-IDENTICAL to the reference wherever
+the reference does not call pow() (only the Marsden non-gravitational term does)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import refharness as rh
+from conftest import ROOT, planets_path, relerr
+from assist_b200 import batch as ab
+from assist_b200.cstructs import Particle
+from assist_b200.synth import populations
+
+pytestmark = pytest.mark.gpu
+
+TERM_TOL = 1e-14
+POS_TOL_AU = 1e-12
+
+
+@pytest.fixture(scope="module")
+def eph(paths, fmt, lib):
+    if lib.assist_gpu_device_count() < 1:
+        pytest.fail("GPU tests need a CUDA device: assist-b200 has no CPU path")
+    return ab.EphemHandle(planets_path(paths, fmt), paths["asteroids_bsp"])
+
+
+def same(a, b):
+    return np.array_equal(np.nan_to_num(a, nan=-7.0), np.nan_to_num(b, nan=-7.0))
+
+
+# ------------------------------------------------------------------ ephemeris
+def test_ephemeris_bit_identical(eph, fmt, golden):
+    g = golden[fmt]
+    for math in (ab.MATH_STRICT, ab.MATH_FAST):
+        out, st = eph.eval(cases.EPHEM_TIMES, math=math)
+        assert np.array_equal(st, g["ephem_status"])
+        ok = g["ephem_status"] == 0
+        if math == ab.MATH_STRICT:
+            assert same(out[ok], g["ephem"][ok])
+        else:
+            assert np.nanmax(np.abs(out[ok][:, 1:4] - g["ephem"][ok][:, 1:4])) < 1e-14
+
+
+def test_ephemeris_against_reference_build(eph, fmt, ref, paths):
+    reph = rh.open_ephem(ref, planets_path(paths, fmt), paths["asteroids_bsp"])
+    rng = np.random.default_rng(1)
+    times = np.sort(rng.uniform(-10544.0, 13455.0, 200))
+    out, st = eph.eval(times)
+    rout, rst = rh.all_bodies(ref, reph, times)
+    assert np.array_equal(st, rst) and same(out, rout)
+
+
+# ------------------------------------------------------------------ force terms
+@pytest.mark.parametrize("term", [t[0] for t in cases.FORCE_TERMS])
+def test_force_terms(eph, fmt, golden, term):
+    name, mask, src, geo = [t for t in cases.FORCE_TERMS if t[0] == term][0]
+    state, params = cases.force_case()
+    want = golden[fmt]["force_" + name]
+    got = ab.eval_forces(eph, cases.FORCE_T, state, params, forces=mask, gr_eih_sources=src, geocentric=geo)
+    assert relerr(got, want) <= TERM_TOL, name
+    if not (mask & 0x08):
+        assert np.array_equal(got, want), "strict math must reproduce the reference bit for bit (%s)" % name
+    fast = ab.eval_forces(eph, cases.FORCE_T, state, params, forces=mask, gr_eih_sources=src, geocentric=geo, math=ab.MATH_FAST)
+    assert relerr(fast, want) <= TERM_TOL, name
+
+
+def test_forces_per_system_times_and_no_params(eph, fmt, ref, paths):
+    """Each system at its own time (per-particle mode's evaluation), particle_params == NULL."""
+    reph = rh.open_ephem(ref, planets_path(paths, fmt), paths["asteroids_bsp"])
+    st = populations.with_variations(populations.neo_mba_mix(12, seed=77), 6)
+    times = cases.T0 + np.linspace(-900.0, 2500.0, 12)
+    got = ab.eval_forces(eph, times, st, None, forces=0x7F, gr_eih_sources=3)
+    for i in range(12):
+        want = rh.forces(ref, reph, times[i], st[i:i + 1], None, forces=0x7F, gr_eih_sources=3)
+        assert np.array_equal(got[i:i + 1], want)
+
+
+# ------------------------------------------------------------------ per-particle IAS15
+def test_per_particle_integration_bit_identical(eph, fmt, golden):
+    g = golden[fmt]
+    st = cases.pp_case()
+    b = ab.Batch(eph, st.shape[0], 0, ab.PER_PARTICLE, forces=0x7F)
+    b.set_state(cases.T0, st[:, None, :])
+    b.integrate(cases.T0 + cases.PP_DAYS)
+    got = b.get_state()
+    assert np.array_equal(got["state"], g["pp_final"])
+    assert np.array_equal(got["t"], g["pp_t"]) and np.array_equal(got["dt"], g["pp_dt"])
+    s = b.stats()
+    assert [s["steps"], s["pc_iterations"], s["force_evals"], s["steps_rejected"]] == list(g["pp_counts"])
+    assert (got["status"] == 0).all()
+
+
+def test_per_particle_fast_math_within_tolerance(eph, fmt, golden):
+    g = golden[fmt]
+    st = cases.pp_case()
+    b = ab.Batch(eph, st.shape[0], 0, ab.PER_PARTICLE, forces=0x7F, math=ab.MATH_FAST)
+    b.set_state(cases.T0, st[:, None, :])
+    b.integrate(cases.T0 + cases.PP_DAYS)
+    d = np.linalg.norm(b.get_state()["state"][:, 0, :3] - g["pp_final"][:, 0, :3], axis=-1)
+    assert d.max() <= POS_TOL_AU
+
+
+def test_per_particle_backward(eph, fmt, golden):
+    g = golden[fmt]
+    st = cases.pp_case()[:6]
+    b = ab.Batch(eph, 6, 0, ab.PER_PARTICLE, forces=0x7F)
+    b.set_state(cases.T0, st[:, None, :])
+    b.integrate(cases.T0 - 300.0)
+    got = b.get_state()
+    assert np.array_equal(got["state"], g["ppback_final"]) and np.array_equal(got["t"], g["ppback_t"])
+
+
+def test_per_particle_variational(eph, fmt, golden):
+    g = golden[fmt]
+    stv = cases.var_case()
+    b = ab.Batch(eph, stv.shape[0], 6, ab.PER_PARTICLE, forces=0x7F)
+    b.set_state(cases.T0, stv)
+    b.integrate(cases.T0 + cases.VAR_DAYS)
+    got = b.get_state()
+    assert np.array_equal(got["state"], g["var_final"]) and np.array_equal(got["t"], g["var_t"])
+
+
+def test_c1_apophis_like_ten_years(eph, fmt, golden):
+    """BASELINE config 1: all forces, 11 EIH sources, Marsden A1/A2, min_dt 1e-3, 10 yr (pow() in the path)."""
+    g = golden[fmt]
+    c1, prm = populations.apophis_like()
+    b = ab.Batch(eph, 1, 0, ab.PER_PARTICLE, forces=0x7F, gr_eih_sources=11, min_dt=1e-3)
+    b.set_state(cases.T0, c1[:, None, :], params=prm[:, None, :])
+    b.integrate(cases.T0 + 3652.5)
+    got = b.get_state()
+    assert got["t"][0] == g["c1_t"][0]
+    assert np.linalg.norm(got["state"][0, 0, :3] - g["c1_final"][0, 0, :3]) <= POS_TOL_AU
+
+
+def test_step_cap_does_not_change_results(eph, fmt, golden, monkeypatch):
+    """Pausing and resuming integrate() every few steps (straggler packing) is invisible in the results."""
+    g = golden[fmt]
+    st = cases.pp_case()
+    for cap in ("0", "1", "5"):
+        monkeypatch.setenv("ASSIST_B200_STEP_CAP", cap)
+        b = ab.Batch(eph, st.shape[0], 0, ab.PER_PARTICLE, forces=0x7F)
+        b.set_state(cases.T0, st[:, None, :])
+        b.integrate(cases.T0 + cases.PP_DAYS)
+        assert np.array_equal(b.get_state()["state"], g["pp_final"]), cap
+        b.close()
+
+
+# ------------------------------------------------------------------ shared step
+def test_shared_step_bit_identical(eph, fmt, golden):
+    g = golden[fmt]
+    st = cases.shared_case()
+    b = ab.Batch(eph, st.shape[0], 0, ab.SHARED_STEP, forces=0x77)
+    b.set_state(cases.T0, st[:, None, :])
+    b.integrate(cases.T0 + cases.SH_DAYS)
+    got = b.get_state()
+    assert np.array_equal(got["state"], g["sh_final"])
+    assert [got["t"][0], got["dt"][0], got["dt_last_done"][0]] == list(g["sh_t_dt"])
+    s = b.stats()
+    assert [s["steps"], s["pc_iterations"], s["steps_rejected"]] == [g["sh_counts"][0], g["sh_counts"][1], g["sh_counts"][3]]
+
+
+def test_shared_step_with_variational(eph, fmt, golden):
+    g = golden[fmt]
+    shv = cases.shared_var_case()
+    b = ab.Batch(eph, 2, 2, ab.SHARED_STEP, forces=0x7F)
+    b.set_state(cases.T0, shv)
+    b.integrate(cases.T0 + 101.0)
+    assert np.array_equal(b.get_state()["state"], g["shv_final"])
+
+
+def test_shared_step_many_ctas_matches_reference(eph, fmt, ref, paths):
+    """More systems than one CTA holds: grid-wide reductions must give the reference's dt sequence."""
+    reph = rh.open_ephem(ref, planets_path(paths, fmt), paths["asteroids_bsp"])
+    st = populations.main_belt(700, seed=31)
+    s = rh.Sim(ref, reph, cases.T0, st, forces=0x77)
+    s.integrate(cases.T0 + 90.0)
+    b = ab.Batch(eph, 700, 0, ab.SHARED_STEP, forces=0x77)
+    b.set_state(cases.T0, st[:, None, :])
+    b.integrate(cases.T0 + 90.0)
+    got = b.get_state()
+    assert np.array_equal(got["state"], s.state()) and got["t"][0] == s.t and got["dt"][0] == s.dt
+    s.close()
+
+
+# ------------------------------------------------------------------ dense output
+def test_dense_output_comets(eph, fmt, golden):
+    """BASELINE config 5 in small: Marsden comets, backward, assist_integrate_or_interpolate semantics."""
+    g = golden[fmt]
+    stc, prm = cases.comet_case()
+    b = ab.Batch(eph, stc.shape[0], 0, ab.PER_PARTICLE, forces=0x7F)
+    b.set_state(cases.T0, stc[:, None, :], params=prm[:, None, :])
+    out = b.integrate_or_interpolate(cases.DENSE_TIMES)
+    assert np.nanmax(np.linalg.norm(out[..., :3] - g["dense"][..., :3], axis=-1)) <= POS_TOL_AU
+    assert np.isfinite(out).all()
+
+
+# ------------------------------------------------------------------ the drop-in C API
+def _product_sim(lib, ephptr, t0, state, forces=None):
+    r = lib.reb_simulation_create()
+    ax = lib.assist_attach(r, ephptr)
+    r.contents.t = t0
+    for s in state:
+        lib.reb_simulation_add(r, Particle(x=s[0], y=s[1], z=s[2], vx=s[3], vy=s[4], vz=s[5]))
+    if forces is not None:
+        ax.contents.forces = forces
+    return r, ax
+
+
+def test_dropin_reb_simulation_integrate(eph, fmt, golden, lib):
+    """reb_simulation_create / assist_attach / reb_simulation_add / reb_simulation_integrate on the PRODUCT library."""
+    g = golden[fmt]
+    st = cases.shared_case()
+    r, ax = _product_sim(lib, eph.ptr, cases.T0, st, forces=0x77)
+    status = lib.reb_simulation_integrate(r, cases.T0 + cases.SH_DAYS)
+    s = r.contents
+    assert status == 0 and s.t == g["sh_t_dt"][0] and s.dt == g["sh_t_dt"][1] and s.dt_last_done == g["sh_t_dt"][2]
+    got = np.array([[s.particles[i].x, s.particles[i].y, s.particles[i].z, s.particles[i].vx, s.particles[i].vy, s.particles[i].vz]
+                    for i in range(st.shape[0])])
+    assert np.array_equal(got, g["sh_final"][:, 0, :])
+    assert s.steps_done == g["sh_counts"][0]
+    lib.assist_free(ax)
+    lib.reb_simulation_free(r)
+
+
+def test_dropin_variational_and_two_calls(eph, fmt, ref, paths, lib):
+    """reference unit_tests/variational_spk layout run on both libraries, two consecutive integrate calls."""
+    reph = rh.open_ephem(ref, planets_path(paths, fmt), paths["asteroids_bsp"])
+    p0 = np.array([-2.724183384883979E+00, -3.523994546329214E-02, 9.036596202793466E-02,
+                   -1.374545432301129E-04, -1.027075301472321E-02, -4.195690627695180E-03])
+    res = []
+    for L, E in ((ref, reph), (lib, eph.ptr)):
+        r = L.reb_simulation_create()
+        ax = L.assist_attach(r, E)
+        r.contents.t = cases.T0
+        L.reb_simulation_add(r, Particle(x=p0[0], y=p0[1], z=p0[2], vx=p0[3], vy=p0[4], vz=p0[5]))
+        L.reb_simulation_add(r, Particle(x=p0[0] + 1e-10, y=p0[1], z=p0[2], vx=p0[3], vy=p0[4], vz=p0[5]))
+        var = L.reb_simulation_add_variation_1st_order(r, 0)
+        r.contents.particles[var].x = 1.0
+        L.reb_simulation_integrate(r, cases.T0 + 1.0)
+        L.reb_simulation_integrate(r, r.contents.t + 100.0)
+        P = r.contents.particles
+        res.append([(P[i].x, P[i].y, P[i].z, P[i].vx, P[i].vy, P[i].vz) for i in range(3)] + [(r.contents.t, r.contents.dt, 0, 0, 0, 0)])
+        L.assist_free(ax)
+        L.reb_simulation_free(r)
+    assert np.array_equal(np.array(res[0]), np.array(res[1]))
+
+
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_dropin_integrate_or_interpolate(eph, fmt, ref, paths, lib, sign):
+    """assist_integrate_or_interpolate on the product library equals the reference at every epoch
+    (reference unit_tests/onthefly_interpolation and onthefly_backwards_interpolation)."""
+    reph = rh.open_ephem(ref, planets_path(paths, fmt), paths["asteroids_bsp"])
+    st = np.array([[-2.724183384883979E+00, -3.523994546329214E-02, 9.036596202793466E-02,
+                    -1.374545432301129E-04, -1.027075301472321E-02, -4.195690627695180E-03]])
+    ts = cases.T0 + sign * (40.0 if sign > 0 else 10.0) * np.arange(1, 21)
+    s = rh.Sim(ref, reph, cases.T0, st)
+    want = np.array([s.integrate_or_interpolate(t)[0, 0] for t in ts])
+    r, ax = _product_sim(lib, eph.ptr, cases.T0, st)
+    got = []
+    for t in ts:
+        lib.assist_integrate_or_interpolate(ax, float(t))
+        p = r.contents.particles[0]
+        got.append((p.x, p.y, p.z, p.vx, p.vy, p.vz))
+    assert np.array_equal(np.array(got), want)
+    lib.assist_free(ax)
+    lib.reb_simulation_free(r)
+    s.close()
+
+
+def test_dropin_get_particle_and_update_acceleration(eph, fmt, golden, lib):
+    g = golden[fmt]
+    for body in (0, 3, 4, 10, 11, 26):
+        err = ctypes.c_int(0)
+        p = lib.assist_get_particle_with_error(eph.ptr, body, float(cases.EPHEM_TIMES[1]), err)
+        assert err.value == 0
+        want = g["ephem"][1, body]
+        assert (p.m, p.x, p.y, p.z) == tuple(want[:4])
+    err = ctypes.c_int(0)
+    lib.assist_get_particle_with_error(eph.ptr, 0, 20000.0, err)
+    assert err.value == 5
+    # assist_additional_forces through reb_simulation_update_acceleration
+    state, params = cases.force_case()
+    got = rh.forces(lib, eph.ptr, cases.FORCE_T, state[:, :3], params[:, :3], forces=0x77, gr_eih_sources=1)
+    want = ab.eval_forces(eph, cases.FORCE_T, state[:, :3], params[:, :3], forces=0x77, gr_eih_sources=1)
+    assert np.array_equal(got, want)
+
+
+def test_dropin_coverage_error_is_reported(eph, lib):
+    """Leaving the ephemeris coverage sets REB_STATUS_GENERIC_ERROR (reference src/forces.c:317-321)
+    instead of reading outside the tables."""
+    st = cases.shared_case()[:3]
+    r, ax = _product_sim(lib, eph.ptr, 13400.0, st)
+    status = lib.reb_simulation_integrate(r, 13600.0)
+    assert status == 1 and r.contents.t < 13455.5
+    lib.assist_free(ax)
+    lib.reb_simulation_free(r)
+
+
+# ------------------------------------------------------------------ size-independent properties at scale
+def test_properties_at_scale(eph, fmt):
+    """20 000 particles: results do not depend on the batch a particle is integrated in, nor on its
+    position in it; restore() reproduces a run exactly; out-and-back returns to the start."""
+    n = 20000
+    st = populations.neo_mba_mix(n, seed=99)
+    b = ab.Batch(eph, n, 0, ab.PER_PARTICLE, forces=0x7F, min_dt=1e-3)
+    b.set_state(cases.T0, st[:, None, :])
+    b.snapshot()
+    b.integrate(cases.T0 + 120.0)
+    full = b.get_state()["state"].copy()
+    assert np.isfinite(full).all()
+    b.restore()
+    b.integrate(cases.T0 + 120.0)
+    assert np.array_equal(b.get_state()["state"], full)
+    perm = np.random.default_rng(5).permutation(n)[:3000]
+    b2 = ab.Batch(eph, perm.size, 0, ab.PER_PARTICLE, forces=0x7F, min_dt=1e-3)
+    b2.set_state(cases.T0, st[perm][:, None, :])
+    b2.integrate(cases.T0 + 120.0)
+    assert np.array_equal(b2.get_state()["state"], full[perm])
+    # out and back (reference unit_tests/roundtrip_adaptive: metres after thousands of days; here 120 d)
+    b.integrate(cases.T0)
+    back = b.get_state()
+    assert (back["t"] == cases.T0).all()
+    d = np.linalg.norm(back["state"][:, 0, :3] - st[:, :3], axis=-1)
+    assert np.median(d) < 1e-13 and d.max() < 1e-9
