@@ -26,7 +26,17 @@
 #include "device_types.h"
 #include "fp_device.cuh"
 
+#ifndef AB_DIRECT_UNROLL
+#define AB_DIRECT_UNROLL 1
+#endif
+#ifndef AB_EIH_UNROLL
+#define AB_EIH_UNROLL 1
+#endif
+
 namespace AB_NS {
+
+constexpr int kDirectUnroll = AB_DIRECT_UNROLL;
+constexpr int kEihUnroll = AB_EIH_UNROLL;
 
 /* Positions/velocities/accelerations of one system in registers/local memory. */
 template <int KM>
@@ -437,13 +447,19 @@ __device__ void ab_force_eih(const AbEphem& E, const AbForceOpts& F, const BT& B
 
     /* sum over the 11 planets of GM_k / r_ik: identical for every source j (src/forces.c:1400-1416) */
     double term0_sum = 0.0;
-    for (int k = 0; k < AB_NPLANETS; k++) {
-        const double dxik = pix + (xo - B.pos[k][0]);
-        const double dyik = piy + (yo - B.pos[k][1]);
-        const double dzik = piz + (zo - B.pos[k][2]);
-        const double rik2 = dxik * dxik + dyik * dyik + dzik * dzik;
-        const double _rik = sqrt(rik2);
-        term0_sum += B.gm[k] / _rik;
+    {
+        double q[AB_NPLANETS];
+#pragma unroll kEihUnroll
+        for (int k = 0; k < AB_NPLANETS; k++) {   /* 11 independent sqrt + quotient chains */
+            const double dxik = pix + (xo - B.pos[k][0]);
+            const double dyik = piy + (yo - B.pos[k][1]);
+            const double dzik = piz + (zo - B.pos[k][2]);
+            const double rik2 = dxik * dxik + dyik * dyik + dzik * dzik;
+            const double _rik = sqrt(rik2);
+            q[k] = B.gm[k] / _rik;
+        }
+#pragma unroll
+        for (int k = 0; k < AB_NPLANETS; k++) term0_sum += q[k];   /* summed in the reference's order */
     }
 
     {   /* real particle, src/forces.c:1319-1501 */
@@ -691,12 +707,105 @@ __device__ void ab_force_eih(const AbEphem& E, const AbForceOpts& F, const BT& B
 }
 
 /* ---- direct Newtonian terms, reference src/forces.c:266-433 ---------------- */
+/* Bodies are taken in the reference's order, four at a time: the separations, square roots and
+ * quotients of a group do not depend on each other, so they are formed first (loads and FP64
+ * latencies of four bodies overlap); the accumulation into the acceleration then runs in the
+ * reference's sequence, which is what fixes the rounding. */
+template <int KM, class BT>
+__device__ __forceinline__ void ab_direct_group(const AbForceOpts& F, const BT& B, AbSysT<KM>& S, const int* idx, int cnt,
+                                                double px, double py, double pz, double xo, double yo, double zo) {
+    double gm[4], dx[4], dy[4], dz[4], r2[4], r[4], prefac[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (q < cnt) {
+            const int i = idx[q];
+            gm[q] = B.gm[i];
+            dx[q] = px + (xo - B.pos[i][0]);
+            dy[q] = py + (yo - B.pos[i][1]);
+            dz[q] = pz + (zo - B.pos[i][2]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (q < cnt) {
+            r2[q] = dx[q] * dx[q] + dy[q] * dy[q] + dz[q] * dz[q];
+            r[q] = sqrt(r2[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (q < cnt) prefac[q] = gm[q] / (r[q] * r[q] * r[q]);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (q < cnt) {
+            const int i = idx[q];
+            bool on = true;
+            if (i == 0 && !(F.forces & 0x01)) on = false;
+            if (i > 0 && i < AB_NPLANETS && !(F.forces & 0x02)) on = false;
+            if (i >= AB_NPLANETS && !(F.forces & 0x04)) on = false;
+            if (on) {
+                S.a[0][0] -= prefac[q] * dx[q];
+                S.a[0][1] -= prefac[q] * dy[q];
+                S.a[0][2] -= prefac[q] * dz[q];
+            }
+            if (S.nv() > 0) {
+                /* no force-mask check here, as in the reference (src/forces.c:359) */
+                const double r3inv = 1. / (r2[q] * r[q]);
+                const double r5inv = 3. * r3inv / r2[q];
+                const double dxdx = dx[q] * dx[q] * r5inv - r3inv;
+                const double dydy = dy[q] * dy[q] * r5inv - r3inv;
+                const double dzdz = dz[q] * dz[q] * r5inv - r3inv;
+                const double dxdy = dx[q] * dy[q] * r5inv;
+                const double dxdz = dx[q] * dz[q] * r5inv;
+                const double dydz = dy[q] * dz[q] * r5inv;
+                for (int vv = 1; vv <= S.nv(); vv++) {
+                    const double ddx = S.x[vv][0], ddy = S.x[vv][1], ddz = S.x[vv][2];
+                    const double dax = ddx * dxdx + ddy * dxdy + ddz * dxdz;
+                    const double day = ddx * dxdy + ddy * dydy + ddz * dydz;
+                    const double daz = ddx * dxdz + ddy * dydz + ddz * dzdz;
+                    S.a[vv][0] += gm[q] * dax;
+                    S.a[vv][1] += gm[q] * day;
+                    S.a[vv][2] += gm[q] * daz;
+                }
+            }
+        }
+    }
+}
+
+#ifndef AB_DIRECT_CHUNK
+#define AB_DIRECT_CHUNK 0
+#endif
+#if AB_DIRECT_CHUNK
+template <int KM, class BT>
+__device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT& B, AbSysT<KM>& S,
+                                double xo, double yo, double zo) {
+    const int ast_num = E.n_ast;
+    const double px = S.x[0][0], py = S.x[0][1], pz = S.x[0][2];
+    /* asteroids first ... */
+    for (int k0 = 0; k0 < ast_num; k0 += 4) {
+        const int idx[4] = {AB_NPLANETS + k0, AB_NPLANETS + k0 + 1, AB_NPLANETS + k0 + 2, AB_NPLANETS + k0 + 3};
+        const int cnt = (ast_num - k0 < 4) ? (ast_num - k0) : 4;
+        ab_direct_group<KM, BT>(F, B, S, idx, cnt, px, py, pz, xo, yo, zo);
+    }
+    /* ... then Pluto, Moon, Mars, Mercury, Neptune, Uranus, Earth, Venus, Saturn, Jupiter, Sun (src/forces.c:281-293) */
+    {
+        const int g0[4] = {10, 4, 5, 1};
+        ab_direct_group<KM, BT>(F, B, S, g0, 4, px, py, pz, xo, yo, zo);
+        const int g1[4] = {9, 8, 3, 2};
+        ab_direct_group<KM, BT>(F, B, S, g1, 4, px, py, pz, xo, yo, zo);
+        const int g2[4] = {7, 6, 0, 0};
+        ab_direct_group<KM, BT>(F, B, S, g2, 3, px, py, pz, xo, yo, zo);
+    }
+}
+
+#else
 template <int KM, class BT>
 __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT& B, AbSysT<KM>& S,
                                 double xo, double yo, double zo) {
     const int order[AB_NPLANETS] = {10, 4, 5, 1, 9, 8, 3, 2, 7, 6, 0};
     const int ast_num = E.n_ast;
     const double px = S.x[0][0], py = S.x[0][1], pz = S.x[0][2];
+#pragma unroll kDirectUnroll
     for (int k = 0; k < AB_NPLANETS + ast_num; k++) {
         const int i = (k >= ast_num) ? order[k - ast_num] : (k + AB_NPLANETS);
         const double GM = B.gm[i];
@@ -737,6 +846,7 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT
         }
     }
 }
+#endif
 
 /* ---- dispatcher, reference src/forces.c:49-173 ----------------------------- */
 /* S.a must be zero on entry (REBOUND zeroes accelerations before the plug-in runs). */

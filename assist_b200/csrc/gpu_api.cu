@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "assist_gpu.h"
 #include "assist_ephem_files.h"
@@ -577,6 +578,9 @@ extern "C" int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int 
         const int* list = NULL;
         int n_active = b->n, resume = 0, which = 0;
         unsigned long long launches = 0;
+        const bool trace = getenv("ASSIST_B200_TRACE") != NULL;
+        struct timespec ts0, ts1;
+        clock_gettime(CLOCK_MONOTONIC, &ts0);
         while (true) {
             if (k1) e = fast ? ab_launch_pp_integrate_k1_fast(E, F, b->d, t_end, exact_finish_time, resume, b->step_cap, list, n_active, 0)
                              : ab_launch_pp_integrate_k1_strict(E, F, b->d, t_end, exact_finish_time, resume, b->step_cap, list, n_active, 0);
@@ -589,6 +593,12 @@ extern "C" int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int 
             compact_active_kernel<<<(n_active + 255) / 256, 256>>>(b->d.status, list, n_active, b->d_active[which], b->d_count);
             int count = 0;
             CU(cudaMemcpy(&count, b->d_count, sizeof(int), cudaMemcpyDeviceToHost));
+            if (trace) {
+                clock_gettime(CLOCK_MONOTONIC, &ts1);
+                fprintf(stderr, "[assist-b200] launch %llu: %d systems in, %d still running, %.2f ms\n", launches, n_active, count,
+                        (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);
+                ts0 = ts1;
+            }
             if (count == 0) break;
             if (launches > 4000000ULL) return set_err(ASSIST_GPU_ERR_CUDA, "per-particle integration did not finish after %llu launches", launches);
             list = b->d_active[which];

@@ -126,7 +126,7 @@ struct PPState {
  * IAS15 attempts until one is accepted.  Each thread owns its times, so the body
  * table is evaluated per thread. */
 template <int KM>
-__device__ void pp_step(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, long long i, PPState& P) {
+__device__ __noinline__ void pp_step(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, long long i, PPState& P) {
     AbSysT<KM> S;
     AbBodies B;
     ab_load_sys(Bt, i, S);
