@@ -109,6 +109,8 @@ struct AbNode {
     double eih_av[1][3];
 };
 
+#define AB_NODE_DOUBLES 94   /* doubles of an AbNode after the gm pointer */
+
 /* Device-side state of a batch.  Arrays are structure-of-arrays over systems:
  * element (component k, system i) lives at [k * n + i]; the seven-deep IAS15
  * tables at [(j * C + k) * n + i], C = 3 * K. */

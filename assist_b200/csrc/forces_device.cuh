@@ -51,6 +51,21 @@ struct AbSysT {
     __device__ __forceinline__ int nv() const { return (KM == 1) ? 0 : nv_; }
 };
 
+/* A node table staged in shared memory, one column per thread (element q of thread `tid` at
+ * [q * AB_BLOCK + tid]: conflict-free).  Same member syntax as AbNode / AbBodies. */
+struct AbColRow { const double* p; __device__ __forceinline__ double operator[](int c) const { return p[c * AB_BLOCK]; } };
+struct AbColMat { const double* p; __device__ __forceinline__ AbColRow operator[](int i) const { return AbColRow{p + 3 * i * AB_BLOCK}; } };
+struct AbColVec { const double* p; __device__ __forceinline__ double operator[](int i) const { return p[i * AB_BLOCK]; } };
+struct AbNodeS {
+    const double* gm;
+    AbColMat pos, vel;
+    AbColVec earth_acc, eih_term1;
+    AbColMat eih_ar, eih_av;
+    __device__ __forceinline__ AbNodeS(const double* gm_, const double* col)
+        : gm(gm_), pos{col}, vel{col + 81 * AB_BLOCK}, earth_acc{col + 84 * AB_BLOCK}, eih_term1{col + 87 * AB_BLOCK},
+          eih_ar{col + 88 * AB_BLOCK}, eih_av{col + 91 * AB_BLOCK} {}
+};
+
 /* 3x6 Jacobian applied to every variational particle of the system. */
 #define AB_APPLY_J36(S, dxdx, dxdy, dxdz, dxdvx, dxdvy, dxdvz, dydx, dydy, dydz, dydvx, dydvy, dydvz, dzdx, dzdy, dzdz, dzdvx, dzdvy, dzdvz) \
     for (int vv = 1; vv <= (S).nv(); vv++) {                                                             \
@@ -799,19 +814,34 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT
 }
 
 #else
+/* Body visited at position k of the reference's loop (src/forces.c:281-306): asteroids first, then
+ * Pluto, Moon, Mars, Mercury, Neptune, Uranus, Earth, Venus, Saturn, Jupiter, Sun -- the planet
+ * sequence packed four bits each, so the index is arithmetic, not a (dependent) table load. */
+__device__ __forceinline__ int ab_direct_body(int k, int ast_num) {
+    return (k >= ast_num) ? (int)((0x0672389154AULL >> (4 * (k - ast_num))) & 0xFULL) : (k + AB_NPLANETS);
+}
+
 template <int KM, class BT>
 __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT& B, AbSysT<KM>& S,
                                 double xo, double yo, double zo) {
-    const int order[AB_NPLANETS] = {10, 4, 5, 1, 9, 8, 3, 2, 7, 6, 0};
     const int ast_num = E.n_ast;
+    const int nb = AB_NPLANETS + ast_num;
     const double px = S.x[0][0], py = S.x[0][1], pz = S.x[0][2];
+    /* the table entries of the next body are requested while the current body is being worked on */
+    int i_next = ab_direct_body(0, ast_num);
+    double bx = B.pos[i_next][0], by = B.pos[i_next][1], bz = B.pos[i_next][2], bgm = B.gm[i_next];
 #pragma unroll kDirectUnroll
-    for (int k = 0; k < AB_NPLANETS + ast_num; k++) {
-        const int i = (k >= ast_num) ? order[k - ast_num] : (k + AB_NPLANETS);
-        const double GM = B.gm[i];
-        const double dx = px + (xo - B.pos[i][0]);
-        const double dy = py + (yo - B.pos[i][1]);
-        const double dz = pz + (zo - B.pos[i][2]);
+    for (int k = 0; k < nb; k++) {
+        const int i = i_next;
+        const double GM = bgm;
+        const double cx = bx, cy = by, cz = bz;
+        if (k + 1 < nb) {
+            i_next = ab_direct_body(k + 1, ast_num);
+            bx = B.pos[i_next][0]; by = B.pos[i_next][1]; bz = B.pos[i_next][2]; bgm = B.gm[i_next];
+        }
+        const double dx = px + (xo - cx);
+        const double dy = py + (yo - cy);
+        const double dz = pz + (zo - cz);
         const double r2 = dx * dx + dy * dy + dz * dz;
         const double _r = sqrt(r2);
         bool on = true;
