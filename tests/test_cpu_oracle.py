@@ -185,3 +185,60 @@ def test_min_dt_clamp_and_c1_counts(golden):
         assert np.isfinite(g["c1_final"]).all()
         assert g["c1_t"][0] == cases.T0 + 3652.5
         assert g["c1_counts"][0] > 100
+
+
+# ---------------------------------------------------------------------------------------------
+# the numpy restatement (oracle/np_oracle.py) against the reference build's outputs
+# ---------------------------------------------------------------------------------------------
+def _np_oracle():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("np_oracle", os.path.join(ROOT, "oracle", "np_oracle.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_numpy_restatement_ephemeris(paths, fmt, golden):
+    npo = _np_oracle()
+    eph = npo.Ephemeris(planets_path(paths, fmt), paths["asteroids_bsp"])
+    g = golden[fmt]
+    for it, t in enumerate(cases.EPHEM_TIMES):
+        if g["ephem_status"][it].max() != 0:
+            continue
+        gm, pos, vel = eph.states(float(t))
+        assert np.array_equal(gm, g["ephem"][it, :, 0])
+        assert np.max(np.abs(pos - g["ephem"][it, :, 1:4])) < 1e-14
+        assert np.max(np.abs(vel[:11] - g["ephem"][it, :11, 4:7])) < 1e-16 + 1e-13 * np.max(np.abs(g["ephem"][it, :11, 4:7]))
+
+
+def test_numpy_restatement_force_terms(paths, fmt, golden):
+    """Every force term of the structurally independent numpy restatement agrees with the reference
+    build to ~1e-13 relative; the variational parts agree with central differences of it to 1e-6."""
+    npo = _np_oracle()
+    eph = npo.Ephemeris(planets_path(paths, fmt), paths["asteroids_bsp"])
+    g = golden[fmt]
+    state, params = cases.force_case()
+    x, v = state[:, 0, :3], state[:, 0, 3:]
+    for name, mask, src, geo in cases.FORCE_TERMS:
+        if geo:
+            continue
+        a = npo.accelerations(eph, cases.FORCE_T, x, v, params[:, 0, :], forces=mask, gr_eih_sources=src)
+        want = g["force_" + name][:, 0, :]
+        assert relerr(a, want) < 2e-13, (name, relerr(a, want))
+    # variational: the reference's Jacobian-times-variation vs numerical differentiation
+    # ("sun", 0x07): the reference's variational direct term ignores the force mask (src/forces.c:359), so the
+    # variational part of the Sun-only evaluation is the derivative of ALL direct terms
+    for name, mask, src in (("sun", 0x07, 1), ("earth_harm", 0x10, 1), ("sun_harm", 0x20, 1), ("eih1", 0x40, 1),
+                            ("gr_simple", 0x80, 1), ("gr_potential", 0x100, 1), ("nongrav", 0x08, 1)):
+        for k in (1, 4):
+            dx, dv = state[:, k, :3], state[:, k, 3:]
+            da = npo.variational_by_differences(eph, cases.FORCE_T, x, v, dx, dv, params[:, 0, :], params[:, k, :],
+                                                forces=mask, gr_eih_sources=src)
+            want = g["force_" + name][:, k, :]
+            if name == "nongrav":
+                # particles with A1 = A2 = A3 = 0 are skipped by the reference, variational part included (src/forces.c:861)
+                skipped = ~np.any(params[:, 0, :] != 0.0, axis=1)
+                assert np.all(want[skipped] == 0.0)
+                da[skipped] = 0.0
+            scale = np.linalg.norm(want, axis=1).max()
+            assert np.max(np.linalg.norm(da - want, axis=1)) < 2e-5 * scale, name
