@@ -327,6 +327,10 @@ struct assist_gpu_batch {
     double* d_stage_prm;    /* [n][K][3] */
     double* d_out;          /* dense output staging */
     size_t d_out_bytes;
+    AbBatch w;              /* working slots of the work-queue scheduler (per-particle mode) */
+    char* wblock;
+    unsigned long long* d_queue;
+    int sched_queue;        /* 1: work-queue kernel (default), 0: capped launches + straggler packing */
     int* d_active[2];       /* ping-pong lists of systems still integrating */
     int* d_count;           /* length of the list being built */
     long long step_cap;     /* accepted steps per system per launch (per-particle mode) */
@@ -382,35 +386,19 @@ __global__ void fill_int_kernel(int* p, long long n, int v) {
 
 static inline int blocks_for(long long n) { return (int)((n + 255) / 256); }
 
-extern "C" assist_gpu_batch* assist_gpu_batch_create(const struct assist_ephem* ephem, int n_sys, int n_var, int mode) {
-    int dev;
-    if (ensure_device(&dev)) return NULL;
-    if (n_sys <= 0 || n_var < 0 || n_var > AB_NVMAX) {
-        set_err(ASSIST_GPU_ERR_UNSUPPORTED, "batch of %d systems with %d variational particles each (max %d) is not supported", n_sys, n_var, AB_NVMAX);
-        return NULL;
-    }
-    assist_gpu_batch* b = (assist_gpu_batch*)calloc(1, sizeof(assist_gpu_batch));
-    b->ephem = ephem; b->n = n_sys; b->nvar = n_var; b->K = 1 + n_var; b->C = 3 * b->K; b->mode = mode; b->device = dev;
-    assist_gpu_default_options(&b->opt);
-    const size_t n = n_sys, C = b->C;
-    const size_t per = C * n;                      /* doubles in one [C][n] array */
-    const size_t n_small = 12 + 42 * 1;            /* pos vel acc x0 v0 a0 csx csv ls_pos ls_vel ls_acc prm  (+ 6 seven-deep tables) */
-    (void)n_small;
-    size_t doubles = 12 * per + 42 * per + 4 * n;  /* + t dt dt_last last_full_dt */
-    size_t bytes = doubles * sizeof(double);
-    bytes += 4 * n * sizeof(unsigned long long);   /* counters */
-    bytes += 2 * n * sizeof(int);                  /* nv, status */
+/* Carve one device allocation into the arrays of an AbBatch for n systems of K bodies. */
+static size_t batch_bytes(size_t n, size_t C) {
+    size_t bytes = (12 * C * n + 42 * C * n + 4 * n) * sizeof(double);
+    bytes += 4 * n * sizeof(unsigned long long);
+    bytes += 2 * n * sizeof(int);
     bytes += sizeof(AbShared) + 64;
-    if (cudaMalloc((void**)&b->block, bytes) != cudaSuccess) {
-        set_err(ASSIST_GPU_ERR_CUDA, "cudaMalloc of %zu bytes failed", bytes);
-        free(b);
-        return NULL;
-    }
-    cudaMemset(b->block, 0, bytes);
-    b->block_bytes = bytes;
-    double* p = (double*)b->block;
-    AbBatch& d = b->d;
-    d.n = n_sys; d.K = b->K; d.C = b->C; d.mode = mode;
+    return bytes;
+}
+
+static void layout_batch(AbBatch& d, char* block, size_t n, int K, int mode) {
+    const size_t C = 3 * (size_t)K, per = C * n;
+    double* p = (double*)block;
+    d.n = (int)n; d.K = K; d.C = (int)C; d.mode = mode;
     d.pos = p; p += per; d.vel = p; p += per; d.acc = p; p += per;
     d.x0 = p; p += per; d.v0 = p; p += per; d.a0 = p; p += per; d.csx = p; p += per; d.csv = p; p += per;
     d.ls_pos = p; p += per; d.ls_vel = p; p += per; d.ls_acc = p; p += per; d.prm = p; p += per;
@@ -422,6 +410,33 @@ extern "C" assist_gpu_batch* assist_gpu_batch_create(const struct assist_ephem* 
     d.sh = (AbShared*)q;
     int* ip = (int*)((char*)q + ((sizeof(AbShared) + 63) / 64) * 64);
     d.nv = ip; ip += n; d.status = ip; ip += n;
+}
+
+extern "C" assist_gpu_batch* assist_gpu_batch_create(const struct assist_ephem* ephem, int n_sys, int n_var, int mode) {
+    int dev;
+    if (ensure_device(&dev)) return NULL;
+    if (n_sys <= 0 || n_var < 0 || n_var > AB_NVMAX) {
+        set_err(ASSIST_GPU_ERR_UNSUPPORTED, "batch of %d systems with %d variational particles each (max %d) is not supported", n_sys, n_var, AB_NVMAX);
+        return NULL;
+    }
+    assist_gpu_batch* b = (assist_gpu_batch*)calloc(1, sizeof(assist_gpu_batch));
+    b->ephem = ephem; b->n = n_sys; b->nvar = n_var; b->K = 1 + n_var; b->C = 3 * b->K; b->mode = mode; b->device = dev;
+    assist_gpu_default_options(&b->opt);
+    const size_t n = n_sys, C = b->C;
+    const size_t bytes = batch_bytes(n, C);
+    if (cudaMalloc((void**)&b->block, bytes) != cudaSuccess) {
+        set_err(ASSIST_GPU_ERR_CUDA, "cudaMalloc of %zu bytes failed", bytes);
+        free(b);
+        return NULL;
+    }
+    cudaMemset(b->block, 0, bytes);
+    b->block_bytes = bytes;
+    AbBatch& d = b->d;
+    layout_batch(d, b->block, n, b->K, mode);
+    {
+        const char* sc = getenv("ASSIST_B200_SCHED");
+        b->sched_queue = !(sc && !strcmp(sc, "capped"));
+    }
     d.epsilon = b->opt.epsilon; d.min_dt = b->opt.min_dt; d.has_params = 0;
     cudaMalloc((void**)&b->d_stage, sizeof(double) * 6 * n * b->K);
     cudaMalloc((void**)&b->d_stage_prm, sizeof(double) * 3 * n * b->K);
@@ -448,6 +463,7 @@ extern "C" void assist_gpu_batch_free(assist_gpu_batch* b) {
     if (!b) return;
     cudaFree(b->block); cudaFree(b->snapshot); cudaFree(b->d_stage); cudaFree(b->d_stage_prm); cudaFree(b->d_out);
     cudaFree(b->d_active[0]); cudaFree(b->d_active[1]); cudaFree(b->d_count);
+    cudaFree(b->wblock); cudaFree(b->d_queue);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     free(b);
@@ -574,6 +590,34 @@ extern "C" int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int 
          * whose integrate() has not returned are then packed into a dense list and relaunched.  This
          * keeps the lanes of a warp busy although step counts differ by 10x between particles. */
         const bool k1 = (b->K == 1);
+        if (b->sched_queue) {
+            /* work-queue scheduling: a resident grid of threads pulls systems until the queue is empty */
+            if (!b->wblock) {
+                int threads = 0;
+                cudaError_t eo = k1 ? (fast ? ab_pp_resident_threads_k1_fast(&threads) : ab_pp_resident_threads_k1_strict(&threads))
+                                    : (fast ? ab_pp_resident_threads_kv_fast(&threads) : ab_pp_resident_threads_kv_strict(&threads));
+                if (eo != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(eo));
+                /* both math variants must fit: take the smaller resident count */
+                int t2 = 0;
+                eo = k1 ? (fast ? ab_pp_resident_threads_k1_strict(&t2) : ab_pp_resident_threads_k1_fast(&t2))
+                        : (fast ? ab_pp_resident_threads_kv_strict(&t2) : ab_pp_resident_threads_kv_fast(&t2));
+                if (eo == cudaSuccess && t2 < threads) threads = t2;
+                size_t slots = (size_t)threads;
+                if (slots > (size_t)b->n) slots = ((size_t)b->n + 127) / 128 * 128;
+                CU(cudaMalloc((void**)&b->wblock, batch_bytes(slots, b->C)));
+                CU(cudaMemset(b->wblock, 0, batch_bytes(slots, b->C)));
+                layout_batch(b->w, b->wblock, slots, b->K, b->mode);
+                CU(cudaMalloc((void**)&b->d_queue, sizeof(unsigned long long)));
+            }
+            b->w.epsilon = b->d.epsilon; b->w.min_dt = b->d.min_dt; b->w.has_params = b->d.has_params;
+            CU(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), 0));
+            CU(cudaEventRecord(b->ev0, 0));
+            if (k1) e = fast ? ab_launch_pp_queue_k1_fast(E, F, b->d, b->w, t_end, exact_finish_time, b->d_queue, NULL, 0)
+                             : ab_launch_pp_queue_k1_strict(E, F, b->d, b->w, t_end, exact_finish_time, b->d_queue, NULL, 0);
+            else e = fast ? ab_launch_pp_queue_kv_fast(E, F, b->d, b->w, t_end, exact_finish_time, b->d_queue, NULL, 0)
+                          : ab_launch_pp_queue_kv_strict(E, F, b->d, b->w, t_end, exact_finish_time, b->d_queue, NULL, 0);
+            return finish_launch(b, e, "pp_queue");
+        }
         CU(cudaEventRecord(b->ev0, 0));
         const int* list = NULL;
         int n_active = b->n, resume = 0, which = 0;

@@ -369,6 +369,75 @@ pp_integrate_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ A
     if (owns) pp_store(Bt, i, P);
 }
 
+/* Move one system between the population arrays (index `i`, stride Bt.n) and a working slot
+ * (index `s`, stride W.n).  54 * C doubles, once per system per integrate() call. */
+__device__ void pp_copy_system(const AbBatch& src, long long i, const AbBatch& dst, long long s, int nv) {
+    const long long ns = src.n, nd = dst.n;
+    const int C = src.C;
+    const int Ca = 3 * (1 + nv);
+    double* const s1[12] = {src.pos, src.vel, src.acc, src.x0, src.v0, src.a0, src.csx, src.csv, src.ls_pos, src.ls_vel, src.ls_acc, src.prm};
+    double* const d1[12] = {dst.pos, dst.vel, dst.acc, dst.x0, dst.v0, dst.a0, dst.csx, dst.csv, dst.ls_pos, dst.ls_vel, dst.ls_acc, dst.prm};
+    double* const s7[6] = {src.b, src.g, src.e, src.csb, src.br, src.er};
+    double* const d7[6] = {dst.b, dst.g, dst.e, dst.csb, dst.br, dst.er};
+    for (int a = 0; a < 12; a++)
+        for (int k = 0; k < Ca; k++) d1[a][(long long)k * nd + s] = s1[a][(long long)k * ns + i];
+    for (int a = 0; a < 6; a++)
+        for (int j = 0; j < 7; j++)
+            for (int k = 0; k < Ca; k++)
+                d7[a][((long long)j * C + k) * nd + s] = s7[a][((long long)j * C + k) * ns + i];
+}
+
+/* Work-queue scheduling: a fixed grid of resident threads; every thread takes the next system
+ * from a global counter, moves its state into a working slot (slot-indexed arrays: coalesced
+ * across the warp whatever the system indices are, and small enough to stay in L2), runs
+ * reb_simulation_integrate for it, writes it back and takes the next one.  All threads of a CTA
+ * do one step per loop trip (one barrier per trip, see pp_integrate_kernel), so lanes only
+ * diverge inside a step.  No thread idles until the queue is empty: the 15x spread in step counts
+ * between particles costs nothing but the very last stragglers. */
+__global__ void __launch_bounds__(AB_PP_BLOCK, AB_PP_MIN_BLOCKS)
+pp_queue_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F,
+                const __grid_constant__ AbBatch Bt, const __grid_constant__ AbBatch W,
+                double tmax, int exact_finish_time, unsigned long long* __restrict__ queue_head,
+                const int* __restrict__ order) {
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool have = false, exhausted = (slot >= W.n);
+    long long sys = -1;
+    int nv = 0;
+    PPState P;
+    while (true) {
+        while (!have && !exhausted) {
+            const unsigned long long q = atomicAdd(queue_head, 1ULL);
+            if (q >= (unsigned long long)Bt.n) { exhausted = true; break; }
+            sys = order ? order[q] : (long long)q;
+            pp_load(Bt, sys, P);
+            if (P.status >= 1000) continue;           /* failed earlier (ephemeris error): skip */
+            nv = Bt.nv[sys];
+            W.nv[slot] = nv;
+            W.status[slot] = 0;
+            pp_copy_system(Bt, sys, W, slot, nv);
+            if (tmax != P.t) P.dt = copysign(P.dt, (tmax > P.t) ? 1.0 : -1.0);
+            P.last_full_dt = P.dt;
+            P.dt_last = 0.;
+            P.status = -1;
+            have = true;
+        }
+        if (!__syncthreads_or(have ? 1 : 0)) break;
+        if (have) {
+            if (ab_check_exit(P.t, P.dt, P.dt_last, P.status, tmax, exact_finish_time, P.last_full_dt) >= 0) {
+                if (exact_finish_time == 1) P.dt = P.last_full_dt;
+                pp_copy_system(W, slot, Bt, sys, nv);
+                if (W.status[slot] >= 1000) Bt.status[sys] = W.status[slot];
+                pp_store(Bt, sys, P);
+                have = false;
+            } else if (F.gr_eih_sources == 1 && !F.geocentric) {
+                pp_step_nodes<PP_KM>(E, F, W, slot, P);
+            } else {
+                pp_step<PP_KM>(E, F, W, slot, P);
+            }
+        }
+    }
+}
+
 /* assist_integrate_or_interpolate(times[e]) for e = 0..n_times-1 per system
  * (reference src/assist.c:642-680); out[n_times][n][K][6]. */
 __global__ void __launch_bounds__(AB_BLOCK, AB_PP_MIN_BLOCKS)
@@ -660,6 +729,26 @@ cudaError_t PP_NAME(ab_launch_pp_integrate)(const AbEphem& E, const AbForceOpts&
     }
     pp_integrate_kernel<<<grid, AB_PP_BLOCK, smem, st>>>(E, F, Bt, tmax, exact, resume, step_cap, active, n_active);
     return cudaGetLastError();
+}
+
+cudaError_t PP_NAME(ab_launch_pp_queue)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const AbBatch& W, double tmax, int exact,
+                                        unsigned long long* queue_head, const int* order, cudaStream_t st) {
+    const int grid = (W.n + AB_PP_BLOCK - 1) / AB_PP_BLOCK;
+    if (grid < 1) return cudaSuccess;
+    pp_queue_kernel<<<grid, AB_PP_BLOCK, 0, st>>>(E, F, Bt, W, tmax, exact, queue_head, order);
+    return cudaGetLastError();
+}
+
+/* resident threads of the per-particle kernels on the current device (size of the working set) */
+cudaError_t PP_NAME(ab_pp_resident_threads)(int* threads) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pp_queue_kernel, AB_PP_BLOCK, 0)) != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    *threads = sms * per_sm * AB_PP_BLOCK;
+    return cudaSuccess;
 }
 
 cudaError_t PP_NAME(ab_launch_pp_dense)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const double* times, int n_times, double* out, cudaStream_t st) {

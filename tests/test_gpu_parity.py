@@ -140,17 +140,34 @@ def test_c1_apophis_like_ten_years(eph, fmt, golden):
     assert np.linalg.norm(got["state"][0, 0, :3] - g["c1_final"][0, 0, :3]) <= POS_TOL_AU
 
 
-def test_step_cap_does_not_change_results(eph, fmt, golden, monkeypatch):
-    """Pausing and resuming integrate() every few steps (straggler packing) is invisible in the results."""
+def test_schedulers_do_not_change_results(eph, fmt, golden, monkeypatch):
+    """The default work-queue scheduler, and the alternative that pauses/resumes integrate() every few steps
+    and packs the stragglers, are invisible in the results."""
     g = golden[fmt]
     st = cases.pp_case()
-    for cap in ("0", "1", "5"):
+    for sched, cap in (("queue", "32"), ("capped", "0"), ("capped", "1"), ("capped", "5")):
+        monkeypatch.setenv("ASSIST_B200_SCHED", sched)
         monkeypatch.setenv("ASSIST_B200_STEP_CAP", cap)
         b = ab.Batch(eph, st.shape[0], 0, ab.PER_PARTICLE, forces=0x7F)
         b.set_state(cases.T0, st[:, None, :])
         b.integrate(cases.T0 + cases.PP_DAYS)
-        assert np.array_equal(b.get_state()["state"], g["pp_final"]), cap
+        assert np.array_equal(b.get_state()["state"], g["pp_final"]), (sched, cap)
         b.close()
+    # more systems than working slots: every slot is reused many times
+    monkeypatch.setenv("ASSIST_B200_SCHED", "queue")
+    n = 150000
+    stn = populations.main_belt(n, seed=71)
+    b = ab.Batch(eph, n, 0, ab.PER_PARTICLE, forces=0x7F)
+    b.set_state(cases.T0, stn[:, None, :])
+    b.integrate(cases.T0 + 30.0)
+    q = b.get_state()["state"].copy()
+    b.close()
+    monkeypatch.setenv("ASSIST_B200_SCHED", "capped")
+    b = ab.Batch(eph, n, 0, ab.PER_PARTICLE, forces=0x7F)
+    b.set_state(cases.T0, stn[:, None, :])
+    b.integrate(cases.T0 + 30.0)
+    assert np.array_equal(b.get_state()["state"], q)
+    b.close()
 
 
 # ------------------------------------------------------------------ shared step
