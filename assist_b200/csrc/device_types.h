@@ -109,6 +109,14 @@ struct AbNode {
     double eih_av[1][3];
 };
 
+/* time slices of the work-queue scheduler (kernels.cu, pp_queue_kernel) */
+struct AbSlices {
+    double origin, wlen;      /* wlen carries the direction of integration */
+    int n_win;
+    int* done;                /* [n] windows completed per system */
+    int* epoch;               /* [n] next output epoch per system (epoch runs) */
+};
+
 #define AB_NODE_DOUBLES 94   /* doubles of an AbNode after the gm pointer */
 
 /* Device-side state of a batch.  Arrays are structure-of-arrays over systems:

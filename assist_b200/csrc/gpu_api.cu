@@ -315,6 +315,10 @@ extern "C" int assist_gpu_eval_forces(const struct assist_ephem* ephem, const st
 /* batches                                                                  */
 /* ------------------------------------------------------------------------ */
 
+#ifndef AB_DEFAULT_SLICE_DAYS
+#define AB_DEFAULT_SLICE_DAYS 256.0
+#endif
+
 struct assist_gpu_batch {
     const struct assist_ephem* ephem;
     int n, nvar, K, C, mode, device;
@@ -330,6 +334,10 @@ struct assist_gpu_batch {
     AbBatch w;              /* working slots of the work-queue scheduler (per-particle mode) */
     char* wblock;
     unsigned long long* d_queue;
+    int* d_slice_done;      /* [n] time slices completed per system (work-queue scheduler) */
+    int* d_slice_epoch;     /* [n] next output epoch per system */
+    double* d_trange;       /* [2] min / max of the systems' times */
+    double slice_days;      /* length of a time slice; 0: one slice */
     int sched_queue;        /* 1: work-queue kernel (default), 0: capped launches + straggler packing */
     int* d_active[2];       /* ping-pong lists of systems still integrating */
     int* d_count;           /* length of the list being built */
@@ -436,6 +444,9 @@ extern "C" assist_gpu_batch* assist_gpu_batch_create(const struct assist_ephem* 
     {
         const char* sc = getenv("ASSIST_B200_SCHED");
         b->sched_queue = !(sc && !strcmp(sc, "capped"));
+        const char* sd = getenv("ASSIST_B200_SLICE_DAYS");
+        b->slice_days = sd ? atof(sd) : AB_DEFAULT_SLICE_DAYS;
+        if (!(b->slice_days >= 0.0)) b->slice_days = 0.0;
     }
     d.epsilon = b->opt.epsilon; d.min_dt = b->opt.min_dt; d.has_params = 0;
     cudaMalloc((void**)&b->d_stage, sizeof(double) * 6 * n * b->K);
@@ -463,7 +474,7 @@ extern "C" void assist_gpu_batch_free(assist_gpu_batch* b) {
     if (!b) return;
     cudaFree(b->block); cudaFree(b->snapshot); cudaFree(b->d_stage); cudaFree(b->d_stage_prm); cudaFree(b->d_out);
     cudaFree(b->d_active[0]); cudaFree(b->d_active[1]); cudaFree(b->d_count);
-    cudaFree(b->wblock); cudaFree(b->d_queue);
+    cudaFree(b->wblock); cudaFree(b->d_queue); cudaFree(b->d_slice_done); cudaFree(b->d_slice_epoch); cudaFree(b->d_trange);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     free(b);
@@ -575,6 +586,96 @@ extern "C" int assist_gpu_batch_integrate(assist_gpu_batch* b, double t_end, int
     return ab_gpu_batch_integrate_ex(b, t_end, exact_finish_time, max_steps, 0);
 }
 
+/* A record boundary of the small-body kernel (else of the planets file), as a time relative to jd_ref. */
+static double ab_slice_anchor(const struct assist_ephem* e) {
+    if (e->spk_asteroids && e->spk_asteroids->num > 0) return e->spk_asteroids->targets[0].beg - e->jd_ref;
+    if (e->spk_planets && e->spk_planets->num > 0) return e->spk_planets->targets[0].beg - e->jd_ref;
+    return 0.0;
+}
+
+/* min / max of the times of the systems that can still run */
+__global__ void trange_kernel(const double* __restrict__ t, const int* __restrict__ status, int n, double* __restrict__ out) {
+    double lo = 1e300, hi = -1e300;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (status[i] >= 1000) continue;
+        const double v = t[i];
+        if (v == v) { lo = fmin(lo, v); hi = fmax(hi, v); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        /* doubles compare like their bit patterns once the sign is folded in */
+        auto key = [](double x) { long long b = __double_as_longlong(x); return (unsigned long long)(b < 0 ? ~b : (b | 0x8000000000000000LL)); };
+        atomicMin((unsigned long long*)&out[0], key(lo));
+        atomicMax((unsigned long long*)&out[1], key(hi));
+    }
+}
+
+static double unkey(unsigned long long k) {
+    long long b = (k & 0x8000000000000000ULL) ? (long long)(k & 0x7fffffffffffffffULL) : ~(long long)k;
+    double x;
+    memcpy(&x, &b, sizeof(x));
+    return x;
+}
+
+/* Time slices of one call (see AbSlices): windows of slice_days on the record grid of the ephemeris, from the
+ * earliest system towards t_end.  One slice when slicing is off or the systems lie on both sides of t_end. */
+static int build_slices(assist_gpu_batch* b, const AbEphem& E, double t_end, AbSlices* SL) {
+    SL->origin = 0.0; SL->wlen = 1.0; SL->n_win = 1;
+    SL->done = b->d_slice_done; SL->epoch = b->d_slice_epoch;
+    if (b->slice_days > 0.0 && t_end == t_end) {
+        unsigned long long init[2] = {~0ULL, 0ULL}, got[2];
+        CU(cudaMemcpy(b->d_trange, init, sizeof(init), cudaMemcpyHostToDevice));
+        trange_kernel<<<256, 256>>>(b->d.t, b->d.status, b->n, b->d_trange);
+        CU(cudaMemcpy(got, b->d_trange, sizeof(got), cudaMemcpyDeviceToHost));
+        if (got[0] != ~0ULL) {
+            const double lo = unkey(got[0]), hi = unkey(got[1]);
+            const double D = b->slice_days;
+            /* a record boundary of the ephemeris, as a time relative to jd_ref */
+            double g0 = 0.0;
+            if (b->ephem) g0 = ab_slice_anchor(b->ephem);
+            double origin = 0.0, wlen = 0.0, span = -1.0;
+            if (hi <= t_end) { origin = g0 + floor((lo - g0) / D) * D; wlen = D; span = t_end - origin; }
+            else if (lo >= t_end) { origin = g0 + ceil((hi - g0) / D) * D; wlen = -D; span = origin - t_end; }
+            if (span > 0.0) {
+                double nw = ceil(span / D);
+                if (nw < 1.0) nw = 1.0;
+                if (nw > 1048576.0) { nw = 1.0; }
+                else { SL->origin = origin; SL->wlen = wlen; }
+                SL->n_win = (int)nw;
+            }
+        }
+    }
+    if (SL->n_win > 1) CU(cudaMemsetAsync(b->d_slice_done, 0, sizeof(int) * (size_t)b->n, 0));
+    return 0;
+}
+
+/* Working batch of the work-queue scheduler: one slot per resident thread of the per-particle kernels. */
+static int ensure_working_batch(assist_gpu_batch* b) {
+    if (!b->wblock) {
+        const bool k1 = (b->K == 1);
+        int threads = 0, t2 = 0;
+        cudaError_t eo = k1 ? ab_pp_resident_threads_k1_strict(&threads) : ab_pp_resident_threads_kv_strict(&threads);
+        if (eo != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(eo));
+        /* both math variants must fit: take the smaller resident count */
+        eo = k1 ? ab_pp_resident_threads_k1_fast(&t2) : ab_pp_resident_threads_kv_fast(&t2);
+        if (eo == cudaSuccess && t2 < threads) threads = t2;
+        size_t slots = (size_t)threads;
+        if (slots > (size_t)b->n) slots = ((size_t)b->n + 127) / 128 * 128;
+        CU(cudaMalloc((void**)&b->wblock, batch_bytes(slots, b->C)));
+        CU(cudaMemset(b->wblock, 0, batch_bytes(slots, b->C)));
+        layout_batch(b->w, b->wblock, slots, b->K, b->mode);
+        CU(cudaMalloc((void**)&b->d_queue, sizeof(unsigned long long)));
+        CU(cudaMalloc((void**)&b->d_slice_done, sizeof(int) * (size_t)b->n));
+        CU(cudaMalloc((void**)&b->d_slice_epoch, sizeof(int) * (size_t)b->n));
+        CU(cudaMalloc((void**)&b->d_trange, sizeof(double) * 2));
+    }
+    b->w.epsilon = b->d.epsilon; b->w.min_dt = b->d.min_dt; b->w.has_params = b->d.has_params;
+    return 0;
+}
+
 extern "C" int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int exact_finish_time, long max_steps, int flags) {
     if (!b) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(b->device));
@@ -592,30 +693,17 @@ extern "C" int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int 
         const bool k1 = (b->K == 1);
         if (b->sched_queue) {
             /* work-queue scheduling: a resident grid of threads pulls systems until the queue is empty */
-            if (!b->wblock) {
-                int threads = 0;
-                cudaError_t eo = k1 ? (fast ? ab_pp_resident_threads_k1_fast(&threads) : ab_pp_resident_threads_k1_strict(&threads))
-                                    : (fast ? ab_pp_resident_threads_kv_fast(&threads) : ab_pp_resident_threads_kv_strict(&threads));
-                if (eo != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(eo));
-                /* both math variants must fit: take the smaller resident count */
-                int t2 = 0;
-                eo = k1 ? (fast ? ab_pp_resident_threads_k1_strict(&t2) : ab_pp_resident_threads_k1_fast(&t2))
-                        : (fast ? ab_pp_resident_threads_kv_strict(&t2) : ab_pp_resident_threads_kv_fast(&t2));
-                if (eo == cudaSuccess && t2 < threads) threads = t2;
-                size_t slots = (size_t)threads;
-                if (slots > (size_t)b->n) slots = ((size_t)b->n + 127) / 128 * 128;
-                CU(cudaMalloc((void**)&b->wblock, batch_bytes(slots, b->C)));
-                CU(cudaMemset(b->wblock, 0, batch_bytes(slots, b->C)));
-                layout_batch(b->w, b->wblock, slots, b->K, b->mode);
-                CU(cudaMalloc((void**)&b->d_queue, sizeof(unsigned long long)));
-            }
-            b->w.epsilon = b->d.epsilon; b->w.min_dt = b->d.min_dt; b->w.has_params = b->d.has_params;
+            rc = ensure_working_batch(b);
+            if (rc) return rc;
+            AbSlices SL;
+            rc = build_slices(b, E, t_end, &SL);
+            if (rc) return rc;
             CU(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), 0));
             CU(cudaEventRecord(b->ev0, 0));
-            if (k1) e = fast ? ab_launch_pp_queue_k1_fast(E, F, b->d, b->w, t_end, exact_finish_time, b->d_queue, NULL, 0)
-                             : ab_launch_pp_queue_k1_strict(E, F, b->d, b->w, t_end, exact_finish_time, b->d_queue, NULL, 0);
-            else e = fast ? ab_launch_pp_queue_kv_fast(E, F, b->d, b->w, t_end, exact_finish_time, b->d_queue, NULL, 0)
-                          : ab_launch_pp_queue_kv_strict(E, F, b->d, b->w, t_end, exact_finish_time, b->d_queue, NULL, 0);
+            if (k1) e = fast ? ab_launch_pp_queue_k1_fast(E, F, b->d, b->w, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, 0)
+                             : ab_launch_pp_queue_k1_strict(E, F, b->d, b->w, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, 0);
+            else e = fast ? ab_launch_pp_queue_kv_fast(E, F, b->d, b->w, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, 0)
+                          : ab_launch_pp_queue_kv_strict(E, F, b->d, b->w, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, 0);
             return finish_launch(b, e, "pp_queue");
         }
         CU(cudaEventRecord(b->ev0, 0));
@@ -685,13 +773,38 @@ extern "C" int assist_gpu_batch_integrate_or_interpolate(assist_gpu_batch* b, co
     }
     double* d_times = (double*)((char*)b->d_out + out_bytes);
     CU(cudaMemcpy(d_times, times, sizeof(double) * n_times, cudaMemcpyHostToDevice));
-    CU(cudaEventRecord(b->ev0, 0));
     const bool fastm = (b->opt.math == ASSIST_GPU_MATH_FAST);
     cudaError_t e;
-    if (b->K == 1) e = fastm ? ab_launch_pp_dense_k1_fast(E, F, b->d, d_times, n_times, b->d_out, 0)
-                             : ab_launch_pp_dense_k1_strict(E, F, b->d, d_times, n_times, b->d_out, 0);
-    else e = fastm ? ab_launch_pp_dense_kv_fast(E, F, b->d, d_times, n_times, b->d_out, 0)
-                   : ab_launch_pp_dense_kv_strict(E, F, b->d, d_times, n_times, b->d_out, 0);
+    if (b->sched_queue) {
+        rc = ensure_working_batch(b);
+        if (rc) return rc;
+        /* slices need epochs that run in one direction; anything else is one slice */
+        bool mono = true;
+        const double dir = (n_times > 1) ? (times[n_times - 1] - times[0]) : 0.0;
+        for (int q = 1; q < n_times; q++)
+            if ((times[q] - times[q - 1]) * dir < 0.0 || !(times[q] == times[q])) mono = false;
+        AbSlices SL;
+        const double keep = b->slice_days;
+        if (!mono) b->slice_days = 0.0;
+        rc = build_slices(b, E, times[n_times - 1], &SL);
+        b->slice_days = keep;
+        if (rc) return rc;
+        if (SL.n_win > 1 && n_times > 1 && SL.wlen * dir < 0.0) {      /* systems ahead of the first epoch: do not slice */
+            SL.n_win = 1;
+        }
+        CU(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), 0));
+        CU(cudaEventRecord(b->ev0, 0));
+        if (b->K == 1) e = fastm ? ab_launch_pp_queue_k1_fast(E, F, b->d, b->w, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, 0)
+                                 : ab_launch_pp_queue_k1_strict(E, F, b->d, b->w, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, 0);
+        else e = fastm ? ab_launch_pp_queue_kv_fast(E, F, b->d, b->w, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, 0)
+                       : ab_launch_pp_queue_kv_strict(E, F, b->d, b->w, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, 0);
+    } else {
+        CU(cudaEventRecord(b->ev0, 0));
+        if (b->K == 1) e = fastm ? ab_launch_pp_dense_k1_fast(E, F, b->d, d_times, n_times, b->d_out, 0)
+                                 : ab_launch_pp_dense_k1_strict(E, F, b->d, d_times, n_times, b->d_out, 0);
+        else e = fastm ? ab_launch_pp_dense_kv_fast(E, F, b->d, d_times, n_times, b->d_out, 0)
+                       : ab_launch_pp_dense_kv_strict(E, F, b->d, d_times, n_times, b->d_out, 0);
+    }
     rc = finish_launch(b, e, "pp_dense");
     if (rc) return rc;
     CU(cudaMemcpy(out, b->d_out, out_bytes, cudaMemcpyDeviceToHost));

@@ -369,8 +369,13 @@ pp_integrate_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ A
     if (owns) pp_store(Bt, i, P);
 }
 
-/* Move one system between the population arrays (index `i`, stride Bt.n) and a working slot
- * (index `s`, stride W.n).  54 * C doubles, once per system per integrate() call. */
+/* Move one system between the population arrays (index `i`, stride src.n) and a working slot
+ * (index `s`, stride dst.n): 54 * C doubles.  CG: the source is read past L1 (another SM may have
+ * written it earlier in the same launch: time slices of one system run on whatever thread is free). */
+template <bool CG>
+__device__ __forceinline__ double pp_ld(const double* p) { return CG ? __ldcg(p) : *p; }
+
+template <bool CG>
 __device__ void pp_copy_system(const AbBatch& src, long long i, const AbBatch& dst, long long s, int nv) {
     const long long ns = src.n, nd = dst.n;
     const int C = src.C;
@@ -379,61 +384,184 @@ __device__ void pp_copy_system(const AbBatch& src, long long i, const AbBatch& d
     double* const d1[12] = {dst.pos, dst.vel, dst.acc, dst.x0, dst.v0, dst.a0, dst.csx, dst.csv, dst.ls_pos, dst.ls_vel, dst.ls_acc, dst.prm};
     double* const s7[6] = {src.b, src.g, src.e, src.csb, src.br, src.er};
     double* const d7[6] = {dst.b, dst.g, dst.e, dst.csb, dst.br, dst.er};
-    for (int a = 0; a < 12; a++)
-        for (int k = 0; k < Ca; k++) d1[a][(long long)k * nd + s] = s1[a][(long long)k * ns + i];
+    /* loads in groups of 12 / 7 before the stores, so that the trips to L2 overlap */
+    for (int k = 0; k < Ca; k++) {
+        double tmp[12];
+#pragma unroll
+        for (int a = 0; a < 12; a++) tmp[a] = pp_ld<CG>(s1[a] + (long long)k * ns + i);
+#pragma unroll
+        for (int a = 0; a < 12; a++) d1[a][(long long)k * nd + s] = tmp[a];
+    }
     for (int a = 0; a < 6; a++)
-        for (int j = 0; j < 7; j++)
-            for (int k = 0; k < Ca; k++)
-                d7[a][((long long)j * C + k) * nd + s] = s7[a][((long long)j * C + k) * ns + i];
+        for (int k = 0; k < Ca; k++) {
+            double tmp[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) tmp[j] = pp_ld<CG>(s7[a] + ((long long)j * C + k) * ns + i);
+#pragma unroll
+            for (int j = 0; j < 7; j++) d7[a][((long long)j * C + k) * nd + s] = tmp[j];
+        }
 }
 
-/* Work-queue scheduling: a fixed grid of resident threads; every thread takes the next system
- * from a global counter, moves its state into a working slot (slot-indexed arrays: coalesced
- * across the warp whatever the system indices are, and small enough to stay in L2), runs
- * reb_simulation_integrate for it, writes it back and takes the next one.  All threads of a CTA
- * do one step per loop trip (one barrier per trip, see pp_integrate_kernel), so lanes only
- * diverge inside a step.  No thread idles until the queue is empty: the 15x spread in step counts
- * between particles costs nothing but the very last stragglers. */
+__device__ __forceinline__ void pp_load_cg(const AbBatch& Bt, long long i, PPState& P) {
+    P.t = __ldcg(Bt.t + i); P.dt = __ldcg(Bt.dt + i); P.dt_last = __ldcg(Bt.dt_last + i); P.last_full_dt = __ldcg(Bt.last_full_dt + i);
+    P.status = __ldcg(Bt.status + i);
+    P.steps = __ldcg(Bt.steps + i); P.rejected = __ldcg(Bt.rejected + i); P.iters = __ldcg(Bt.iters + i); P.evals = __ldcg(Bt.evals + i);
+}
+
+/* State at one output epoch of assist_integrate_or_interpolate (reference src/assist.c:642-680, 556-597):
+ * the system sits in slot `s` of W at time P.t, its last completed step was P.dt_last long. */
+__device__ void pp_emit(const AbBatch& W, long long s, int nv, const PPState& P, double t, double* __restrict__ o) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double h = 1.0 - (P.t - t) / P.dt_last;
+    if (P.status > 0) {
+        for (int q = 0; q < 6 * (1 + nv); q++) o[q] = nan;
+    } else if (P.t - t == 0.) {
+        for (int j = 0; j <= nv; j++)
+            for (int c = 0; c < 3; c++) {
+                o[6 * j + c] = W.pos[(long long)(3 * j + c) * W.n + s];
+                o[6 * j + 3 + c] = W.vel[(long long)(3 * j + c) * W.n + s];
+            }
+    } else if (h < 0.0 || h >= 1.0 || !ab_isnormal(h)) {
+        for (int q = 0; q < 6 * (1 + nv); q++) o[q] = nan;
+    } else {
+        ab_interpolate(W, s, nv, P.dt_last, h, o);
+    }
+}
+
+/* entry of reb_simulation_integrate(tmax) */
+__device__ __forceinline__ void pp_integrate_entry(PPState& P, double tmax) {
+    if (tmax != P.t) P.dt = copysign(P.dt, (tmax > P.t) ? 1.0 : -1.0);
+    P.last_full_dt = P.dt;
+    P.dt_last = 0.;
+    P.status = -1;
+}
+
+/* Time slices: the span of the call is cut into n_win windows [.., origin + (w + 1) * wlen) and the queue
+ * hands out (window, system) pairs, window-major.  A thread takes a system through one window and puts
+ * it back; the next window of that system is picked up by whichever thread gets to it (after `done[sys]`
+ * says the previous one is stored).  Slicing never touches the step sequence of a system -- a step that
+ * has started is finished, and the next window resumes exactly where integrate() was paused -- but it
+ *   - keeps every lane busy to the end when systems differ 10x in step count or are few (comets), and
+ *   - keeps the lanes of a warp within the same few Chebyshev records of the ephemeris. */
+
+/* Work-queue scheduling: a fixed grid of resident threads; every thread takes the next (window, system)
+ * pair from a global counter, moves the system's state into a working slot (slot-indexed arrays:
+ * coalesced across the warp whatever the system indices are), runs reb_simulation_integrate for it up to
+ * the end of the window, writes it back and takes the next pair.  All threads of a CTA do one step per
+ * loop trip (one barrier per trip, see pp_integrate_kernel), so lanes only diverge inside a step.
+ *
+ * With `times` the kernel runs assist_integrate_or_interpolate for the n_times epochs of every system
+ * (out[n_times][n][K][6]) instead of one integrate(tmax): the same loop, with the epochs that fall
+ * inside the last completed step written out between steps. */
 __global__ void __launch_bounds__(AB_PP_BLOCK, AB_PP_MIN_BLOCKS)
 pp_queue_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F,
                 const __grid_constant__ AbBatch Bt, const __grid_constant__ AbBatch W,
                 double tmax, int exact_finish_time, unsigned long long* __restrict__ queue_head,
-                const int* __restrict__ order) {
+                const __grid_constant__ AbSlices SL, const double* __restrict__ times, int n_times, double* __restrict__ out) {
     const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    bool have = false, exhausted = (slot >= W.n);
+    const bool dense = (times != nullptr);
+    const double wsign = (SL.wlen < 0.0) ? -1.0 : 1.0;
+    const unsigned long long n_items = (unsigned long long)SL.n_win * (unsigned long long)Bt.n;
+    bool have = false, pending = false, exhausted = (slot >= W.n), integrating = false;
     long long sys = -1;
-    int nv = 0;
+    int nv = 0, ep = 0, win = 0;
+    double target = tmax, wend = 0.0;
     PPState P;
     while (true) {
         while (!have && !exhausted) {
-            const unsigned long long q = atomicAdd(queue_head, 1ULL);
-            if (q >= (unsigned long long)Bt.n) { exhausted = true; break; }
-            sys = order ? order[q] : (long long)q;
-            pp_load(Bt, sys, P);
-            if (P.status >= 1000) continue;           /* failed earlier (ephemeris error): skip */
+            if (!pending) {
+                const unsigned long long q = atomicAdd(queue_head, 1ULL);
+                if (q >= n_items) { exhausted = true; break; }
+                win = (int)(q / (unsigned long long)Bt.n);
+                sys = (long long)(q % (unsigned long long)Bt.n);
+                pending = true;
+            }
+            /* the previous window of this system must have been stored (it was handed out earlier, so it is running or done) */
+            if (win > 0 && *((volatile int*)(SL.done + sys)) < win) break;       /* try again after the next trip */
+            __threadfence();
+            pending = false;
+            pp_load_cg(Bt, sys, P);
+            wend = SL.origin + (double)(win + 1) * SL.wlen;
+            const bool last = (win == SL.n_win - 1);
+            const bool beyond = !last && wsign * P.t >= wsign * wend;            /* nothing to do in this window */
+            bool skip = (P.status >= 1000);                                       /* failed earlier (ephemeris error) */
+            if (!skip && !dense) {
+                if (win == 0) {
+                    pp_integrate_entry(P, tmax);                                  /* every system enters integrate() in window 0 */
+                    if (beyond) { pp_store(Bt, sys, P); skip = true; }
+                } else if (P.status >= 0 || beyond) {
+                    skip = true;                                                  /* integrate() has returned / resumes later */
+                }
+                integrating = true;
+            } else if (!skip) {
+                ep = (win == 0) ? 0 : __ldcg(SL.epoch + sys);
+                integrating = (win > 0 && (P.status == -1 || P.status == -2));    /* paused inside an integrate(times[ep]) */
+                if (integrating) target = times[ep];
+                if (beyond || (!integrating && ep >= n_times)) {
+                    if (win == 0) SL.epoch[sys] = 0;
+                    skip = true;
+                }
+            }
+            if (skip) {
+                if (SL.n_win > 1) { __threadfence(); *((volatile int*)(SL.done + sys)) = win + 1; }
+                continue;
+            }
             nv = Bt.nv[sys];
             W.nv[slot] = nv;
             W.status[slot] = 0;
-            pp_copy_system(Bt, sys, W, slot, nv);
-            if (tmax != P.t) P.dt = copysign(P.dt, (tmax > P.t) ? 1.0 : -1.0);
-            P.last_full_dt = P.dt;
-            P.dt_last = 0.;
-            P.status = -1;
+            pp_copy_system<true>(Bt, sys, W, slot, nv);
             have = true;
         }
-        if (!__syncthreads_or(have ? 1 : 0)) break;
-        if (have) {
-            if (ab_check_exit(P.t, P.dt, P.dt_last, P.status, tmax, exact_finish_time, P.last_full_dt) >= 0) {
-                if (exact_finish_time == 1) P.dt = P.last_full_dt;
-                pp_copy_system(W, slot, Bt, sys, nv);
-                if (W.status[slot] >= 1000) Bt.status[sys] = W.status[slot];
-                pp_store(Bt, sys, P);
-                have = false;
-            } else if (F.gr_eih_sources == 1 && !F.geocentric) {
-                pp_step_nodes<PP_KM>(E, F, W, slot, P);
-            } else {
-                pp_step<PP_KM>(E, F, W, slot, P);
+        if (!__syncthreads_or((have || pending) ? 1 : 0)) break;
+        /* per-lane bookkeeping until a step is due (so that every trip of a busy lane ends in a step), the window
+         * ends or the system is done */
+        const bool last = (win == SL.n_win - 1);
+        bool step_due = false;
+        while (have) {
+            if (dense && !integrating) {
+                /* epochs inside the last completed step are interpolated; the first one outside starts an integrate() */
+                while (ep < n_times) {
+                    target = times[ep];
+                    const double dts = copysign(1., P.dt_last);
+                    if (dts * (P.t - P.dt_last) > dts * target || dts * target > dts * P.t || P.dt_last == 0.0) {
+                        pp_integrate_entry(P, target);
+                        integrating = true;
+                        break;
+                    }
+                    pp_emit(W, slot, nv, P, target, out + ((long long)ep * Bt.n + sys) * Bt.K * 6);
+                    ep++;
+                }
             }
+            if (integrating && !last && wsign * P.t >= wsign * wend) break;      /* end of the window: pause integrate() */
+            if (integrating && ab_check_exit(P.t, P.dt, P.dt_last, P.status, target, exact_finish_time, P.last_full_dt) < 0) {
+                step_due = true;
+                break;
+            }
+            if (integrating) {           /* integrate() returns */
+                if (exact_finish_time == 1) P.dt = P.last_full_dt;
+                integrating = false;
+                if (dense) {
+                    pp_emit(W, slot, nv, P, target, out + ((long long)ep * Bt.n + sys) * Bt.K * 6);
+                    ep++;
+                    continue;
+                }
+            }
+            break;                       /* finished */
+        }
+        /* the lanes left the bookkeeping through different exits: bring the warp back together, so that the step
+         * below (99 % of the trip) runs once for the whole warp */
+        __syncwarp();
+        if (step_due) {
+            if (F.gr_eih_sources == 1 && !F.geocentric) pp_step_nodes<PP_KM>(E, F, W, slot, P);
+            else pp_step<PP_KM>(E, F, W, slot, P);
+        } else if (have) {
+            /* paused at the end of the window, or finished: back to the population arrays */
+            pp_copy_system<false>(W, slot, Bt, sys, nv);
+            if (W.status[slot] >= 1000) Bt.status[sys] = W.status[slot];
+            pp_store(Bt, sys, P);
+            if (dense) SL.epoch[sys] = ep;
+            if (SL.n_win > 1) { __threadfence(); *((volatile int*)(SL.done + sys)) = win + 1; }
+            have = false;
         }
     }
 }
@@ -732,10 +860,11 @@ cudaError_t PP_NAME(ab_launch_pp_integrate)(const AbEphem& E, const AbForceOpts&
 }
 
 cudaError_t PP_NAME(ab_launch_pp_queue)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const AbBatch& W, double tmax, int exact,
-                                        unsigned long long* queue_head, const int* order, cudaStream_t st) {
+                                        unsigned long long* queue_head, const AbSlices& SL, const double* times, int n_times, double* out,
+                                        cudaStream_t st) {
     const int grid = (W.n + AB_PP_BLOCK - 1) / AB_PP_BLOCK;
     if (grid < 1) return cudaSuccess;
-    pp_queue_kernel<<<grid, AB_PP_BLOCK, 0, st>>>(E, F, Bt, W, tmax, exact, queue_head, order);
+    pp_queue_kernel<<<grid, AB_PP_BLOCK, 0, st>>>(E, F, Bt, W, tmax, exact, queue_head, SL, times, n_times, out);
     return cudaGetLastError();
 }
 

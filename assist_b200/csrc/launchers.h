@@ -22,11 +22,11 @@
                                                 double tmax, int exact, int resume, long long step_cap,            \
                                                 const int* active, int n_active, cudaStream_t st);                 \
     cudaError_t ab_launch_pp_queue_k1_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const AbBatch& W,  \
-                                            double tmax, int exact, unsigned long long* queue_head, const int* order, \
-                                            cudaStream_t st);                                                       \
+                                            double tmax, int exact, unsigned long long* queue_head, const AbSlices& SL, \
+                                            const double* times, int n_times, double* out, cudaStream_t st);        \
     cudaError_t ab_launch_pp_queue_kv_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const AbBatch& W,  \
-                                            double tmax, int exact, unsigned long long* queue_head, const int* order, \
-                                            cudaStream_t st);                                                       \
+                                            double tmax, int exact, unsigned long long* queue_head, const AbSlices& SL, \
+                                            const double* times, int n_times, double* out, cudaStream_t st);        \
     cudaError_t ab_pp_resident_threads_k1_##sfx(int* threads);                                                      \
     cudaError_t ab_pp_resident_threads_kv_##sfx(int* threads);                                                      \
     cudaError_t ab_launch_pp_dense_k1_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt,             \

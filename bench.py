@@ -4,16 +4,18 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N>1)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own C code on the host cores
 
-Workload (BASELINE.json configs[2], "C3"): synthetic NEO+MBA population, per-particle
-adaptive dt, all default forces (mask 0x7F, gr_eih_sources 1), 10 yr forward, synthetic
-DE440-format planets .bsp + 16-asteroid .bsp.  One bench "step" = one full pass of the hot
-path over the batch (every particle integrated over the whole span).  Weak scaling: every
-GPU integrates its own --n-per-gpu particles; no collective on the data path.
+Default workload (BASELINE.json configs[2], "c3", the configuration the metric is quoted on):
+synthetic NEO+MBA population, per-particle adaptive dt, all default forces (mask 0x7F,
+gr_eih_sources 1), 10 yr forward, synthetic DE440-layout planets .bsp + 16-asteroid .bsp.
+The other configs of BASELINE.json are available with --workload c2|c4|c5.
+One bench "step" = one full pass of the hot path over the batch (every particle integrated over
+the whole span).  Weak scaling: every GPU integrates its own --n-per-gpu particles; no collective
+on the data path (torch.distributed only carries the barrier and a max/sum of scalars).
 
 `value`   accepted IAS15 particle-steps per second, whole job, inputs resident in HBM
           (device snapshot -> integrate), timed between barriers, max over ranks.
-`e2e`     same metric with the step's inputs copied from pinned host memory and the final
-          states copied back inside the timed region.
+`e2e`     same metric with the step's inputs copied from pinned host memory and the results
+          copied back inside the timed region.
 `roofline` FP64: algorithmic flops / kernel time / measured DFMA peak.
 `cpu_baseline` the reference's src/*.c (oracle/_ref) on the host cores, bounded sample.
 """
@@ -33,21 +35,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SPAN_DAYS = 3652.5
-FORCES = 0x7F
-MIN_DT = 1e-3
 METRIC = "test-particle IAS15 steps/sec (all forces)"
 UNIT = "particle-steps/s"
 
 # algorithmic flops, hand-counted from the reference source
-F_FORCE_NV0 = 1053.0          # one force evaluation, Nv = 0, no non-grav
-F_STEPPER_SUBSTEP = 300.0     # predictor + g/b update per substep (per body)
-F_STEP_FINAL = 150.0          # dt control, advance, predict_next per step (per body)
+F_FORCE = {0: 1053.0, 6: 7540.0}      # one force evaluation of one system, default mask, one EIH source (Nv = 0 / 6)
+F_MARSDEN = {0: 92.0, 6: 982.0}       # extra for the non-gravitational term
+F_STEPPER_SUBSTEP = 300.0             # predictor + g/b update per substep, per body
+F_STEP_FINAL = 150.0                  # dt control, advance, predict_next per step, per body
 
 
-def ephem_flops_per_eval(planet_P, ast_P):
-    """Algorithmic flops of one per-particle body-table evaluation: position series for every
-    body (T recurrence 3(P-2), three sums 6P, argument 10), velocity too for the Sun."""
+def ephem_flops_per_table(planet_P, ast_P):
+    """Algorithmic flops of one body table (all bodies at one time): position series for every body
+    (T recurrence 3(P-2), three sums 6P, argument 10), velocity too for the Sun, EIH pair sums."""
     f = 0.0
     for P in planet_P:
         f += 3 * (P - 2) + 6 * P + 10 + 3
@@ -56,6 +56,35 @@ def ephem_flops_per_eval(planet_P, ast_P):
         f += 3 * (P - 2) + 6 * P + 10 + 6
     f += 10 * 25                                        # EIH pair sums for one source (10 bodies)
     return f
+
+
+def workloads():
+    """BASELINE.json configs as (population, batch options, span).  state generators return [n][K][6]."""
+    from assist_b200.synth import populations as pop
+    return {
+        "c3": dict(desc="C3 NEO+MBA population (20% NEO / 80% main belt), per-particle adaptive dt, forces 0x7F, "
+                        "gr_eih_sources 1, min_dt 0.001 d, 3652.5 d forward",
+                   gen=lambda n, seed: pop.neo_mba_mix(n, seed=seed)[:, None, :], prm=None,
+                   seed=20261703, n=1000000, nvar=0, mode="pp", forces=0x7F, min_dt=1e-3, span=3652.5, dense=None, cpu_per_core=512),
+        "c2": dict(desc="C2 main-belt population in ONE simulation (shared step: global dt and convergence), forces 0x77, "
+                        "gr_eih_sources 1, 3652.5 d forward",
+                   gen=lambda n, seed: pop.main_belt(n, seed=seed)[:, None, :], prm=None,
+                   seed=20261702, n=10000, nvar=0, mode="shared", forces=0x77, min_dt=0.0, span=3652.5, dense=None, cpu_per_core=300),
+        "c4": dict(desc="C4 main-belt particles, each with 6 first-order variational particles (identity initial conditions), "
+                        "per-particle dt, forces 0x7F, 1826.25 d forward",
+                   gen=lambda n, seed: pop.with_variations(pop.main_belt(n, seed=seed), 6), prm=None,
+                   seed=20261704, n=100000, nvar=6, mode="pp", forces=0x7F, min_dt=0.0, span=1826.25, dense=None, cpu_per_core=600),
+        "c5": dict(desc="C5 comets with Marsden A1/A2/A3, per-particle dt, forces 0x7F, min_dt 0.001 d, 18262.5 d BACKWARD, "
+                        "dense output every 10 d (assist_integrate_or_interpolate semantics)",
+                   gen=lambda n, seed: pop.comets(n, seed=seed)[0][:, None, :],
+                   prm=lambda n, seed: pop.comets(n, seed=seed)[1][:, None, :],
+                   seed=20261705, n=100000, nvar=0, mode="pp", forces=0x7F, min_dt=1e-3, span=-18262.5, dense=10.0, cpu_per_core=64),
+    }
+
+
+def dense_epochs(t0, wl):
+    k = np.arange(1, int(abs(wl["span"]) / wl["dense"]) + 1)
+    return np.ascontiguousarray(t0 + np.sign(wl["span"]) * wl["dense"] * k)
 
 
 # ---------------------------------------------------------------------------------------
@@ -103,7 +132,7 @@ class ClockSampler:
 # CPU arm: the reference's own C code (oracle/_ref) on the host cores
 # ---------------------------------------------------------------------------------------
 def _cpu_worker(job):
-    core, planets, asteroids, t0, state, t_end = job
+    core, planets, asteroids, t0, state, params, wl = job
     try:
         os.sched_setaffinity(0, {core})
     except Exception:
@@ -112,31 +141,65 @@ def _cpu_worker(job):
     import refharness as rh
     lib = rh.ref_lib()
     eph = rh.open_ephem(lib, planets, asteroids)
+    n = state.shape[0]
+    kw = dict(forces=wl["forces"], min_dt=wl["min_dt"])
     t_start = time.perf_counter()
-    _, _, _, tot = rh.integrate_each(lib, eph, t0, state, t_end, forces=FORCES, min_dt=MIN_DT)
-    return tot["steps"], tot["force_evals"], tot["pc_iterations"], time.perf_counter() - t_start
+    if wl["mode"] == "shared":
+        s = rh.Sim(lib, eph, t0, state, **kw)
+        s.integrate(t0 + wl["span"])
+        c = s.counters()
+        steps, evals = c["steps"] * n, c["force_evals"] * n
+        s.close()
+    elif wl["dense"]:
+        times = dense_epochs(t0, wl)
+        steps = evals = 0
+        for i in range(n):
+            s = rh.Sim(lib, eph, t0, state[i:i + 1], params=None if params is None else params[i:i + 1], **kw)
+            for t in times:
+                lib.assist_integrate_or_interpolate(s.ax, float(t))
+            c = s.counters()
+            steps += c["steps"]; evals += c["force_evals"]
+            s.close()
+    else:
+        _, _, _, tot = rh.integrate_each(lib, eph, t0, state, t0 + wl["span"], params=params, **kw)
+        steps, evals = tot["steps"], tot["force_evals"]
+    return steps, evals, time.perf_counter() - t_start
 
 
-def cpu_reference_run(paths, state, t0, t_end, cores):
-    """One simulation per particle, particles split over `cores` pinned processes.  Returns dict."""
+def cpu_reference_run(paths, state, params, t0, wl, cores):
+    """One simulation per particle (ONE simulation in all for the shared-step workload, which cannot be split
+    without changing its dt sequence), particles split over `cores` pinned processes."""
     import multiprocessing as mp
-    chunks = np.array_split(np.arange(state.shape[0]), cores)
+    plain = {k: wl[k] for k in ("mode", "forces", "min_dt", "span", "dense")}
+    if wl["mode"] == "shared":
+        cores = 1
+    # round-robin, not contiguous: the population is ordered (NEOs first, 6x the steps of a main-belt object),
+    # and the reference arm is timed as the slowest process
+    chunks = [np.arange(c, state.shape[0], cores) for c in range(cores)]
     avail = sorted(os.sched_getaffinity(0))
-    jobs = [(avail[c % len(avail)], paths["planets_bsp"], paths["asteroids_bsp"], t0, state[idx], t_end)
-            for c, idx in enumerate(chunks) if idx.size]
+    jobs = [(avail[c % len(avail)], paths["planets_bsp"], paths["asteroids_bsp"], t0, state[idx],
+             None if params is None else params[idx], plain) for c, idx in enumerate(chunks) if idx.size]
     ctx = mp.get_context("fork")
-    t_start = time.perf_counter()
     with ctx.Pool(len(jobs)) as pool:
         res = pool.map(_cpu_worker, jobs)
-    wall = time.perf_counter() - t_start
-    busy = max(r[3] for r in res)                       # max over processes, excluding pool start-up
+    busy = max(r[2] for r in res)                       # max over processes, excluding pool start-up
     steps = sum(r[0] for r in res)
-    return {"steps": steps, "evals": sum(r[1] for r in res), "iters": sum(r[2] for r in res), "wall_s": wall, "busy_s": busy,
-            "steps_per_s": steps / busy}
+    return {"steps": steps, "evals": sum(r[1] for r in res), "busy_s": busy, "steps_per_s": steps / busy, "cores": len(jobs)}
 
 
 def have_ref():
     return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libassist_ref.so"))
+
+
+def cpu_sample(wl, st, prm, cores, override):
+    """Bounded sample of the workload for the CPU arm, spread over the population (same NEO/MBA mix)."""
+    n_sample = override or (wl["cpu_per_core"] if wl["mode"] == "shared" else wl["cpu_per_core"] * cores)
+    n_sample = min(n_sample, st.shape[0])
+    pick = np.linspace(0, st.shape[0] - 1, n_sample).astype(np.int64)
+    how = ("ONE %d-particle shared-step simulation on one core" % n_sample if wl["mode"] == "shared" else
+           "%d particles spread over the %d-particle population, one simulation per particle, one pinned process per core"
+           % (n_sample, st.shape[0]))
+    return st[pick], (None if prm is None else prm[pick]), how + ", full span; reference src/*.c + IAS15 restatement (oracle/_ref)"
 
 
 # ---------------------------------------------------------------------------------------
@@ -146,11 +209,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n-per-gpu", type=int, default=1000000)
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--n-per-gpu", type=int, default=0, help="particles per GPU (0 = the workload's own size)")
     ap.add_argument("--math", default="strict", choices=["strict", "fast"])
-    ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the CPU baseline sample (0 = 512 per core)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the CPU baseline sample (0 = sized for ~10-30 s)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: --n-per-gpu particles on every GPU; strong: --n-per-gpu particles in total, sliced")
+                    help="weak: --n-per-gpu particles on every GPU; strong: that many in total, sliced")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -158,12 +222,20 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    from assist_b200 import sharding
     from assist_b200.synth import ephem_writer, populations
+    wl = workloads()[args.workload]
+    n_req = args.n_per_gpu or wl["n"]
     T0 = populations.T0
-    T_END = T0 + SPAN_DAYS
+    T_END = T0 + wl["span"]
     data_dir = os.path.join(ROOT, "data")
-    workload = ("C3 NEO+MBA population (20%% NEO / 80%% main belt), per-particle adaptive dt, forces 0x7F, "
-                "gr_eih_sources 1, min_dt %g d, %.1f d forward" % (MIN_DT, SPAN_DAYS))
+
+    def population(world_, rank_):
+        st_ = sharding.local_population(lambda n, seed: wl["gen"](n, seed), n_req, wl["seed"], world_, rank_, args.scaling)
+        pr_ = None
+        if wl["prm"]:
+            pr_ = np.ascontiguousarray(sharding.local_population(lambda n, seed: wl["prm"](n, seed), n_req, wl["seed"], world_, rank_, args.scaling))
+        return np.ascontiguousarray(st_), pr_
 
     # ------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -174,25 +246,21 @@ def main():
             return 0
         paths = ephem_writer.write_all(data_dir)
         cores = len(os.sched_getaffinity(0))
-        n_sample = args.cpu_sample or 512 * cores
-        st = populations.neo_mba_mix(args.n_per_gpu, seed=20261703)
-        # spread the sample over the population so that it holds the same NEO/MBA mix
-        pick = np.linspace(0, args.n_per_gpu - 1, n_sample).astype(np.int64)
-        sample = st[pick]
-        for _ in range(max(args.warmup, 0) and 1):
-            cpu_reference_run(paths, sample[:cores * 2], T0, T_END, cores)
-        tot_steps, tot_time = 0, 0.0
+        st, prm = population(1, 0)
+        s_st, s_pr, how = cpu_sample(wl, st, prm, cores, args.cpu_sample)
+        if args.warmup:
+            k = max(2, cores)
+            cpu_reference_run(paths, s_st[:k], None if s_pr is None else s_pr[:k], T0, wl, cores)
+        tot_steps, tot_time, used = 0, 0.0, cores
         for _ in range(args.steps):
-            r = cpu_reference_run(paths, sample, T0, T_END, cores)
-            tot_steps += r["steps"]; tot_time += r["busy_s"]
+            r = cpu_reference_run(paths, s_st, s_pr, T0, wl, cores)
+            tot_steps += r["steps"]; tot_time += r["busy_s"]; used = r["cores"]
         value = tot_steps / tot_time
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * tot_time / args.steps, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": 1e3 * tot_time / args.steps, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload, "n_per_gpu": args.n_per_gpu, "sample_particles": int(n_sample)},
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
-                                 "sample": "%d particles spread over the %d-particle population, full %.1f d span, one simulation per particle, "
-                                           "one pinned process per core; reference src/*.c + IAS15 restatement (oracle/_ref)" % (n_sample, args.n_per_gpu, SPAN_DAYS)},
+                "config": {"workload": wl["desc"], "n_per_gpu": n_req, "sample_particles": int(s_st.shape[0])},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "reference", "sample": how},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -220,134 +288,159 @@ def main():
     lib.assist_gpu_set_device(local_rank)
 
     if rank == 0:
-        paths = ephem_writer.write_all(data_dir)
+        ephem_writer.write_all(data_dir)
     barrier()
     paths = ephem_writer.write_all(data_dir)
 
-    from assist_b200 import sharding
-    st = sharding.local_population(populations.neo_mba_mix, args.n_per_gpu, 20261703, world, rank, args.scaling)
-    n = st.shape[0]
+    st, prm = population(world, rank)
+    n, K = st.shape[0], st.shape[1]
+    shared = wl["mode"] == "shared"
     math_mode = ab.MATH_FAST if args.math == "fast" else ab.MATH_STRICT
     eph = ab.EphemHandle(paths["planets_bsp"], paths["asteroids_bsp"])
-    b = ab.Batch(eph, n, 0, ab.PER_PARTICLE, forces=FORCES, gr_eih_sources=1, min_dt=MIN_DT, math=math_mode)
-
-    # pinned host buffers for the end-to-end leg
-    nbytes = n * 6 * 8
-    h_in = lib.assist_gpu_host_alloc(nbytes)
-    h_out = lib.assist_gpu_host_alloc(nbytes)
-    if not h_in or not h_out:
-        raise SystemExit("pinned allocation failed: " + lib.assist_gpu_last_error().decode())
-    in_arr = np.ctypeslib.as_array(ctypes.cast(h_in, ctypes.POINTER(ctypes.c_double)), shape=(n, 1, 6))
-    out_arr = np.ctypeslib.as_array(ctypes.cast(h_out, ctypes.POINTER(ctypes.c_double)), shape=(n, 1, 6))
-    in_arr[:, 0, :] = st
+    b = ab.Batch(eph, n, wl["nvar"], ab.SHARED_STEP if shared else ab.PER_PARTICLE, forces=wl["forces"], gr_eih_sources=1,
+                 min_dt=wl["min_dt"], math=math_mode)
+    times = dense_epochs(T0, wl) if wl["dense"] else None
 
     def dptr(a):
-        return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 
     def check(rc, what):
         if rc != 0:
             raise SystemExit("%s failed (%d): %s" % (what, rc, lib.assist_gpu_last_error().decode()))
 
-    check(lib.assist_gpu_batch_set_state(b.ptr, T0, 0.001, dptr(in_arr), None, None), "set_state")
-    b.snapshot()
+    def pinned(shape):
+        nb = int(np.prod(shape)) * 8
+        p = lib.assist_gpu_host_alloc(nb)
+        if not p:
+            raise SystemExit("pinned allocation failed: " + lib.assist_gpu_last_error().decode())
+        return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_double)), shape=shape), nb
+
+    # pinned host buffers for the end-to-end leg
+    in_arr, in_bytes = pinned((n, K, 6))
+    in_arr[...] = st
+    prm_arr, prm_bytes = None, 0
+    if prm is not None:
+        prm_arr, prm_bytes = pinned((n, K, 3))
+        prm_arr[...] = prm
+    out_arr, out_bytes = pinned((n, K, 6) if times is None else (times.size, n, K, 6))
+
+    def set_state():
+        check(lib.assist_gpu_batch_set_state(b.ptr, T0, 0.001, dptr(in_arr), dptr(prm_arr), None), "set_state")
+
+    def run(to_host):
+        if times is None:
+            check(lib.assist_gpu_batch_integrate(b.ptr, T_END, 1, 0), "integrate")
+            if to_host:
+                check(lib.assist_gpu_batch_get_state(b.ptr, dptr(out_arr), None, None, None, None, None), "get_state")
+        else:
+            # the epochs entry point returns its [epoch][particle] block to the host buffer in both legs
+            check(lib.assist_gpu_batch_integrate_or_interpolate(b.ptr, dptr(times), times.size, dptr(out_arr)), "integrate_or_interpolate")
 
     def device_step():
         b.restore()
-        b.integrate(T_END)
+        run(False)
 
     def e2e_step():
-        check(lib.assist_gpu_batch_set_state(b.ptr, T0, 0.001, dptr(in_arr), None, None), "set_state")
-        check(lib.assist_gpu_batch_integrate(b.ptr, T_END, 1, 0), "integrate")
-        check(lib.assist_gpu_batch_get_state(b.ptr, dptr(out_arr), None, None, None, None, None), "get_state")
+        set_state()
+        run(True)
 
+    set_state()
+    b.snapshot()
     for _ in range(args.warmup):
         device_step()
-    s0 = b.stats()
-    steps_per_pass = s0["steps"]
-    evals_per_pass = s0["force_evals"]
-    iters_per_pass = s0["pc_iterations"]
-    launches_per_pass = s0["kernel_launches"] if args.warmup else None
 
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     t_start = time.perf_counter()
-    kernel_ms = 0.0
-    launches = 0
+    kernel_ms, launches = 0.0, 0
+    sk = None
     for _ in range(args.steps):
         device_step()
         sk = b.stats()
         kernel_ms += sk["last_kernel_ms"]
         launches += sk["kernel_launches"]
-        steps_per_pass = sk["steps"]; evals_per_pass = sk["force_evals"]; iters_per_pass = sk["pc_iterations"]
     barrier()
     t_dev = time.perf_counter() - t_start
     clocks = sampler.stop()
+    iters_per_step = sk["pc_iterations"] / max(sk["steps"], 1)
+    steps_per_pass = sk["steps"] * (n if shared else 1)    # a shared-step batch reports global steps; the metric counts particle-steps
+    evals_per_pass = sk["force_evals"]
 
+    dev_result = None if times is not None else b.get_state()["state"].copy()
     barrier()
     t_start = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
     barrier()
     t_e2e = time.perf_counter() - t_start
-
-    # parity guard inside the bench: the e2e result equals the device-resident result
-    dev_state = b.get_state()["state"]
-    if not np.array_equal(dev_state, out_arr):
+    # guard inside the bench: the end-to-end leg produced the same numbers as the device-resident leg
+    if dev_result is not None and not np.array_equal(dev_result, out_arr):
         raise SystemExit("bench.py: e2e and device-resident paths disagree")
+    if times is not None and not np.isfinite(out_arr).all():
+        raise SystemExit("bench.py: dense output holds non-finite values")
 
     # reduce over ranks: max time, sum steps
-    (t_dev, t_e2e, kernel_ms), (tot_steps, tot_evals, tot_iters, tot_n) = sharding.reduce_max_sum(
-        dist, [t_dev, t_e2e, kernel_ms], [float(steps_per_pass), float(evals_per_pass), float(iters_per_pass), float(n)],
-        device="cuda" if dist is not None else None)
-
+    (t_dev, t_e2e, kernel_ms), (tot_steps, tot_n) = sharding.reduce_max_sum(
+        dist, [t_dev, t_e2e, kernel_ms], [float(steps_per_pass), float(n)], device="cuda" if dist is not None else None)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
-    K = args.steps
-    value = tot_steps * K / t_dev
-    e2e_value = tot_steps * K / t_e2e
+    S = args.steps
+    value = tot_steps * S / t_dev
+    e2e_value = tot_steps * S / t_e2e
 
     # roofline of the fused integrate kernel (this rank): algorithmic flops / kernel time
     peak = lib.assist_gpu_measure_fp64_peak(2000)
+    f_force = F_FORCE[wl["nvar"]] + (F_MARSDEN[wl["nvar"]] if prm is not None else 0.0)
     sub_evals = evals_per_pass - steps_per_pass          # evaluations at Gauss-Radau nodes
-    flops = evals_per_pass * F_FORCE_NV0 + sub_evals * F_STEPPER_SUBSTEP + steps_per_pass * F_STEP_FINAL
+    flops = evals_per_pass * f_force + sub_evals * F_STEPPER_SUBSTEP * K + steps_per_pass * F_STEP_FINAL * K
     planet_P = [11, 14, 10, 13, 13, 13, 11, 8, 7, 6, 6, 6]     # Sun, Mer, Ven, EMB, Earth, Moon, Mar..Plu (synthetic DE440 layout)
-    f_eph = ephem_flops_per_eval(planet_P, [16] * 16)
-    kernel_s = kernel_ms * 1e-3 / K
+    f_eph = ephem_flops_per_table(planet_P, [16] * 16)
+    kernel_s = kernel_ms * 1e-3 / S
     achieved = flops / kernel_s / 1e12
-    # the body tables are needed at 8 times per step attempt (start + 7 nodes); the reference's 7-slot time cache
-    # gives it the same reuse, so the algorithmic ephemeris work is 8 evaluations per step, not one per force call
-    achieved_eph = (flops + 8.0 * steps_per_pass * f_eph) / kernel_s / 1e12
+    # body tables are needed at 8 times per step attempt (start + 7 nodes); the reference's 7-slot time cache gives it the
+    # same reuse, so the algorithmic ephemeris work is 8 tables per step.  In a shared-step batch all particles share them.
+    eph_flops = 8.0 * f_eph * (sk["steps"] if shared else steps_per_pass)
+    achieved_eph = (flops + eph_flops) / kernel_s / 1e12
+    # DRAM bytes of one launch of this kernel, from the committed ncu capture of the same configuration (profiles/README.md)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get("%s:%d:%s" % (args.workload, n, args.math))
+    except OSError:
+        pass
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None,
-                "kernel": "pp_integrate_kernel (fused ephemeris + forces + IAS15), %d launches per pass" % (launches // K),
-                "flops_per_force_eval": F_FORCE_NV0, "achieved_incl_ephemeris": achieved_eph, "frac_incl_ephemeris": achieved_eph / peak,
+                "traffic": traffic,
+                "kernel": "fused ephemeris + forces + IAS15 integrate kernel (%s), %d launch(es) per pass"
+                          % ("sh_integrate_kernel" if shared else "pp_dense_kernel" if times is not None else "pp_queue_kernel", launches // S),
+                "flops_per_force_eval": f_force, "achieved_incl_ephemeris": achieved_eph, "frac_incl_ephemeris": achieved_eph / peak,
                 "ephemeris_flops_per_table": f_eph, "ephemeris_tables_per_step": 8, "force_evals_per_s": evals_per_pass / kernel_s,
-                "pc_iterations_per_step": tot_iters / tot_steps,
+                "pc_iterations_per_step": iters_per_step,
                 "peak_source": "register-resident DFMA loop measured in this run (MEASURED_PEAKS.json has no FP64 entry)"}
 
     cpu_baseline = None
     if args.gpus == 1 and not args.no_cpu_baseline and have_ref():
         cores = len(os.sched_getaffinity(0))
-        n_sample = args.cpu_sample or 512 * cores
-        pick = np.linspace(0, n - 1, n_sample).astype(np.int64)
-        r = cpu_reference_run(paths, st[pick], T0, T_END, cores)
-        cpu_baseline = {"value": r["steps_per_s"], "unit": UNIT, "cores": cores, "kind": "reference",
-                        "sample": "%d particles spread over the population, full %.1f d span, one simulation per particle, one pinned "
-                                  "process per core (%.1f s); reference src/*.c + IAS15 restatement (oracle/_ref)" % (n_sample, SPAN_DAYS, r["busy_s"])}
+        s_st, s_pr, how = cpu_sample(wl, st, prm, cores, args.cpu_sample)
+        r = cpu_reference_run(paths, s_st, s_pr, T0, wl, cores)
+        cpu_baseline = {"value": r["steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+                        "sample": how + " (%.1f s)" % r["busy_s"]}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+    state_gb = n * K * (61 * 3 + 4) * 8 / 1e9
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": S, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_dev / S, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "n_per_gpu": n, "n_total": int(tot_n), "math": args.math,
+            "config": {"workload": wl["desc"], "n_per_gpu": n, "n_total": int(tot_n), "math": args.math,
                        "ephemeris": "synthetic DE440-layout planets .bsp + 16-asteroid .bsp (JD 2441000.5-2465000.5)",
-                       "cache": "per-GPU state %.2f GB >> 126 MB L2, so every pass streams from HBM" % (n * 1.5e3 / 1e9),
+                       "cache": ("per-GPU batch state %.2f GB >> 126 MB L2, so every pass streams from HBM" % state_gb) if state_gb > 0.5 else
+                                ("per-GPU batch state %.3f GB; every pass restarts from a device snapshot and rewrites the whole "
+                                 "state, nothing is reused between passes" % state_gb),
                        "particle_steps_per_pass": tot_steps, "parity": "strict math is bit-identical to the reference C build (tests/)"},
-            "kernel_ms_per_step": kernel_ms / K,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes)},
+            "kernel_ms_per_step": kernel_ms / S,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes + prm_bytes), "d2h_bytes_per_step": int(out_bytes)},
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
     print(json.dumps(line))

@@ -145,16 +145,19 @@ def test_schedulers_do_not_change_results(eph, fmt, golden, monkeypatch):
     and packs the stragglers, are invisible in the results."""
     g = golden[fmt]
     st = cases.pp_case()
-    for sched, cap in (("queue", "32"), ("capped", "0"), ("capped", "1"), ("capped", "5")):
+    for sched, cap, days in (("queue", "32", "0"), ("queue", "32", "7"), ("queue", "32", "32"), ("queue", "32", "1000"),
+                             ("capped", "0", "0"), ("capped", "1", "0"), ("capped", "5", "0")):
         monkeypatch.setenv("ASSIST_B200_SCHED", sched)
         monkeypatch.setenv("ASSIST_B200_STEP_CAP", cap)
+        monkeypatch.setenv("ASSIST_B200_SLICE_DAYS", days)      # time slices of the work queue
         b = ab.Batch(eph, st.shape[0], 0, ab.PER_PARTICLE, forces=0x7F)
         b.set_state(cases.T0, st[:, None, :])
         b.integrate(cases.T0 + cases.PP_DAYS)
-        assert np.array_equal(b.get_state()["state"], g["pp_final"]), (sched, cap)
+        assert np.array_equal(b.get_state()["state"], g["pp_final"]), (sched, cap, days)
         b.close()
     # more systems than working slots: every slot is reused many times
     monkeypatch.setenv("ASSIST_B200_SCHED", "queue")
+    monkeypatch.setenv("ASSIST_B200_SLICE_DAYS", "10")
     n = 150000
     stn = populations.main_belt(n, seed=71)
     b = ab.Batch(eph, n, 0, ab.PER_PARTICLE, forces=0x7F)
@@ -217,6 +220,45 @@ def test_dense_output_comets(eph, fmt, golden):
     out = b.integrate_or_interpolate(cases.DENSE_TIMES)
     assert np.nanmax(np.linalg.norm(out[..., :3] - g["dense"][..., :3], axis=-1)) <= POS_TOL_AU
     assert np.isfinite(out).all()
+
+
+def test_dense_output_schedulers_agree(eph, fmt, monkeypatch):
+    """Epoch output through the work queue (default) and through the one-thread-per-system kernel: same bits,
+    same final time/step bookkeeping, also when the slots of the working batch are reused."""
+    n = 70000
+    st = populations.main_belt(n, seed=72)
+    times = cases.T0 - np.array([0.0, 3.0, 10.0, 10.5, 11.0, 40.0, 41.0])
+    res = {}
+    for sched, days in (("queue", "0"), ("queue", "6"), ("queue", "128"), ("capped", "0")):
+        monkeypatch.setenv("ASSIST_B200_SCHED", sched)
+        monkeypatch.setenv("ASSIST_B200_SLICE_DAYS", days)
+        b = ab.Batch(eph, n, 0, ab.PER_PARTICLE, forces=0x7F)
+        b.set_state(cases.T0, st[:, None, :])
+        out = b.integrate_or_interpolate(times)
+        fin = b.get_state()
+        res[sched + days] = (out.copy(), fin["state"].copy(), fin["t"].copy(), fin["dt"].copy(), fin["dt_last_done"].copy())
+        b.close()
+    for key in ("queue0", "queue6", "queue128"):
+        for a, c in zip(res[key], res["capped0"]):
+            assert np.array_equal(a, c, equal_nan=True), key
+    assert np.isfinite(res["queue6"][0]).all()
+    # variational systems too
+    stv = populations.with_variations(populations.main_belt(300, seed=73), 6)
+    outs = []
+    for sched, days in (("queue", "9"), ("capped", "0")):
+        monkeypatch.setenv("ASSIST_B200_SCHED", sched)
+        monkeypatch.setenv("ASSIST_B200_SLICE_DAYS", days)
+        b = ab.Batch(eph, 300, 6, ab.PER_PARTICLE, forces=0x7F)
+        b.set_state(cases.T0, stv)
+        outs.append(b.integrate_or_interpolate(cases.T0 + np.array([5.0, 20.0, 21.0, 60.0])).copy())
+        # a second call continues from wherever the first one left the systems, then one goes back in time
+        outs.append(b.integrate_or_interpolate(cases.T0 + np.array([61.0, 90.0])).copy())
+        outs.append(b.integrate_or_interpolate(cases.T0 + np.array([80.0, 30.0, 31.0, 70.0])).copy())
+        b.integrate(cases.T0 + 10.0)
+        outs.append(b.get_state()["state"].copy())
+        b.close()
+    for a, c in zip(outs[:4], outs[4:]):
+        assert np.array_equal(a, c, equal_nan=True)
 
 
 # ------------------------------------------------------------------ the drop-in C API
