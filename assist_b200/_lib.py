@@ -79,6 +79,8 @@ def load():
     lib.assist_gpu_batch_get_stats.argtypes = [c_void_p, P(GpuStats)]
     lib.assist_gpu_measure_fp64_peak.restype = c_double
     lib.assist_gpu_measure_fp64_peak.argtypes = [c_int]
+    lib.assist_gpu_kernel_launches.restype = c_ulonglong
+    lib.assist_gpu_kernel_launches.argtypes = []
     lib.assist_gpu_batch_get_counters.argtypes = [c_void_p, P(c_ulonglong), P(c_ulonglong), P(c_ulonglong), P(c_ulonglong)]
     lib.assist_gpu_host_alloc.restype = c_void_p
     lib.assist_gpu_host_alloc.argtypes = [ctypes.c_size_t]

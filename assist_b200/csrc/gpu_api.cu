@@ -3,6 +3,7 @@
  * and kernel launches.  No physics here; the kernels are in kernels.cu.
  */
 #include <cuda_runtime.h>
+#include <atomic>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -38,6 +39,12 @@ static int set_err(int code, const char* fmt, ...) {
     } while (0)
 
 extern "C" const char* assist_gpu_last_error(void) { return g_err; }
+
+/* every kernel this library launches, process-wide (assist_gpu_kernel_launches) */
+static std::atomic<unsigned long long> g_kernel_launches{0};
+#define AB_COUNT(k) g_kernel_launches.fetch_add((unsigned long long)(k), std::memory_order_relaxed)
+
+extern "C" unsigned long long assist_gpu_kernel_launches(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
 
 extern "C" int assist_gpu_device_count(void) {
     int n = 0;
@@ -258,6 +265,7 @@ extern "C" int assist_gpu_ephem_eval(const struct assist_ephem* ephem, int math,
     CU(cudaMemcpy(d_t, t, sizeof(double) * n_t, cudaMemcpyHostToDevice));
     cudaError_t e = (math == ASSIST_GPU_MATH_FAST) ? ab_launch_ephem_eval_fast(E, d_t, n_t, d_out, d_st, 0)
                                                    : ab_launch_ephem_eval_strict(E, d_t, n_t, d_out, d_st, 0);
+    AB_COUNT(1);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * 10 * (size_t)n_t * nb, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && status) e = cudaMemcpy(status, d_st, sizeof(int) * (size_t)n_t * nb, cudaMemcpyDeviceToHost);
@@ -293,6 +301,7 @@ extern "C" int assist_gpu_eval_forces(const struct assist_ephem* ephem, const st
     cudaError_t e = (opt->math == ASSIST_GPU_MATH_FAST)
         ? ab_launch_force_eval_fast(E, F, n_sys, K, d_t, t_per_system, d_state, d_prm, d_acc, d_st, 0)
         : ab_launch_force_eval_strict(E, F, n_sys, K, d_t, t_per_system, d_state, d_prm, d_acc, d_st, 0);
+    AB_COUNT(1);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(acc, d_acc, sizeof(double) * 3 * (size_t)n_sys * K, cudaMemcpyDeviceToHost);
     int first_err = 0;
@@ -460,8 +469,8 @@ extern "C" assist_gpu_batch* assist_gpu_batch_create(const struct assist_ephem* 
     }
     cudaEventCreate(&b->ev0);
     cudaEventCreate(&b->ev1);
-    fill_int_kernel<<<blocks_for(n), 256>>>(d.nv, n, n_var);
-    fill_int_kernel<<<blocks_for(n), 256>>>(d.status, n, -3);
+    fill_int_kernel<<<blocks_for(n), 256>>>(d.nv, n, n_var); AB_COUNT(1);
+    fill_int_kernel<<<blocks_for(n), 256>>>(d.status, n, -3); AB_COUNT(1);
     if (cudaDeviceSynchronize() != cudaSuccess) {
         set_err(ASSIST_GPU_ERR_CUDA, "batch initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
         assist_gpu_batch_free(b);
@@ -491,8 +500,8 @@ extern "C" int assist_gpu_batch_set_options(assist_gpu_batch* b, const struct as
 static int upload_particles(assist_gpu_batch* b, const double* state) {
     const size_t n = b->n;
     CU(cudaMemcpy(b->d_stage, state, sizeof(double) * 6 * n * b->K, cudaMemcpyHostToDevice));
-    aos_to_soa_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d_stage, b->n, b->K, 6, 0, 3, b->d.pos);
-    aos_to_soa_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d_stage, b->n, b->K, 6, 3, 3, b->d.vel);
+    aos_to_soa_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d_stage, b->n, b->K, 6, 0, 3, b->d.pos); AB_COUNT(1);
+    aos_to_soa_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d_stage, b->n, b->K, 6, 3, 3, b->d.vel); AB_COUNT(1);
     CU(cudaGetLastError());
     return 0;
 }
@@ -508,7 +517,7 @@ extern "C" int assist_gpu_batch_set_state(assist_gpu_batch* b, double t0, double
     if (rc) return rc;
     if (params) {
         CU(cudaMemcpy(b->d_stage_prm, params, sizeof(double) * 3 * n * b->K, cudaMemcpyHostToDevice));
-        aos_to_soa_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d_stage_prm, b->n, b->K, 3, 0, 3, b->d.prm);
+        aos_to_soa_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d_stage_prm, b->n, b->K, 3, 0, 3, b->d.prm); AB_COUNT(1);
         b->d.has_params = 1;
     } else {
         b->d.has_params = 0;
@@ -518,11 +527,11 @@ extern "C" int assist_gpu_batch_set_state(assist_gpu_batch* b, double t0, double
             if (nvar_per_system[i] < 0 || nvar_per_system[i] > b->nvar) return set_err(ASSIST_GPU_ERR_ARG, "nvar_per_system[%zu] out of range", i);
         CU(cudaMemcpy(b->d.nv, nvar_per_system, sizeof(int) * n, cudaMemcpyHostToDevice));
     } else {
-        fill_int_kernel<<<blocks_for(n), 256>>>(b->d.nv, n, b->nvar);
+        fill_int_kernel<<<blocks_for(n), 256>>>(b->d.nv, n, b->nvar); AB_COUNT(1);
     }
-    fill_kernel<<<blocks_for(n), 256>>>(b->d.t, n, t0);
-    fill_kernel<<<blocks_for(n), 256>>>(b->d.dt, n, dt0);
-    fill_int_kernel<<<blocks_for(n), 256>>>(b->d.status, n, -3);
+    fill_kernel<<<blocks_for(n), 256>>>(b->d.t, n, t0); AB_COUNT(1);
+    fill_kernel<<<blocks_for(n), 256>>>(b->d.dt, n, dt0); AB_COUNT(1);
+    fill_int_kernel<<<blocks_for(n), 256>>>(b->d.status, n, -3); AB_COUNT(1);
     AbShared sh;
     memset(&sh, 0, sizeof(sh));
     sh.t = t0; sh.dt = dt0; sh.status = -3;
@@ -545,8 +554,8 @@ extern "C" int assist_gpu_batch_set_time(assist_gpu_batch* b, double t, double d
     if (!b) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(b->device));
     const size_t n = b->n;
-    fill_kernel<<<blocks_for(n), 256>>>(b->d.t, n, t);
-    fill_kernel<<<blocks_for(n), 256>>>(b->d.dt, n, dt);
+    fill_kernel<<<blocks_for(n), 256>>>(b->d.t, n, t); AB_COUNT(1);
+    fill_kernel<<<blocks_for(n), 256>>>(b->d.dt, n, dt); AB_COUNT(1);
     AbShared sh;
     CU(cudaMemcpy(&sh, b->d.sh, sizeof(sh), cudaMemcpyDeviceToHost));
     sh.t = t; sh.dt = dt;
@@ -579,6 +588,7 @@ static int finish_launch(assist_gpu_batch* b, cudaError_t e, const char* what) {
     cudaEventElapsedTime(&ms, b->ev0, b->ev1);
     b->stats.last_kernel_ms = ms;
     b->stats.kernel_launches++;
+    AB_COUNT(1);
     return 0;
 }
 
@@ -628,7 +638,7 @@ static int build_slices(assist_gpu_batch* b, const AbEphem& E, double t_end, AbS
     if (b->slice_days > 0.0 && t_end == t_end) {
         unsigned long long init[2] = {~0ULL, 0ULL}, got[2];
         CU(cudaMemcpy(b->d_trange, init, sizeof(init), cudaMemcpyHostToDevice));
-        trange_kernel<<<256, 256>>>(b->d.t, b->d.status, b->n, b->d_trange);
+        trange_kernel<<<256, 256>>>(b->d.t, b->d.status, b->n, b->d_trange); AB_COUNT(1);
         CU(cudaMemcpy(got, b->d_trange, sizeof(got), cudaMemcpyDeviceToHost));
         if (got[0] != ~0ULL) {
             const double lo = unkey(got[0]), hi = unkey(got[1]);
@@ -722,7 +732,7 @@ extern "C" int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int 
             launches++;
             if (b->step_cap <= 0) break;
             CU(cudaMemsetAsync(b->d_count, 0, sizeof(int), 0));
-            compact_active_kernel<<<(n_active + 255) / 256, 256>>>(b->d.status, list, n_active, b->d_active[which], b->d_count);
+            compact_active_kernel<<<(n_active + 255) / 256, 256>>>(b->d.status, list, n_active, b->d_active[which], b->d_count); AB_COUNT(1);
             int count = 0;
             CU(cudaMemcpy(&count, b->d_count, sizeof(int), cudaMemcpyDeviceToHost));
             if (trace) {
@@ -738,6 +748,7 @@ extern "C" int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int 
             which ^= 1;
             resume = 1;
         }
+        AB_COUNT(2 * launches - 2);
         b->stats.kernel_launches += 2 * launches - 2;   /* integrate launches + compaction kernels (finish_launch adds one) */
         return finish_launch(b, cudaSuccess, "pp_integrate");
     }
@@ -817,12 +828,12 @@ extern "C" int assist_gpu_batch_get_state(assist_gpu_batch* b, double* state, do
     CU(cudaSetDevice(b->device));
     const size_t n = b->n;
     if (state) {
-        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.pos, b->n, b->K, 6, 0, 3, b->d_stage);
-        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.vel, b->n, b->K, 6, 3, 3, b->d_stage);
+        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.pos, b->n, b->K, 6, 0, 3, b->d_stage); AB_COUNT(1);
+        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.vel, b->n, b->K, 6, 3, 3, b->d_stage); AB_COUNT(1);
         CU(cudaMemcpy(state, b->d_stage, sizeof(double) * 6 * n * b->K, cudaMemcpyDeviceToHost));
     }
     if (acc) {
-        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.acc, b->n, b->K, 3, 0, 3, b->d_stage_prm);
+        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.acc, b->n, b->K, 3, 0, 3, b->d_stage_prm); AB_COUNT(1);
         CU(cudaMemcpy(acc, b->d_stage_prm, sizeof(double) * 3 * n * b->K, cudaMemcpyDeviceToHost));
     }
     if (b->mode == ASSIST_GPU_PER_PARTICLE) {
@@ -847,7 +858,7 @@ extern "C" int ab_gpu_batch_update_params(assist_gpu_batch* b, const double* par
     const size_t n = b->n;
     if (params) {
         CU(cudaMemcpy(b->d_stage_prm, params, sizeof(double) * 3 * n * b->K, cudaMemcpyHostToDevice));
-        aos_to_soa_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d_stage_prm, b->n, b->K, 3, 0, 3, b->d.prm);
+        aos_to_soa_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d_stage_prm, b->n, b->K, 3, 0, 3, b->d.prm); AB_COUNT(1);
         CU(cudaGetLastError());
         b->d.has_params = 1;
     } else {
@@ -862,12 +873,12 @@ extern "C" int ab_gpu_batch_get_last_state(assist_gpu_batch* b, double* state, d
     CU(cudaSetDevice(b->device));
     const size_t n = b->n;
     if (state) {
-        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.ls_pos, b->n, b->K, 6, 0, 3, b->d_stage);
-        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.ls_vel, b->n, b->K, 6, 3, 3, b->d_stage);
+        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.ls_pos, b->n, b->K, 6, 0, 3, b->d_stage); AB_COUNT(1);
+        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.ls_vel, b->n, b->K, 6, 3, 3, b->d_stage); AB_COUNT(1);
         CU(cudaMemcpy(state, b->d_stage, sizeof(double) * 6 * n * b->K, cudaMemcpyDeviceToHost));
     }
     if (acc) {
-        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.ls_acc, b->n, b->K, 3, 0, 3, b->d_stage_prm);
+        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.ls_acc, b->n, b->K, 3, 0, 3, b->d_stage_prm); AB_COUNT(1);
         CU(cudaMemcpy(acc, b->d_stage_prm, sizeof(double) * 3 * n * b->K, cudaMemcpyDeviceToHost));
     }
     return 0;
@@ -881,6 +892,7 @@ extern "C" int assist_gpu_batch_interpolate(assist_gpu_batch* b, double h, doubl
     CU(cudaMemcpy(&sh, b->d.sh, sizeof(sh), cudaMemcpyDeviceToHost));
     cudaError_t e = (b->opt.math == ASSIST_GPU_MATH_FAST) ? ab_launch_sh_interpolate_fast(b->d, sh.dt_last, h, b->d_stage, 0)
                                                           : ab_launch_sh_interpolate_strict(b->d, sh.dt_last, h, b->d_stage, 0);
+    AB_COUNT(1);
     if (e != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "interpolate: %s", cudaGetErrorString(e));
     CU(cudaMemcpy(out, b->d_stage, sizeof(double) * 6 * (size_t)b->n * b->K, cudaMemcpyDeviceToHost));
     return 0;
@@ -903,6 +915,8 @@ extern "C" int assist_gpu_batch_get_stats(assist_gpu_batch* b, struct assist_gpu
         CU(cudaMemset(d_sum, 0, sizeof(h)));
         const unsigned long long* src[4] = {b->d.steps, b->d.rejected, b->d.iters, b->d.evals};
         for (int q = 0; q < 4; q++) sum_counters_kernel<<<256, 256>>>(src[q], b->n, d_sum + q);
+        AB_COUNT(4);
+        AB_COUNT(4);
         CU(cudaMemcpy(h, d_sum, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(d_sum);
         b->stats.steps = h[0]; b->stats.steps_rejected = h[1]; b->stats.pc_iterations = h[2]; b->stats.force_evals = h[3];
@@ -943,11 +957,11 @@ extern "C" double assist_gpu_measure_fp64_peak(int iters) {
     if (cudaMalloc((void**)&d, sizeof(double) * (size_t)grid * threads) != cudaSuccess) return -1.0;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    dfma_peak_kernel<<<grid, threads>>>(d, 16);     /* warm-up */
+    dfma_peak_kernel<<<grid, threads>>>(d, 16); AB_COUNT(1);
     double best = 0.0;
     for (int rep = 0; rep < 5; rep++) {
         cudaEventRecord(e0, 0);
-        dfma_peak_kernel<<<grid, threads>>>(d, iters);
+        dfma_peak_kernel<<<grid, threads>>>(d, iters); AB_COUNT(1);
         cudaEventRecord(e1, 0);
         cudaEventSynchronize(e1);
         float ms = 0.f;

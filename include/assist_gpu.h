@@ -135,6 +135,8 @@ void* assist_gpu_host_alloc(size_t bytes);
 void assist_gpu_host_free(void* p);
 /* Peak FP64 FMA rate of the current device measured with a register-resident DFMA loop (TFLOP/s). */
 double assist_gpu_measure_fp64_peak(int iters);
+/* Number of CUDA kernels this library has launched in this process so far (all devices, all batches). */
+unsigned long long assist_gpu_kernel_launches(void);
 
 #ifdef __cplusplus
 }
