@@ -274,6 +274,10 @@ __device__ void ab_body_states(const AbEphem& E, const AbForceOpts& F, double t,
  * one-time routines above: each sum sees the same operands in the same order.
  * ------------------------------------------------------------------------------------------ */
 #define AB_NT 8
+#ifndef AB_CHEB_UNROLL
+#define AB_CHEB_UNROLL 1
+#endif
+constexpr int kChebUnroll = AB_CHEB_UNROLL;
 
 /* position sums (km) of one series at AB_NT arguments; cf[k] points at the X coefficients */
 __device__ __forceinline__ void ab_cheb_pos_multi(const double* const* cf, int P, const double* z, double (*u)[3]) {
@@ -288,6 +292,7 @@ __device__ __forceinline__ void ab_cheb_pos_multi(const double* const* cf, int P
         a0[k] = s0; a1[k] = s1; a2[k] = s2;
         T2[k] = 1.0; T1[k] = z[k];
     }
+#pragma unroll kChebUnroll
     for (int p = 2; p < P; p++) {
 #pragma unroll
         for (int k = 0; k < AB_NT; k++) {

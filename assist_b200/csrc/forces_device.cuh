@@ -32,6 +32,16 @@
 #ifndef AB_EIH_UNROLL
 #define AB_EIH_UNROLL 1
 #endif
+/* single-change switches measured in profiles/README.md */
+#ifndef AB_OPT_FMASK
+#define AB_OPT_FMASK 1
+#endif
+#ifndef AB_OPT_REGACC
+#define AB_OPT_REGACC 1
+#endif
+#ifndef AB_OPT_EIHPIPE
+#define AB_OPT_EIHPIPE 1
+#endif
 
 namespace AB_NS {
 
@@ -462,6 +472,7 @@ __device__ void ab_force_eih(const AbEphem& E, const AbForceOpts& F, const BT& B
 
     /* sum over the 11 planets of GM_k / r_ik: identical for every source j (src/forces.c:1400-1416) */
     double term0_sum = 0.0;
+#if !AB_OPT_EIHPIPE
     {
         double q[AB_NPLANETS];
 #pragma unroll kEihUnroll
@@ -476,6 +487,23 @@ __device__ void ab_force_eih(const AbEphem& E, const AbForceOpts& F, const BT& B
 #pragma unroll
         for (int k = 0; k < AB_NPLANETS; k++) term0_sum += q[k];   /* summed in the reference's order */
     }
+#else
+    {   /* rolled, the next planet's table entries requested one trip ahead */
+        const double* const gm = B.gm;
+        double nx = B.pos[0][0], ny = B.pos[0][1], nz = B.pos[0][2], ngm = gm[0];
+#pragma unroll 1
+        for (int k = 0; k < AB_NPLANETS; k++) {
+            const double cx = nx, cy = ny, cz = nz, GMk = ngm;
+            if (k + 1 < AB_NPLANETS) { nx = B.pos[k + 1][0]; ny = B.pos[k + 1][1]; nz = B.pos[k + 1][2]; ngm = gm[k + 1]; }
+            const double dxik = pix + (xo - cx);
+            const double dyik = piy + (yo - cy);
+            const double dzik = piz + (zo - cz);
+            const double rik2 = dxik * dxik + dyik * dyik + dzik * dzik;
+            const double _rik = sqrt(rik2);
+            term0_sum += GMk / _rik;
+        }
+    }
+#endif
 
     {   /* real particle, src/forces.c:1319-1501 */
         double term7x_sum = 0.0, term7y_sum = 0.0, term7z_sum = 0.0;
@@ -827,9 +855,19 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT
     const int ast_num = E.n_ast;
     const int nb = AB_NPLANETS + ast_num;
     const double px = S.x[0][0], py = S.x[0][1], pz = S.x[0][2];
+#if AB_OPT_FMASK
+    const int fmask = F.forces;
+#else
+#define fmask F.forces
+#endif
+#if AB_OPT_REGACC
+    /* the running sums stay in registers; the additions happen in the reference's sequence */
+    double acx = S.a[0][0], acy = S.a[0][1], acz = S.a[0][2];
+#endif
     /* the table entries of the next body are requested while the current body is being worked on */
+    const double* const gm = B.gm;       /* read once: the table is not written while the forces are evaluated */
     int i_next = ab_direct_body(0, ast_num);
-    double bx = B.pos[i_next][0], by = B.pos[i_next][1], bz = B.pos[i_next][2], bgm = B.gm[i_next];
+    double bx = B.pos[i_next][0], by = B.pos[i_next][1], bz = B.pos[i_next][2], bgm = gm[i_next];
 #pragma unroll kDirectUnroll
     for (int k = 0; k < nb; k++) {
         const int i = i_next;
@@ -837,7 +875,7 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT
         const double cx = bx, cy = by, cz = bz;
         if (k + 1 < nb) {
             i_next = ab_direct_body(k + 1, ast_num);
-            bx = B.pos[i_next][0]; by = B.pos[i_next][1]; bz = B.pos[i_next][2]; bgm = B.gm[i_next];
+            bx = B.pos[i_next][0]; by = B.pos[i_next][1]; bz = B.pos[i_next][2]; bgm = gm[i_next];
         }
         const double dx = px + (xo - cx);
         const double dy = py + (yo - cy);
@@ -845,14 +883,20 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT
         const double r2 = dx * dx + dy * dy + dz * dz;
         const double _r = sqrt(r2);
         bool on = true;
-        if (i == 0 && !(F.forces & 0x01)) on = false;
-        if (i > 0 && i < AB_NPLANETS && !(F.forces & 0x02)) on = false;
-        if (i >= AB_NPLANETS && !(F.forces & 0x04)) on = false;
+        if (i == 0 && !(fmask & 0x01)) on = false;
+        if (i > 0 && i < AB_NPLANETS && !(fmask & 0x02)) on = false;
+        if (i >= AB_NPLANETS && !(fmask & 0x04)) on = false;
         if (on) {
             const double prefac = GM / (_r * _r * _r);
+#if AB_OPT_REGACC
+            acx -= prefac * dx;
+            acy -= prefac * dy;
+            acz -= prefac * dz;
+#else
             S.a[0][0] -= prefac * dx;
             S.a[0][1] -= prefac * dy;
             S.a[0][2] -= prefac * dz;
+#endif
         }
         if (S.nv() > 0) {
             /* no force-mask check here, as in the reference (src/forces.c:359) */
@@ -875,6 +919,12 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT
             }
         }
     }
+#if AB_OPT_REGACC
+    S.a[0][0] = acx; S.a[0][1] = acy; S.a[0][2] = acz;
+#endif
+#if !AB_OPT_FMASK
+#undef fmask
+#endif
 }
 #endif
 
