@@ -384,21 +384,29 @@ __device__ void pp_copy_system(const AbBatch& src, long long i, const AbBatch& d
     double* const d1[12] = {dst.pos, dst.vel, dst.acc, dst.x0, dst.v0, dst.a0, dst.csx, dst.csv, dst.ls_pos, dst.ls_vel, dst.ls_acc, dst.prm};
     double* const s7[6] = {src.b, src.g, src.e, src.csb, src.br, src.er};
     double* const d7[6] = {dst.b, dst.g, dst.e, dst.csb, dst.br, dst.er};
-    /* loads in groups of 12 / 7 before the stores, so that the trips to L2 overlap */
-    for (int k = 0; k < Ca; k++) {
-        double tmp[12];
+    /* a body (3 components) at a time: 36 / 21 independent loads before the stores, so that the trips to L2 overlap */
+    for (int k0 = 0; k0 < Ca; k0 += 3) {
+        double tmp[12][3];
 #pragma unroll
-        for (int a = 0; a < 12; a++) tmp[a] = pp_ld<CG>(s1[a] + (long long)k * ns + i);
+        for (int a = 0; a < 12; a++)
 #pragma unroll
-        for (int a = 0; a < 12; a++) d1[a][(long long)k * nd + s] = tmp[a];
+            for (int c = 0; c < 3; c++) tmp[a][c] = pp_ld<CG>(s1[a] + (long long)(k0 + c) * ns + i);
+#pragma unroll
+        for (int a = 0; a < 12; a++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) d1[a][(long long)(k0 + c) * nd + s] = tmp[a][c];
     }
     for (int a = 0; a < 6; a++)
-        for (int k = 0; k < Ca; k++) {
-            double tmp[7];
+        for (int k0 = 0; k0 < Ca; k0 += 3) {
+            double tmp[7][3];
 #pragma unroll
-            for (int j = 0; j < 7; j++) tmp[j] = pp_ld<CG>(s7[a] + ((long long)j * C + k) * ns + i);
+            for (int j = 0; j < 7; j++)
 #pragma unroll
-            for (int j = 0; j < 7; j++) d7[a][((long long)j * C + k) * nd + s] = tmp[j];
+                for (int c = 0; c < 3; c++) tmp[j][c] = pp_ld<CG>(s7[a] + ((long long)j * C + k0 + c) * ns + i);
+#pragma unroll
+            for (int j = 0; j < 7; j++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) d7[a][((long long)j * C + k0 + c) * nd + s] = tmp[j][c];
         }
 }
 
@@ -468,6 +476,10 @@ pp_queue_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbFor
     double target = tmax, wend = 0.0;
     PPState P;
     while (true) {
+        /* Phase A, per lane: get to a point where a step is due.  A lane whose system pauses or finishes stores it
+         * and takes the next one in the same trip (two attempts), so that it does not sit out a step of its CTA. */
+        bool step_due = false;
+        for (int attempt = 0; attempt < 2 && !step_due; attempt++) {
         while (!have && !exhausted) {
             if (!pending) {
                 const unsigned long long q = atomicAdd(queue_head, 1ULL);
@@ -512,12 +524,10 @@ pp_queue_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbFor
             pp_copy_system<true>(Bt, sys, W, slot, nv);
             have = true;
         }
-        if (!__syncthreads_or((have || pending) ? 1 : 0)) break;
-        /* per-lane bookkeeping until a step is due (so that every trip of a busy lane ends in a step), the window
-         * ends or the system is done */
+        if (!have) break;
+        /* bookkeeping until a step is due, the window ends or the system is done */
         const bool last = (win == SL.n_win - 1);
-        bool step_due = false;
-        while (have) {
+        while (true) {
             if (dense && !integrating) {
                 /* epochs inside the last completed step are interpolated; the first one outside starts an integrate() */
                 while (ep < n_times) {
@@ -548,13 +558,7 @@ pp_queue_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbFor
             }
             break;                       /* finished */
         }
-        /* the lanes left the bookkeeping through different exits: bring the warp back together, so that the step
-         * below (99 % of the trip) runs once for the whole warp */
-        __syncwarp();
-        if (step_due) {
-            if (F.gr_eih_sources == 1 && !F.geocentric) pp_step_nodes<PP_KM>(E, F, W, slot, P);
-            else pp_step<PP_KM>(E, F, W, slot, P);
-        } else if (have) {
+        if (!step_due) {
             /* paused at the end of the window, or finished: back to the population arrays */
             pp_copy_system<false>(W, slot, Bt, sys, nv);
             if (W.status[slot] >= 1000) Bt.status[sys] = W.status[slot];
@@ -562,6 +566,15 @@ pp_queue_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbFor
             if (dense) SL.epoch[sys] = ep;
             if (SL.n_win > 1) { __threadfence(); *((volatile int*)(SL.done + sys)) = win + 1; }
             have = false;
+        }
+        }   /* attempts */
+        /* Phase B, the CTA together: one step.  The barrier also brings back together the lanes that left phase A
+         * through different exits -- otherwise the compiler runs the step (99 % of a trip) once per group. */
+        if (!__syncthreads_or((have || pending) ? 1 : 0)) break;
+        __syncwarp();
+        if (step_due) {
+            if (F.gr_eih_sources == 1 && !F.geocentric) pp_step_nodes<PP_KM>(E, F, W, slot, P);
+            else pp_step<PP_KM>(E, F, W, slot, P);
         }
     }
 }
