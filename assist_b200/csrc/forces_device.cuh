@@ -39,6 +39,9 @@
 #ifndef AB_OPT_REGACC
 #define AB_OPT_REGACC 1
 #endif
+#ifndef AB_DIRECT_PF
+#define AB_DIRECT_PF 1
+#endif
 #ifndef AB_OPT_EIHPIPE
 #define AB_OPT_EIHPIPE 1
 #endif
@@ -868,15 +871,28 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT
     const double* const gm = B.gm;       /* read once: the table is not written while the forces are evaluated */
     int i_next = ab_direct_body(0, ast_num);
     double bx = B.pos[i_next][0], by = B.pos[i_next][1], bz = B.pos[i_next][2], bgm = gm[i_next];
+#if AB_DIRECT_PF == 2
+    /* two bodies ahead: a trip to HBM (the tables of 57 k threads do not fit L2) is longer than one loop trip */
+    int i_next2 = (nb > 1) ? ab_direct_body(1, ast_num) : i_next;
+    double ex = B.pos[i_next2][0], ey = B.pos[i_next2][1], ez = B.pos[i_next2][2], egm = gm[i_next2];
+#endif
 #pragma unroll kDirectUnroll
     for (int k = 0; k < nb; k++) {
         const int i = i_next;
         const double GM = bgm;
         const double cx = bx, cy = by, cz = bz;
+#if AB_DIRECT_PF == 2
+        i_next = i_next2; bx = ex; by = ey; bz = ez; bgm = egm;
+        if (k + 2 < nb) {
+            i_next2 = ab_direct_body(k + 2, ast_num);
+            ex = B.pos[i_next2][0]; ey = B.pos[i_next2][1]; ez = B.pos[i_next2][2]; egm = gm[i_next2];
+        }
+#else
         if (k + 1 < nb) {
             i_next = ab_direct_body(k + 1, ast_num);
             bx = B.pos[i_next][0]; by = B.pos[i_next][1]; bz = B.pos[i_next][2]; bgm = gm[i_next];
         }
+#endif
         const double dx = px + (xo - cx);
         const double dy = py + (yo - cy);
         const double dz = pz + (zo - cz);
