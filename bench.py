@@ -414,8 +414,18 @@ def main():
             traffic = json.load(fh).get("%s:%d:%s" % (args.workload, n, args.math))
     except OSError:
         pass
+    # the same launch against the HBM roof (MEASURED_PEAKS.json, driver-written): the kernel is far from both
+    hbm = None
+    if traffic:
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                hbm_peak, hbm_src = float(json.load(fh)["hbm_gbs"]), "of measured (MEASURED_PEAKS.json)"
+        except (OSError, KeyError, ValueError):
+            hbm_peak, hbm_src = 6650.0, "of fallback (B200_PROFILING.md)"
+        hbm = {"achieved_gbs": traffic / kernel_s / 1e9, "peak_gbs": hbm_peak, "frac": traffic / kernel_s / 1e9 / hbm_peak,
+               "peak_source": hbm_src}
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic,
+                "traffic": traffic, "hbm": hbm,
                 "kernel": "fused ephemeris + forces + IAS15 integrate kernel (%s), %d launch(es) per pass"
                           % ("sh_integrate_kernel" if shared else "pp_queue_kernel, epoch output" if times is not None else "pp_queue_kernel", launches // S),
                 "flops_per_force_eval": f_force, "achieved_incl_ephemeris": achieved_eph, "frac_incl_ephemeris": achieved_eph / peak,
