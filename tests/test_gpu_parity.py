@@ -389,3 +389,33 @@ def test_properties_at_scale(eph, fmt):
     assert (back["t"] == cases.T0).all()
     d = np.linalg.norm(back["state"][:, 0, :3] - st[:, :3], axis=-1)
     assert np.median(d) < 1e-13 and d.max() < 1e-9
+
+
+def test_full_size_population(eph, fmt, ref, paths):
+    """BASELINE config 3 at its full size (10^6 particles of the bench population, 60 d): every system finishes,
+    a random subset integrated alone gives the same bits (so the 10^6-batch is 10^6 independent reference
+    integrations), and a handful of them are checked against the reference C build itself."""
+    if fmt != "bsp":
+        pytest.skip("one file format is enough at this size")
+    n = 1000000
+    st = populations.neo_mba_mix(n, seed=20261703)
+    t_end = cases.T0 + 60.0
+    b = ab.Batch(eph, n, 0, ab.PER_PARTICLE, forces=0x7F, min_dt=1e-3)
+    b.set_state(cases.T0, st[:, None, :])
+    b.integrate(t_end)
+    got = b.get_state()
+    full = got["state"].copy()
+    assert (got["status"] == 0).all() and (got["t"] == t_end).all() and np.isfinite(full).all()
+    c = b.counters()
+    assert c["steps"].min() >= 2 and int(c["evals"].sum()) == b.stats()["force_evals"]
+    b.close()
+    pick = np.sort(np.random.default_rng(11).choice(n, 5000, replace=False))
+    b2 = ab.Batch(eph, pick.size, 0, ab.PER_PARTICLE, forces=0x7F, min_dt=1e-3)
+    b2.set_state(cases.T0, st[pick][:, None, :])
+    b2.integrate(t_end)
+    assert np.array_equal(b2.get_state()["state"], full[pick])
+    b2.close()
+    reph = rh.open_ephem(ref, planets_path(paths, fmt), paths["asteroids_bsp"])
+    few = pick[::500]
+    want, _, _, _ = rh.integrate_each(ref, reph, cases.T0, st[few], t_end, forces=0x7F, min_dt=1e-3)
+    assert np.array_equal(full[few], want)
