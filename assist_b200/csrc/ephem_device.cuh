@@ -274,16 +274,6 @@ __device__ void ab_body_states(const AbEphem& E, const AbForceOpts& F, double t,
  * one-time routines above: each sum sees the same operands in the same order.
  * ------------------------------------------------------------------------------------------ */
 #define AB_NT 8
-#ifndef AB_OPT_SUNCOPY
-#define AB_OPT_SUNCOPY 1
-#endif
-#ifndef AB_OPT_EIHEARLY
-#define AB_OPT_EIHEARLY 1
-#endif
-#ifndef AB_CHEB_UNROLL
-#define AB_CHEB_UNROLL 1
-#endif
-constexpr int kChebUnroll = AB_CHEB_UNROLL;
 
 /* position sums (km) of one series at AB_NT arguments; cf[k] points at the X coefficients */
 __device__ __forceinline__ void ab_cheb_pos_multi(const double* const* cf, int P, const double* z, double (*u)[3]) {
@@ -298,7 +288,7 @@ __device__ __forceinline__ void ab_cheb_pos_multi(const double* const* cf, int P
         a0[k] = s0; a1[k] = s1; a2[k] = s2;
         T2[k] = 1.0; T1[k] = z[k];
     }
-#pragma unroll kChebUnroll
+#pragma unroll 1
     for (int p = 2; p < P; p++) {
 #pragma unroll
         for (int k = 0; k < AB_NT; k++) {
@@ -414,7 +404,6 @@ __device__ __noinline__ int ab_fill_nodes(const AbEphem& E, const AbForceOpts& F
                 for (int c = 0; c < 3; c++) nodes[k].pos[b][c] = ab_divc(u[k][c], E.u_d[0], E.u_rd[0]);
         }
     }
-#if AB_OPT_EIHEARLY
     /* right after the planets, while their table entries are still in L1 */
     /* particle-independent EIH sums for source 0 */
     const bool need_eih = (F.forces & 0x40) != 0;
@@ -440,7 +429,6 @@ __device__ __noinline__ int ab_fill_nodes(const AbEphem& E, const AbForceOpts& F
         N.eih_ar[0][0] = arx; N.eih_ar[0][1] = ary; N.eih_ar[0][2] = arz;
         N.eih_av[0][0] = avx; N.eih_av[0][1] = avy; N.eih_av[0][2] = avz;
     }
-#endif
     /* Sun velocity (non-grav, simple GR and the EIH source) */
     for (int k = 0; k < AB_NT; k++) {
         double GM, x[3], a[3];
@@ -449,47 +437,15 @@ __device__ __noinline__ int ab_fill_nodes(const AbEphem& E, const AbForceOpts& F
     }
     /* asteroids: heliocentric SPK position / 149597870.7 + Sun.  The Sun's 24 values are copied out of the
      * 8 tables once: by now their lines have left L1, and 16 asteroids would fetch them 16 times. */
-#if AB_OPT_SUNCOPY
     double sun[AB_NT][3];
     for (int k = 0; k < AB_NT; k++)
         for (int c = 0; c < 3; c++) sun[k][c] = nodes[k].pos[0][c];
-#endif
     for (int m = 0; m < E.n_ast; m++) {
         ab_spk_pos_multi(E.spka_img, E.a_tgt[m], jd_ref, t, u);
         for (int k = 0; k < AB_NT; k++)
             for (int c = 0; c < 3; c++)
-#if AB_OPT_SUNCOPY
                 nodes[k].pos[AB_NPLANETS + m][c] = AB_DIVK(u[k][c], 149597870.7) + sun[k][c];
-#else
-                nodes[k].pos[AB_NPLANETS + m][c] = AB_DIVK(u[k][c], 149597870.7) + nodes[k].pos[0][c];
-#endif
     }
-#if !AB_OPT_EIHEARLY
-    /* particle-independent EIH sums for source 0 */
-    const bool need_eih = (F.forces & 0x40) != 0;
-    for (int k = 0; k < AB_NT; k++) {
-        AbNode& N = nodes[k];
-        N.gm = E.gm;
-        if (!need_eih) continue;
-        double term1 = 0.0, arx = 0.0, ary = 0.0, arz = 0.0, avx = 0.0, avy = 0.0, avz = 0.0;
-        for (int q = 1; q < AB_NPLANETS; q++) {
-            const double GMk = E.gm[q];
-            const double dxjk = N.pos[0][0] - N.pos[q][0];
-            const double dyjk = N.pos[0][1] - N.pos[q][1];
-            const double dzjk = N.pos[0][2] - N.pos[q][2];
-            const double rjk2 = dxjk * dxjk + dyjk * dyjk + dzjk * dzjk;
-            const double _rjk = sqrt(rjk2);
-            term1 += GMk / _rjk;
-            const double fac = GMk / (rjk2 * _rjk);
-            arx -= fac * dxjk; ary -= fac * dyjk; arz -= fac * dzjk;
-            const AbDivisor r3(_rjk * _rjk * _rjk);
-            avx -= r3(GMk * dxjk); avy -= r3(GMk * dyjk); avz -= r3(GMk * dzjk);
-        }
-        N.eih_term1[0] = term1;
-        N.eih_ar[0][0] = arx; N.eih_ar[0][1] = ary; N.eih_ar[0][2] = arz;
-        N.eih_av[0][0] = avx; N.eih_av[0][1] = avy; N.eih_av[0][2] = avz;
-    }
-#endif
     return AB_OK;
 }
 

@@ -26,30 +26,7 @@
 #include "device_types.h"
 #include "fp_device.cuh"
 
-#ifndef AB_DIRECT_UNROLL
-#define AB_DIRECT_UNROLL 1
-#endif
-#ifndef AB_EIH_UNROLL
-#define AB_EIH_UNROLL 1
-#endif
-/* single-change switches measured in profiles/README.md */
-#ifndef AB_OPT_FMASK
-#define AB_OPT_FMASK 1
-#endif
-#ifndef AB_OPT_REGACC
-#define AB_OPT_REGACC 1
-#endif
-#ifndef AB_DIRECT_PF
-#define AB_DIRECT_PF 1
-#endif
-#ifndef AB_OPT_EIHPIPE
-#define AB_OPT_EIHPIPE 1
-#endif
-
 namespace AB_NS {
-
-constexpr int kDirectUnroll = AB_DIRECT_UNROLL;
-constexpr int kEihUnroll = AB_EIH_UNROLL;
 
 /* Positions/velocities/accelerations of one system in registers/local memory. */
 template <int KM>
@@ -62,21 +39,6 @@ struct AbSysT {
     /* KM == 1 means "no variational particles": the count is a compile-time zero so that
      * every array index is static and the state lives in registers */
     __device__ __forceinline__ int nv() const { return (KM == 1) ? 0 : nv_; }
-};
-
-/* A node table staged in shared memory, one column per thread (element q of thread `tid` at
- * [q * AB_BLOCK + tid]: conflict-free).  Same member syntax as AbNode / AbBodies. */
-struct AbColRow { const double* p; __device__ __forceinline__ double operator[](int c) const { return p[c * AB_BLOCK]; } };
-struct AbColMat { const double* p; __device__ __forceinline__ AbColRow operator[](int i) const { return AbColRow{p + 3 * i * AB_BLOCK}; } };
-struct AbColVec { const double* p; __device__ __forceinline__ double operator[](int i) const { return p[i * AB_BLOCK]; } };
-struct AbNodeS {
-    const double* gm;
-    AbColMat pos, vel;
-    AbColVec earth_acc, eih_term1;
-    AbColMat eih_ar, eih_av;
-    __device__ __forceinline__ AbNodeS(const double* gm_, const double* col)
-        : gm(gm_), pos{col}, vel{col + 81 * AB_BLOCK}, earth_acc{col + 84 * AB_BLOCK}, eih_term1{col + 87 * AB_BLOCK},
-          eih_ar{col + 88 * AB_BLOCK}, eih_av{col + 91 * AB_BLOCK} {}
 };
 
 /* 3x6 Jacobian applied to every variational particle of the system. */
@@ -475,22 +437,6 @@ __device__ void ab_force_eih(const AbEphem& E, const AbForceOpts& F, const BT& B
 
     /* sum over the 11 planets of GM_k / r_ik: identical for every source j (src/forces.c:1400-1416) */
     double term0_sum = 0.0;
-#if !AB_OPT_EIHPIPE
-    {
-        double q[AB_NPLANETS];
-#pragma unroll kEihUnroll
-        for (int k = 0; k < AB_NPLANETS; k++) {   /* 11 independent sqrt + quotient chains */
-            const double dxik = pix + (xo - B.pos[k][0]);
-            const double dyik = piy + (yo - B.pos[k][1]);
-            const double dzik = piz + (zo - B.pos[k][2]);
-            const double rik2 = dxik * dxik + dyik * dyik + dzik * dzik;
-            const double _rik = sqrt(rik2);
-            q[k] = B.gm[k] / _rik;
-        }
-#pragma unroll
-        for (int k = 0; k < AB_NPLANETS; k++) term0_sum += q[k];   /* summed in the reference's order */
-    }
-#else
     {   /* rolled, the next planet's table entries requested one trip ahead */
         const double* const gm = B.gm;
         double nx = B.pos[0][0], ny = B.pos[0][1], nz = B.pos[0][2], ngm = gm[0];
@@ -506,7 +452,6 @@ __device__ void ab_force_eih(const AbEphem& E, const AbForceOpts& F, const BT& B
             term0_sum += GMk / _rik;
         }
     }
-#endif
 
     {   /* real particle, src/forces.c:1319-1501 */
         double term7x_sum = 0.0, term7y_sum = 0.0, term7z_sum = 0.0;
@@ -753,98 +698,6 @@ __device__ void ab_force_eih(const AbEphem& E, const AbForceOpts& F, const BT& B
 }
 
 /* ---- direct Newtonian terms, reference src/forces.c:266-433 ---------------- */
-/* Bodies are taken in the reference's order, four at a time: the separations, square roots and
- * quotients of a group do not depend on each other, so they are formed first (loads and FP64
- * latencies of four bodies overlap); the accumulation into the acceleration then runs in the
- * reference's sequence, which is what fixes the rounding. */
-template <int KM, class BT>
-__device__ __forceinline__ void ab_direct_group(const AbForceOpts& F, const BT& B, AbSysT<KM>& S, const int* idx, int cnt,
-                                                double px, double py, double pz, double xo, double yo, double zo) {
-    double gm[4], dx[4], dy[4], dz[4], r2[4], r[4], prefac[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        if (q < cnt) {
-            const int i = idx[q];
-            gm[q] = B.gm[i];
-            dx[q] = px + (xo - B.pos[i][0]);
-            dy[q] = py + (yo - B.pos[i][1]);
-            dz[q] = pz + (zo - B.pos[i][2]);
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        if (q < cnt) {
-            r2[q] = dx[q] * dx[q] + dy[q] * dy[q] + dz[q] * dz[q];
-            r[q] = sqrt(r2[q]);
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-        if (q < cnt) prefac[q] = gm[q] / (r[q] * r[q] * r[q]);
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        if (q < cnt) {
-            const int i = idx[q];
-            bool on = true;
-            if (i == 0 && !(F.forces & 0x01)) on = false;
-            if (i > 0 && i < AB_NPLANETS && !(F.forces & 0x02)) on = false;
-            if (i >= AB_NPLANETS && !(F.forces & 0x04)) on = false;
-            if (on) {
-                S.a[0][0] -= prefac[q] * dx[q];
-                S.a[0][1] -= prefac[q] * dy[q];
-                S.a[0][2] -= prefac[q] * dz[q];
-            }
-            if (S.nv() > 0) {
-                /* no force-mask check here, as in the reference (src/forces.c:359) */
-                const double r3inv = 1. / (r2[q] * r[q]);
-                const double r5inv = 3. * r3inv / r2[q];
-                const double dxdx = dx[q] * dx[q] * r5inv - r3inv;
-                const double dydy = dy[q] * dy[q] * r5inv - r3inv;
-                const double dzdz = dz[q] * dz[q] * r5inv - r3inv;
-                const double dxdy = dx[q] * dy[q] * r5inv;
-                const double dxdz = dx[q] * dz[q] * r5inv;
-                const double dydz = dy[q] * dz[q] * r5inv;
-                for (int vv = 1; vv <= S.nv(); vv++) {
-                    const double ddx = S.x[vv][0], ddy = S.x[vv][1], ddz = S.x[vv][2];
-                    const double dax = ddx * dxdx + ddy * dxdy + ddz * dxdz;
-                    const double day = ddx * dxdy + ddy * dydy + ddz * dydz;
-                    const double daz = ddx * dxdz + ddy * dydz + ddz * dzdz;
-                    S.a[vv][0] += gm[q] * dax;
-                    S.a[vv][1] += gm[q] * day;
-                    S.a[vv][2] += gm[q] * daz;
-                }
-            }
-        }
-    }
-}
-
-#ifndef AB_DIRECT_CHUNK
-#define AB_DIRECT_CHUNK 0
-#endif
-#if AB_DIRECT_CHUNK
-template <int KM, class BT>
-__device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT& B, AbSysT<KM>& S,
-                                double xo, double yo, double zo) {
-    const int ast_num = E.n_ast;
-    const double px = S.x[0][0], py = S.x[0][1], pz = S.x[0][2];
-    /* asteroids first ... */
-    for (int k0 = 0; k0 < ast_num; k0 += 4) {
-        const int idx[4] = {AB_NPLANETS + k0, AB_NPLANETS + k0 + 1, AB_NPLANETS + k0 + 2, AB_NPLANETS + k0 + 3};
-        const int cnt = (ast_num - k0 < 4) ? (ast_num - k0) : 4;
-        ab_direct_group<KM, BT>(F, B, S, idx, cnt, px, py, pz, xo, yo, zo);
-    }
-    /* ... then Pluto, Moon, Mars, Mercury, Neptune, Uranus, Earth, Venus, Saturn, Jupiter, Sun (src/forces.c:281-293) */
-    {
-        const int g0[4] = {10, 4, 5, 1};
-        ab_direct_group<KM, BT>(F, B, S, g0, 4, px, py, pz, xo, yo, zo);
-        const int g1[4] = {9, 8, 3, 2};
-        ab_direct_group<KM, BT>(F, B, S, g1, 4, px, py, pz, xo, yo, zo);
-        const int g2[4] = {7, 6, 0, 0};
-        ab_direct_group<KM, BT>(F, B, S, g2, 3, px, py, pz, xo, yo, zo);
-    }
-}
-
-#else
 /* Body visited at position k of the reference's loop (src/forces.c:281-306): asteroids first, then
  * Pluto, Moon, Mars, Mercury, Neptune, Uranus, Earth, Venus, Saturn, Jupiter, Sun -- the planet
  * sequence packed four bits each, so the index is arithmetic, not a (dependent) table load. */
@@ -858,41 +711,22 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT
     const int ast_num = E.n_ast;
     const int nb = AB_NPLANETS + ast_num;
     const double px = S.x[0][0], py = S.x[0][1], pz = S.x[0][2];
-#if AB_OPT_FMASK
     const int fmask = F.forces;
-#else
-#define fmask F.forces
-#endif
-#if AB_OPT_REGACC
     /* the running sums stay in registers; the additions happen in the reference's sequence */
     double acx = S.a[0][0], acy = S.a[0][1], acz = S.a[0][2];
-#endif
     /* the table entries of the next body are requested while the current body is being worked on */
     const double* const gm = B.gm;       /* read once: the table is not written while the forces are evaluated */
     int i_next = ab_direct_body(0, ast_num);
     double bx = B.pos[i_next][0], by = B.pos[i_next][1], bz = B.pos[i_next][2], bgm = gm[i_next];
-#if AB_DIRECT_PF == 2
-    /* two bodies ahead: a trip to HBM (the tables of 57 k threads do not fit L2) is longer than one loop trip */
-    int i_next2 = (nb > 1) ? ab_direct_body(1, ast_num) : i_next;
-    double ex = B.pos[i_next2][0], ey = B.pos[i_next2][1], ez = B.pos[i_next2][2], egm = gm[i_next2];
-#endif
-#pragma unroll kDirectUnroll
+#pragma unroll 1      /* rolled on purpose: unrolled x2 / x3 it is 3-6 % slower (instruction fetch), profiles/README.md */
     for (int k = 0; k < nb; k++) {
         const int i = i_next;
         const double GM = bgm;
         const double cx = bx, cy = by, cz = bz;
-#if AB_DIRECT_PF == 2
-        i_next = i_next2; bx = ex; by = ey; bz = ez; bgm = egm;
-        if (k + 2 < nb) {
-            i_next2 = ab_direct_body(k + 2, ast_num);
-            ex = B.pos[i_next2][0]; ey = B.pos[i_next2][1]; ez = B.pos[i_next2][2]; egm = gm[i_next2];
-        }
-#else
         if (k + 1 < nb) {
             i_next = ab_direct_body(k + 1, ast_num);
             bx = B.pos[i_next][0]; by = B.pos[i_next][1]; bz = B.pos[i_next][2]; bgm = gm[i_next];
         }
-#endif
         const double dx = px + (xo - cx);
         const double dy = py + (yo - cy);
         const double dz = pz + (zo - cz);
@@ -904,15 +738,9 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT
         if (i >= AB_NPLANETS && !(fmask & 0x04)) on = false;
         if (on) {
             const double prefac = GM / (_r * _r * _r);
-#if AB_OPT_REGACC
             acx -= prefac * dx;
             acy -= prefac * dy;
             acz -= prefac * dz;
-#else
-            S.a[0][0] -= prefac * dx;
-            S.a[0][1] -= prefac * dy;
-            S.a[0][2] -= prefac * dz;
-#endif
         }
         if (S.nv() > 0) {
             /* no force-mask check here, as in the reference (src/forces.c:359) */
@@ -935,14 +763,8 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT
             }
         }
     }
-#if AB_OPT_REGACC
     S.a[0][0] = acx; S.a[0][1] = acy; S.a[0][2] = acz;
-#endif
-#if !AB_OPT_FMASK
-#undef fmask
-#endif
 }
-#endif
 
 /* ---- dispatcher, reference src/forces.c:49-173 ----------------------------- */
 /* S.a must be zero on entry (REBOUND zeroes accelerations before the plug-in runs). */

@@ -45,21 +45,6 @@ __device__ __noinline__ void ab_forces_ol(const AbEphem& E, const AbForceOpts& F
     ab_forces<KM, BT>(E, F, B, S);
 }
 
-#ifndef AB_STAGE_NODES
-#define AB_STAGE_NODES 0
-#endif
-/* Forces from a node table that is first copied, in one burst of independent loads, from the
- * thread's local-memory table into its shared-memory column: the ~90 table reads of a force
- * evaluation then cost shared-memory latency instead of 90 separate trips to L2/HBM. */
-template <int KM>
-__device__ __noinline__ void ab_forces_staged(const AbEphem& E, const AbForceOpts& F, const AbNode& N, AbSysT<KM>& S, double* col) {
-    const double* src = &N.pos[0][0];
-#pragma unroll 16
-    for (int q = 0; q < AB_NODE_DOUBLES; q++) col[q * AB_BLOCK] = src[q];
-    const AbNodeS V(N.gm, col);
-    ab_forces<KM, AbNodeS>(E, F, V, S);
-}
-
 #if AB_TU == 0
 /* ------------------------------------------------------------------------ */
 /* ephemeris + force evaluation kernels                                     */
@@ -210,13 +195,7 @@ __device__ __noinline__ void pp_step(const AbEphem& E, const AbForceOpts& F, con
  * predictor-corrector sweep reuses them -- what the reference's 7-slot time cache does. */
 template <int KM>
 __device__ void pp_step_nodes(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, long long i, PPState& P) {
-#if AB_STAGE_NODES
-    extern __shared__ double ab_smem[];
-    double* col = ab_smem + threadIdx.x;
-#define AB_NODE_FORCES(N) ab_forces_staged<KM>(E, F, N, S, col)
-#else
 #define AB_NODE_FORCES(N) ab_forces_ol<KM, AbNode>(E, F, N, S)
-#endif
     AbSysT<KM> S;
     AbNode nodes[AB_NT];
     double times[AB_NT];
@@ -861,14 +840,7 @@ cudaError_t PP_NAME(ab_launch_pp_integrate)(const AbEphem& E, const AbForceOpts&
                                             long long step_cap, const int* active, int n_active, cudaStream_t st) {
     const int grid = (n_active + AB_PP_BLOCK - 1) / AB_PP_BLOCK;
     if (grid < 1) return cudaSuccess;
-    const size_t smem = AB_STAGE_NODES ? sizeof(double) * AB_NODE_DOUBLES * AB_BLOCK : 0;
-    static bool attr_set = false;
-    if (smem && !attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(pp_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    pp_integrate_kernel<<<grid, AB_PP_BLOCK, smem, st>>>(E, F, Bt, tmax, exact, resume, step_cap, active, n_active);
+    pp_integrate_kernel<<<grid, AB_PP_BLOCK, 0, st>>>(E, F, Bt, tmax, exact, resume, step_cap, active, n_active);
     return cudaGetLastError();
 }
 
@@ -895,14 +867,7 @@ cudaError_t PP_NAME(ab_pp_resident_threads)(int* threads) {
 
 cudaError_t PP_NAME(ab_launch_pp_dense)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const double* times, int n_times, double* out, cudaStream_t st) {
     const int grid = (Bt.n + AB_BLOCK - 1) / AB_BLOCK;
-    const size_t smem = AB_STAGE_NODES ? sizeof(double) * AB_NODE_DOUBLES * AB_BLOCK : 0;
-    static bool attr_set = false;
-    if (smem && !attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(pp_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    pp_dense_kernel<<<grid, AB_BLOCK, smem, st>>>(E, F, Bt, times, n_times, out);
+    pp_dense_kernel<<<grid, AB_BLOCK, 0, st>>>(E, F, Bt, times, n_times, out);
     return cudaGetLastError();
 }
 #endif
