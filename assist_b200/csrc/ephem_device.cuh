@@ -37,16 +37,19 @@ __device__ __forceinline__ double ab_jul(double eph) { return 2451545.0 + AB_DIV
 
 /* Chebyshev sums for one record: 3 components, P coefficients each, argument z,
  * derivative scale c.  LEVEL 0: position, 1: +velocity, 2: +acceleration. */
-template <int LEVEL>
+/* PACKED: the device copy of an SPK kernel holds the coefficients of a record as [p][x y z] (gpu_api.cu,
+ * upload_packed_spk); DE-binary images keep the file's [x y z][p]. */
+template <int LEVEL, bool PACKED>
 __device__ __forceinline__ void ab_cheb3(const double* __restrict__ cf, int P, double z, double c,
                                          double u[3], double v[3], double w[3]) {
     double u0 = 0.0, u1 = 0.0, u2 = 0.0;
     double v0 = 0.0, v1 = 0.0, v2 = 0.0;
     double w0 = 0.0, w1 = 0.0, w2 = 0.0;
     double Tm1 = 0.0, Tm2 = 0.0, Sm1 = 0.0, Sm2 = 0.0, Um1 = 0.0, Um2 = 0.0;
+    const int stride = PACKED ? 3 : 1;
     const double* __restrict__ cx = cf;
-    const double* __restrict__ cy = cf + P;
-    const double* __restrict__ cz = cf + 2 * P;
+    const double* __restrict__ cy = cf + (PACKED ? 1 : P);
+    const double* __restrict__ cz = cf + (PACKED ? 2 : 2 * P);
     for (int p = 0; p < P; p++) {
         double T, S = 0.0, U = 0.0;
         if (p == 0) { T = 1.0; S = 0.0; U = 0.0; }
@@ -56,7 +59,7 @@ __device__ __forceinline__ void ab_cheb3(const double* __restrict__ cf, int P, d
             if (LEVEL >= 1) S = 2.0 * z * Sm1 + 2.0 * Tm1 - Sm2;
             if (LEVEL >= 2) U = (p == 2) ? 4.0 : (2.0 * z * Um1 + 4.0 * Sm1 - Um2);
         }
-        const double ax = __ldg(cx + p), ay = __ldg(cy + p), az = __ldg(cz + p);
+        const double ax = __ldg(cx + stride * p), ay = __ldg(cy + stride * p), az = __ldg(cz + stride * p);
         u0 += ax * T; u1 += ay * T; u2 += az * T;
         if (LEVEL >= 1) { v0 += ax * S * c; v1 += ay * S * c; v2 += az * S * c; }
         if (LEVEL >= 2) { w0 += ax * U * c * c; w1 += ay * U * c * c; w2 += az * U * c * c; }
@@ -98,7 +101,7 @@ __device__ __forceinline__ void ab_spk_target_pos(const double* __restrict__ img
                                                   double jd_ref, double t, double u[3], double v[3], double w[3]) {
     int P; double z, c;
     const double* cf = ab_spk_record(img, tg, jd_ref, t, &P, &z, &c);
-    ab_cheb3<LEVEL>(cf, P, z, c, u, v, w);
+    ab_cheb3<LEVEL, true>(cf, P, z, c, u, v, w);
 }
 
 /* Planet (body < 11) from an SPK kernel, reference src/spk.c:550-610, 632-693. */
@@ -148,7 +151,7 @@ __device__ __forceinline__ void ab_ascii_work(const double* __restrict__ Pcol, i
     const int b = (int)tt;
     const double frac = tt - (double)b;            /* == fmod(tt, 1.0) for tt >= 0, exactly */
     const double z = 2.0 * frac - 1.0;
-    ab_cheb3<LEVEL>(Pcol + ncf * (b * 3), ncf, z, c, u, v, w);
+    ab_cheb3<LEVEL, false>(Pcol + ncf * (b * 3), ncf, z, c, u, v, w);
 }
 
 /* Planet (body < 11) from a DE-binary file, reference src/ascii_ephem.c:275-384. */
@@ -196,7 +199,7 @@ __device__ __forceinline__ int ab_asteroid(const AbEphem& E, int m, double t, do
     int P; double z, c;
     const double* cf = ab_spk_record(E.spka_img, tg, jd_ref, t, &P, &z, &c);
     double u[3], dv[3], dw[3];
-    ab_cheb3<0>(cf, P, z, c, u, dv, dw);
+    ab_cheb3<0, true>(cf, P, z, c, u, dv, dw);
     x[0] = AB_DIVK(u[0], 149597870.7); x[1] = AB_DIVK(u[1], 149597870.7); x[2] = AB_DIVK(u[2], 149597870.7);
     return AB_OK;
 }
@@ -275,27 +278,66 @@ __device__ void ab_body_states(const AbEphem& E, const AbForceOpts& F, double t,
  * ------------------------------------------------------------------------------------------ */
 #define AB_NT 8
 
-/* position sums (km) of one series at AB_NT arguments; cf[k] points at the X coefficients */
+/* position sums (km) of one series at AB_NT arguments; cf[k] points at the first coefficient of the record.
+ * PACKED records ([p][x y z], 16-byte aligned) are read two terms at a time with three 16-byte loads. */
+template <bool PACKED>
 __device__ __forceinline__ void ab_cheb_pos_multi(const double* const* cf, int P, const double* z, double (*u)[3]) {
     double T1[AB_NT], T2[AB_NT], a0[AB_NT], a1[AB_NT], a2[AB_NT];
-#pragma unroll
-    for (int k = 0; k < AB_NT; k++) {
-        /* p = 0 (T = 1) and p = 1 (T = z) */
-        const double* c = cf[k];
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        s0 += __ldg(c) * 1.0; s1 += __ldg(c + P) * 1.0; s2 += __ldg(c + 2 * P) * 1.0;
-        s0 += __ldg(c + 1) * z[k]; s1 += __ldg(c + P + 1) * z[k]; s2 += __ldg(c + 2 * P + 1) * z[k];
-        a0[k] = s0; a1[k] = s1; a2[k] = s2;
-        T2[k] = 1.0; T1[k] = z[k];
-    }
-#pragma unroll 1
-    for (int p = 2; p < P; p++) {
+    if (PACKED) {
 #pragma unroll
         for (int k = 0; k < AB_NT; k++) {
-            const double T = 2.0 * z[k] * T1[k] - T2[k];
-            const double* c = cf[k] + p;
-            a0[k] += __ldg(c) * T; a1[k] += __ldg(c + P) * T; a2[k] += __ldg(c + 2 * P) * T;
-            T2[k] = T1[k]; T1[k] = T;
+            /* p = 0 (T = 1) and p = 1 (T = z) */
+            const double2* q = reinterpret_cast<const double2*>(cf[k]);
+            const double2 A = __ldg(q), B = __ldg(q + 1), C = __ldg(q + 2);      /* x0 y0 | z0 x1 | y1 z1 */
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            s0 += A.x * 1.0; s1 += A.y * 1.0; s2 += B.x * 1.0;
+            s0 += B.y * z[k]; s1 += C.x * z[k]; s2 += C.y * z[k];
+            a0[k] = s0; a1[k] = s1; a2[k] = s2;
+            T2[k] = 1.0; T1[k] = z[k];
+        }
+        int p = 2;
+#pragma unroll 1
+        for (; p + 1 < P; p += 2) {
+#pragma unroll
+            for (int k = 0; k < AB_NT; k++) {
+                const double2* q = reinterpret_cast<const double2*>(cf[k]) + 3 * (p >> 1);
+                const double2 A = __ldg(q), B = __ldg(q + 1), C = __ldg(q + 2);  /* xp yp | zp xp+1 | yp+1 zp+1 */
+                const double Ta = 2.0 * z[k] * T1[k] - T2[k];
+                a0[k] += A.x * Ta; a1[k] += A.y * Ta; a2[k] += B.x * Ta;
+                const double Tb = 2.0 * z[k] * Ta - T1[k];
+                a0[k] += B.y * Tb; a1[k] += C.x * Tb; a2[k] += C.y * Tb;
+                T2[k] = Ta; T1[k] = Tb;
+            }
+        }
+        if (p < P) {      /* odd number of terms: the second half of the last 16-byte pair is padding */
+#pragma unroll
+            for (int k = 0; k < AB_NT; k++) {
+                const double2* q = reinterpret_cast<const double2*>(cf[k]) + 3 * (p >> 1);
+                const double2 A = __ldg(q), B = __ldg(q + 1);
+                const double Ta = 2.0 * z[k] * T1[k] - T2[k];
+                a0[k] += A.x * Ta; a1[k] += A.y * Ta; a2[k] += B.x * Ta;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < AB_NT; k++) {
+            /* p = 0 (T = 1) and p = 1 (T = z) */
+            const double* c = cf[k];
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            s0 += __ldg(c) * 1.0; s1 += __ldg(c + P) * 1.0; s2 += __ldg(c + 2 * P) * 1.0;
+            s0 += __ldg(c + 1) * z[k]; s1 += __ldg(c + P + 1) * z[k]; s2 += __ldg(c + 2 * P + 1) * z[k];
+            a0[k] = s0; a1[k] = s1; a2[k] = s2;
+            T2[k] = 1.0; T1[k] = z[k];
+        }
+#pragma unroll 1
+        for (int p = 2; p < P; p++) {
+#pragma unroll
+            for (int k = 0; k < AB_NT; k++) {
+                const double T = 2.0 * z[k] * T1[k] - T2[k];
+                const double* c = cf[k] + p;
+                a0[k] += __ldg(c) * T; a1[k] += __ldg(c + P) * T; a2[k] += __ldg(c + 2 * P) * T;
+                T2[k] = T1[k]; T1[k] = T;
+            }
         }
     }
 #pragma unroll
@@ -316,7 +358,7 @@ __device__ __noinline__ void ab_spk_pos_multi(const double* __restrict__ img, co
         if (k == 0) P0 = P; else same = same && (P == P0);
     }
     if (same) {
-        ab_cheb_pos_multi(cf, P0, z, u);
+        ab_cheb_pos_multi<true>(cf, P0, z, u);
     } else {   /* nodes in segments with different record sizes: one at a time */
         for (int k = 0; k < AB_NT; k++) {
             double dv[3], dw[3];
@@ -341,7 +383,7 @@ __device__ __noinline__ void ab_ascii_pos_multi(const AbEphem& E, int col, const
         z[k] = 2.0 * (tt - (double)b) - 1.0;
         cf[k] = rec + E.a_off[col] + ncf * (b * 3);
     }
-    ab_cheb_pos_multi(cf, ncf, z, u);
+    ab_cheb_pos_multi<false>(cf, ncf, z, u);
 }
 
 /* Fill the AB_NT node tables of a step for the common configuration: one EIH source (the Sun),

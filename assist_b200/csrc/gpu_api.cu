@@ -4,6 +4,7 @@
  */
 #include <cuda_runtime.h>
 #include <atomic>
+#include <vector>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -105,7 +106,62 @@ static int upload_image(void** slot, const void* host, size_t len) {
     return 0;
 }
 
-static int fill_target(AbSpkTarget* d, const struct spk_target* t, const struct spk_s* file) {
+/* Device copy of an SPK kernel: only the type-2 records, segment after segment, each record as
+ * [MID, RADIUS, (x y z) of term 0, (x y z) of term 1, ...] padded to an even number of doubles, so that the
+ * coefficients of a record start on a 16-byte boundary and the three components of a term are adjacent
+ * (ephem_device.cuh reads two terms with three 16-byte loads).  Values are copied, never recomputed.
+ * off[m * AB_MAXSEG + s] = first word of segment s of target m in that copy. */
+static int spk_layout(const struct spk_s* file, std::vector<long long>& off, size_t* total_words) {
+    const double* img = (const double*)file->map;
+    const size_t words = file->len / sizeof(double);
+    off.assign((size_t)file->num * AB_MAXSEG, 0);
+    long long cur = 0;
+    for (int m = 0; m < file->num; m++) {
+        const struct spk_target* t = &file->targets[m];
+        const int nseg = t->ind + 1;
+        if (nseg > AB_MAXSEG)
+            return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "SPK target %d has %d segments (max %d)", t->code, nseg, AB_MAXSEG);
+        for (int s = 0; s < nseg; s++) {
+            if (t->two[s] < 4 || (size_t)t->two[s] > words || t->one[s] < 1)
+                return set_err(ASSIST_GPU_ERR_ARG, "SPK target %d: segment addresses out of range", t->code);
+            const double* val = img + t->two[s] - 1;
+            const int R = (int)val[-1], nrec = (int)val[0];
+            if (R < 8 || R > 98 || nrec < 1 || (size_t)(t->one[s] - 1) + (size_t)nrec * R > words)
+                return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "SPK target %d: not a type-2 Chebyshev segment", t->code);
+            off[(size_t)m * AB_MAXSEG + s] = cur;
+            cur += (long long)nrec * ((R + 1) & ~1);
+        }
+    }
+    *total_words = (size_t)cur + 2;      /* the last 16-byte pair of an odd-length record may be read past its end */
+    return 0;
+}
+
+static int upload_packed_spk(void** slot, const struct spk_s* file, const std::vector<long long>& off, size_t total_words) {
+    if (*slot) return 0;
+    const double* img = (const double*)file->map;
+    std::vector<double> buf(total_words, 0.0);
+    for (int m = 0; m < file->num; m++) {
+        const struct spk_target* t = &file->targets[m];
+        for (int s = 0; s <= t->ind; s++) {
+            const double* val = img + t->two[s] - 1;
+            const int R = (int)val[-1], nrec = (int)val[0], P = (R - 2) / 3, Rp = (R + 1) & ~1;
+            for (int b = 0; b < nrec; b++) {
+                const double* src = img + (t->one[s] - 1) + (size_t)b * R;
+                double* dst = buf.data() + off[(size_t)m * AB_MAXSEG + s] + (size_t)b * Rp;
+                dst[0] = src[0]; dst[1] = src[1];
+                for (int p = 0; p < P; p++)
+                    for (int c = 0; c < 3; c++) dst[2 + 3 * p + c] = src[2 + c * P + p];
+            }
+        }
+    }
+    void* d = nullptr;
+    CU(cudaMalloc(&d, sizeof(double) * total_words));
+    CU(cudaMemcpy(d, buf.data(), sizeof(double) * total_words, cudaMemcpyHostToDevice));
+    *slot = d;
+    return 0;
+}
+
+static int fill_target(AbSpkTarget* d, const struct spk_target* t, const struct spk_s* file, const long long* seg_off) {
     memset(d, 0, sizeof(*d));
     d->beg = t->beg; d->end = t->end; d->res = t->res; d->res_rd = 1.0 / t->res; d->mass = t->mass;
     d->code = t->code; d->cen = t->cen; d->nseg = t->ind + 1;
@@ -136,6 +192,9 @@ static int fill_target(AbSpkTarget* d, const struct spk_target* t, const struct 
         sg->uniform = 1;
         for (int b = 1; b < sg->nrec; b++)
             if (rec0[(size_t)b * sg->R + 1] != radius) { sg->uniform = 0; break; }
+        /* from here on the descriptor addresses the packed device copy, not the file */
+        sg->one = (int)(seg_off[s] + 1);
+        sg->R = (sg->R + 1) & ~1;
     }
     return 0;
 }
@@ -171,7 +230,10 @@ static int build_ephem(const struct assist_ephem* e, AbEphem* E) {
         for (int k = 0; k < AB_NPLANETS; k++) E->a_mass[k] = a->mass[k];
     } else if (e->spk_planets) {
         struct spk_s* pl = e->spk_planets;
-        if ((rc = upload_image(&pl->b200_dev_image[dev], pl->map, pl->len))) return rc;
+        std::vector<long long> poff;
+        size_t pwords = 0;
+        if ((rc = spk_layout(pl, poff, &pwords))) return rc;
+        if ((rc = upload_packed_spk(&pl->b200_dev_image[dev], pl, poff, pwords))) return rc;
         E->spkp_img = (const double*)pl->b200_dev_image[dev];
         {
             const double au = e->AU, seconds_per_day = 86400.;
@@ -181,7 +243,7 @@ static int build_ephem(const struct assist_ephem* e, AbEphem* E) {
             return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "planet kernel has %d targets (max %d)", pl->num, AB_MAX_PTGT);
         E->n_ptgt = pl->num;
         for (int m = 0; m < pl->num; m++)
-            if ((rc = fill_target(&E->p_tgt[m], &pl->targets[m], pl))) return rc;
+            if ((rc = fill_target(&E->p_tgt[m], &pl->targets[m], pl, &poff[(size_t)m * AB_MAXSEG]))) return rc;
         static const int naif_by_assist[AB_NPLANETS] = {10, 1, 2, 399, 301, 4, 5, 6, 7, 8, 9};
         for (int k = 0; k < AB_NPLANETS; k++) {
             /* precomputed index when it is consistent, else a search by NAIF code (reference src/spk.c:646-659) */
@@ -206,12 +268,15 @@ static int build_ephem(const struct assist_ephem* e, AbEphem* E) {
         struct spk_s* sb = e->spk_asteroids;
         if (sb->num > AB_MAX_AST)
             return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "small-body kernel has %d targets (max %d in this build)", sb->num, AB_MAX_AST);
-        if ((rc = upload_image(&sb->b200_dev_image[dev], sb->map, sb->len))) return rc;
+        std::vector<long long> aoff;
+        size_t awords = 0;
+        if ((rc = spk_layout(sb, aoff, &awords))) return rc;
+        if ((rc = upload_packed_spk(&sb->b200_dev_image[dev], sb, aoff, awords))) return rc;
         E->spka_img = (const double*)sb->b200_dev_image[dev];
         E->n_ast = sb->num;
         AbSpkTarget tg[AB_MAX_AST];
         for (int m = 0; m < sb->num; m++)
-            if ((rc = fill_target(&tg[m], &sb->targets[m], sb))) return rc;
+            if ((rc = fill_target(&tg[m], &sb->targets[m], sb, &aoff[(size_t)m * AB_MAXSEG]))) return rc;
         if (!sb->b200_dev_targets[dev]) CU(cudaMalloc(&sb->b200_dev_targets[dev], sizeof(AbSpkTarget) * AB_MAX_AST));
         /* descriptors carry the (joinable) masses, so they are refreshed on every build */
         CU(cudaMemcpy(sb->b200_dev_targets[dev], tg, sizeof(AbSpkTarget) * sb->num, cudaMemcpyHostToDevice));
