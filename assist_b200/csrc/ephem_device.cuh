@@ -84,13 +84,13 @@ __device__ __forceinline__ const double* ab_spk_record(const double* __restrict_
     if (b > sg.nrec - 1) b = sg.nrec - 1;
     if (b < 0) b = 0;
     const double* rec = img + (sg.one - 1) + (long long)b * sg.R;
-    const double mid = __ldg(rec);
+    const double jul_mid = __ldg(rec);          /* the packed copy holds _jul(MID) = 2451545.0 + MID / 86400.0, formed at upload */
     if (sg.uniform) {
-        *z = ab_divc((jd_ref - ab_jul(mid)) + t, sg.radius_d, sg.radius_rd);
+        *z = ab_divc((jd_ref - jul_mid) + t, sg.radius_d, sg.radius_rd);
         *c = sg.radius_inv;
     } else {
         const double radius = __ldg(rec + 1);
-        *z = ((jd_ref - ab_jul(mid)) + t) / AB_DIVK(radius, 86400.0);
+        *z = ((jd_ref - jul_mid) + t) / AB_DIVK(radius, 86400.0);
         *c = 1.0 / radius;
     }
     return rec + 2;
@@ -390,8 +390,9 @@ __device__ __noinline__ void ab_ascii_pos_multi(const AbEphem& E, int col, const
  * barycentric.  Returns an ASSIST status. */
 __device__ __noinline__ int ab_fill_nodes(const AbEphem& E, const AbForceOpts& F, const double* t, AbNode* nodes) {
     const double jd_ref = E.jd_ref;
-    /* coverage (reference src/spk.c:563-565, 416-418; src/ascii_ephem.c:294-295) */
-    for (int k = 0; k < AB_NT; k++) {
+    /* coverage (reference src/spk.c:563-565, 416-418; src/ascii_ephem.c:294-295): the node times run monotonically
+     * from t[0] to t[AB_NT - 1], so the two ends decide for all of them */
+    for (int k = 0; k < AB_NT; k += AB_NT - 1) {
         const double jd = jd_ref + t[k];
         if (E.planets_source == AB_SRC_ASCII) {
             if (jd < E.a_beg || jd > E.a_end) return AB_ERR_COVERAGE;

@@ -148,7 +148,8 @@ static int upload_packed_spk(void** slot, const struct spk_s* file, const std::v
             for (int b = 0; b < nrec; b++) {
                 const double* src = img + (t->one[s] - 1) + (size_t)b * R;
                 double* dst = buf.data() + off[(size_t)m * AB_MAXSEG + s] + (size_t)b * Rp;
-                dst[0] = src[0]; dst[1] = src[1];
+                dst[0] = 2451545.0 + src[0] / 86400.0;      /* _jul(MID), reference src/spk.c:60: one IEEE division and one addition, as there */
+                dst[1] = src[1];
                 for (int p = 0; p < P; p++)
                     for (int c = 0; c < 3; c++) dst[2 + 3 * p + c] = src[2 + c * P + p];
             }
