@@ -72,14 +72,17 @@ __device__ __forceinline__ void ab_cheb3(const double* __restrict__ cf, int P, d
     if (LEVEL >= 2) { w[0] = w0; w[1] = w1; w[2] = w2; }
 }
 
-/* Locate the type-2 record of `tg` that holds jd_ref + t (reference src/spk.c:501-517). */
-__device__ __forceinline__ const double* ab_spk_record(const double* __restrict__ img, const AbSpkTarget& tg,
-                                                       double jd_ref, double t, int* P, double* z, double* c) {
+/* Segment of `tg` that holds jd_ref + t (reference src/spk.c:501-502). */
+__device__ __forceinline__ int ab_spk_segment(const AbSpkTarget& tg, double jd_ref, double t) {
     int n = (int)ab_divc(jd_ref + t - tg.beg, tg.res, tg.res_rd);
     if (n > tg.nseg - 1) n = tg.nseg - 1;       /* jd == end: the reference indexes one past; stay in the last segment */
     if (n < 0) n = 0;
-    const AbSpkSeg& sg = tg.seg[n];
-    *P = sg.P;
+    return n;
+}
+
+/* Locate the type-2 record of segment `sg` that holds jd_ref + t (reference src/spk.c:503-517). */
+__device__ __forceinline__ const double* ab_spk_record_in(const double* __restrict__ img, const AbSpkSeg& sg,
+                                                          double jd_ref, double t, double* z, double* c) {
     int b = (int)ab_divc((jd_ref - sg.jul_init) + t, sg.intlen_d, sg.intlen_rd);
     if (b > sg.nrec - 1) b = sg.nrec - 1;
     if (b < 0) b = 0;
@@ -94,6 +97,13 @@ __device__ __forceinline__ const double* ab_spk_record(const double* __restrict_
         *c = 1.0 / radius;
     }
     return rec + 2;
+}
+
+__device__ __forceinline__ const double* ab_spk_record(const double* __restrict__ img, const AbSpkTarget& tg,
+                                                       double jd_ref, double t, int* P, double* z, double* c) {
+    const AbSpkSeg& sg = tg.seg[ab_spk_segment(tg, jd_ref, t)];
+    *P = sg.P;
+    return ab_spk_record_in(img, sg, jd_ref, t, z, c);
 }
 
 template <int LEVEL>
@@ -351,11 +361,24 @@ __device__ __noinline__ void ab_spk_pos_multi(const double* __restrict__ img, co
     double z[AB_NT];
     int P0 = 0;
     bool same = true;
+    /* the node times run monotonically from t[0] to t[AB_NT - 1]: when the two ends fall into the same segment
+     * (segments are years long) so do all of them, and its descriptor is looked up once */
+    const int n_first = ab_spk_segment(tg, jd_ref, t[0]);
+    if (n_first == ab_spk_segment(tg, jd_ref, t[AB_NT - 1])) {
+        const AbSpkSeg& sg = tg.seg[n_first];
+        P0 = sg.P;
 #pragma unroll
-    for (int k = 0; k < AB_NT; k++) {
-        int P; double c;
-        cf[k] = ab_spk_record(img, tg, jd_ref, t[k], &P, &z[k], &c);
-        if (k == 0) P0 = P; else same = same && (P == P0);
+        for (int k = 0; k < AB_NT; k++) {
+            double c;
+            cf[k] = ab_spk_record_in(img, sg, jd_ref, t[k], &z[k], &c);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < AB_NT; k++) {
+            int P; double c;
+            cf[k] = ab_spk_record(img, tg, jd_ref, t[k], &P, &z[k], &c);
+            if (k == 0) P0 = P; else same = same && (P == P0);
+        }
     }
     if (same) {
         ab_cheb_pos_multi<true>(cf, P0, z, u);
