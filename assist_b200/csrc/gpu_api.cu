@@ -136,10 +136,39 @@ static int spk_layout(const struct spk_s* file, std::vector<long long>& off, siz
     return 0;
 }
 
+static void pack_spk(const struct spk_s* file, const std::vector<long long>& off, std::vector<double>& buf);
+
 static int upload_packed_spk(void** slot, const struct spk_s* file, const std::vector<long long>& off, size_t total_words) {
     if (*slot) return 0;
-    const double* img = (const double*)file->map;
     std::vector<double> buf(total_words, 0.0);
+    pack_spk(file, off, buf);
+    void* d = nullptr;
+    CU(cudaMalloc(&d, sizeof(double) * total_words));
+    CU(cudaMemcpy(d, buf.data(), sizeof(double) * total_words, cudaMemcpyHostToDevice));
+    *slot = d;
+    return 0;
+}
+
+/* Host-only view of the packed copy (no device needed): what upload_packed_spk sends.  `*out` is malloc'ed
+ * (free() it), seg_off receives AB_MAXSEG entries per target.  Used by tests/test_cpu_host.py. */
+extern "C" int assist_gpu_spk_pack_host(const struct spk_s* file, double** out, size_t* words, long long* seg_off, int seg_off_len) {
+    if (!file || !out || !words) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    std::vector<long long> off;
+    size_t total = 0;
+    int rc = spk_layout(file, off, &total);
+    if (rc) return rc;
+    std::vector<double> buf(total, 0.0);
+    pack_spk(file, off, buf);
+    double* o = (double*)malloc(sizeof(double) * total);
+    if (!o) return set_err(ASSIST_GPU_ERR_ARG, "out of memory");
+    memcpy(o, buf.data(), sizeof(double) * total);
+    *out = o; *words = total;
+    if (seg_off) for (int q = 0; q < seg_off_len && q < (int)off.size(); q++) seg_off[q] = off[q];
+    return 0;
+}
+
+static void pack_spk(const struct spk_s* file, const std::vector<long long>& off, std::vector<double>& buf) {
+    const double* img = (const double*)file->map;
     for (int m = 0; m < file->num; m++) {
         const struct spk_target* t = &file->targets[m];
         for (int s = 0; s <= t->ind; s++) {
@@ -155,11 +184,6 @@ static int upload_packed_spk(void** slot, const struct spk_s* file, const std::v
             }
         }
     }
-    void* d = nullptr;
-    CU(cudaMalloc(&d, sizeof(double) * total_words));
-    CU(cudaMemcpy(d, buf.data(), sizeof(double) * total_words, cudaMemcpyHostToDevice));
-    *slot = d;
-    return 0;
 }
 
 static int fill_target(AbSpkTarget* d, const struct spk_target* t, const struct spk_s* file, const long long* seg_off) {

@@ -137,6 +137,11 @@ void assist_gpu_host_free(void* p);
 double assist_gpu_measure_fp64_peak(int iters);
 /* Number of CUDA kernels this library has launched in this process so far (all devices, all batches). */
 unsigned long long assist_gpu_kernel_launches(void);
+/* Host-only test hook: the re-packed copy of an SPK kernel that is uploaded to the device (type-2 records only,
+ * each [_jul(MID), RADIUS, (x y z) of term 0, (x y z) of term 1, ...] padded to an even number of doubles).
+ * *out is malloc'ed; seg_off[target * 4 + segment] = first word of that segment in the copy. */
+struct spk_s;
+int assist_gpu_spk_pack_host(const struct spk_s* file, double** out, size_t* words, long long* seg_off, int seg_off_len);
 
 #ifdef __cplusplus
 }

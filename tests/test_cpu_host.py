@@ -167,3 +167,48 @@ def test_synthetic_inputs_are_deterministic(tmp_path):
     assert not np.array_equal(a, populations.neo_mba_mix(1000, seed=4))
     c, prm = populations.comets(100)
     assert c.shape == (100, 6) and prm.shape == (100, 3) and np.isfinite(c).all()
+
+
+def test_packed_spk_copy_is_a_pure_rearrangement(lib, paths):
+    """The device copy of an SPK kernel (gpu_api.cu, upload_packed_spk) against an independent reader of the file:
+    records 16-byte aligned, [_jul(MID), RADIUS, (x y z) per term], nothing else changed."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import np_oracle
+    lib.assist_spk_init.restype = ctypes.c_void_p
+    lib.assist_spk_init.argtypes = [ctypes.c_char_p]
+    lib.assist_spk_free.argtypes = [ctypes.c_void_p]
+    lib.assist_gpu_spk_pack_host.restype = ctypes.c_int
+    lib.assist_gpu_spk_pack_host.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.POINTER(ctypes.c_double)),
+                                            ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
+    libc = ctypes.CDLL(None)
+    libc.free.argtypes = [ctypes.c_void_p]
+    for key in ("planets_bsp", "asteroids_bsp"):
+        f = np_oracle.SpkFile(paths[key])
+        h = lib.assist_spk_init(paths[key].encode())
+        assert h
+        out = ctypes.POINTER(ctypes.c_double)()
+        words = ctypes.c_size_t(0)
+        nt = len(f.order)
+        off = (ctypes.c_longlong * (4 * nt))()
+        assert lib.assist_gpu_spk_pack_host(h, ctypes.byref(out), ctypes.byref(words), off, 4 * nt) == 0
+        packed = np.ctypeslib.as_array(out, shape=(words.value,)).copy()
+        libc.free(out)
+        lib.assist_spk_free(h)
+        expect_words = 0
+        for m, code in enumerate(f.order):
+            for s, (one, two) in enumerate(f.targets[code]["segs"]):
+                init, intlen, rsize, nrec = f.words[two - 4: two]
+                R, nrec = int(rsize), int(nrec)
+                P, Rp = (R - 2) // 3, (R + 1) & ~1
+                o = off[4 * m + s]
+                assert o % 2 == 0 and o == expect_words
+                src = f.words[one - 1: one - 1 + nrec * R].reshape(nrec, R)
+                dst = packed[o: o + nrec * Rp].reshape(nrec, Rp)
+                assert np.array_equal(dst[:, 0], 2451545.0 + src[:, 0] / 86400.0)
+                assert np.array_equal(dst[:, 1], src[:, 1])
+                coef = src[:, 2:].reshape(nrec, 3, P)
+                assert np.array_equal(dst[:, 2: 2 + 3 * P].reshape(nrec, P, 3), coef.transpose(0, 2, 1))
+                assert (dst[:, 2 + 3 * P:] == 0).all()
+                expect_words += nrec * Rp
+        assert words.value == expect_words + 2 and (packed[expect_words:] == 0).all()
