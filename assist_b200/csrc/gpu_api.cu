@@ -874,6 +874,8 @@ extern "C" int assist_gpu_batch_integrate_or_interpolate(assist_gpu_batch* b, co
     }
     double* d_times = (double*)((char*)b->d_out + out_bytes);
     CU(cudaMemcpy(d_times, times, sizeof(double) * n_times, cudaMemcpyHostToDevice));
+    /* rows the kernel does not write (variational slots a system does not use, systems that failed earlier) read NaN */
+    CU(cudaMemsetAsync(b->d_out, 0xFF, out_bytes, 0));
     const bool fastm = (b->opt.math == ASSIST_GPU_MATH_FAST);
     cudaError_t e;
     if (b->sched_queue) {
