@@ -117,7 +117,12 @@ int assist_gpu_batch_restore(assist_gpu_batch* b);
 /* reb_simulation_integrate(tmax) for every system. exact_finish_time as in REBOUND. max_steps<=0: no limit
  * (shared-step mode only: stop after that many accepted steps). */
 int assist_gpu_batch_integrate(assist_gpu_batch* b, double t_end, int exact_finish_time, long max_steps);
-/* assist_integrate_or_interpolate for a sorted list of epochs; out[n_times][n_sys][K][6]. */
+/* assist_integrate_or_interpolate(times[e]) for e = 0..n_times-1, per system (reference src/assist.c:642-680):
+ * out[n_times][n_sys][K][6], per-particle batches only.  The epochs are visited in the given order, whatever it is
+ * (an epoch inside the last completed step is interpolated, any other one integrates towards it, as the reference
+ * does call by call); lists that run in one direction are additionally cut into time slices for load balance.
+ * Rows that cannot be produced (a system that left the ephemeris coverage, variational slots a system does not use)
+ * hold NaN. */
 int assist_gpu_batch_integrate_or_interpolate(assist_gpu_batch* b, const double* times, int n_times, double* out);
 /* state/acc[n_sys][K][6|3]; t, dt, dt_last_done: n_sys entries in per-particle mode, 1 in shared-step mode.
  * Any pointer may be NULL. */
