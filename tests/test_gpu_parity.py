@@ -419,3 +419,30 @@ def test_full_size_population(eph, fmt, ref, paths):
     few = pick[::500]
     want, _, _, _ = rh.integrate_each(ref, reph, cases.T0, st[few], t_end, forces=0x7F, min_dt=1e-3)
     assert np.array_equal(full[few], want)
+
+
+def test_kepler_orbit_analytic(tmp_path, paths, lib):
+    """The analytic pin of tests/test_cpu_oracle.py on the CUDA path: Sun at rest (planet masses zeroed in the
+    synthetic model), SUN force only, e = 0.6: back at the start after 170 periods."""
+    from assist_b200.synth import ephem_writer as ew
+    model = ew.SolarSystemModel()
+    for p in model.planets.values():
+        p["gm"] = 0.0
+    planets = str(tmp_path / "kepler_planets.bsp")
+    ew.write_planets_bsp(planets, model)
+    e_ = ab.EphemHandle(planets, paths["asteroids_bsp"])
+    mu = ew.CONSTANTS["GMS"]
+    a, e = 0.5, 0.6
+    period = 2.0 * np.pi * np.sqrt(a ** 3 / mu)
+    x0 = np.array([[a * (1 - e), 0.0, 0.0, 0.0, np.sqrt(mu / a * (1 + e) / (1 - e)), 0.0]])
+    t0 = -10000.0
+    b = ab.Batch(e_, 1, 0, ab.PER_PARTICLE, forces=0x01)
+    b.set_state(t0, x0[:, None, :])
+    b.integrate(t0 + 170 * period)
+    st = b.get_state()["state"][0, 0]
+    b.close()
+    def energy(q):
+        return 0.5 * np.dot(q[3:], q[3:]) - mu / np.linalg.norm(q[:3])
+    assert abs(energy(st) / energy(x0[0]) - 1.0) < 1e-14
+    dt_res = (t0 + 170 * period) - t0 - 170 * period
+    assert np.linalg.norm(st[:3] - np.array([x0[0, 0], x0[0, 4] * dt_res, 0.0])) < 1e-11
