@@ -1,0 +1,653 @@
+/*
+ * coop_device.cuh -- per-particle-dt IAS15 with a whole CTA stepping 32 systems together.
+ *
+ * Why: one thread per system (kernels.cu, pp_queue_kernel) keeps the 8 body tables of a step (6 KB) and the
+ * IAS15 tables in thread-local / global memory and walks one dependent chain per system.  Here a system's
+ * working set lives ON CHIP -- the body tables of its 8 node times in shared memory, its IAS15 state in the
+ * registers of three "component" warps -- and the independent work of a step is spread over the CTA:
+ *
+ *     lane  = system slot (32 systems per CTA, structure-of-arrays in shared memory with stride 32:
+ *             every access of a warp is 32 consecutive doubles, conflict free)
+ *     warp  = task
+ *         warps 0-2    component x / y / z of every system: predictor, ordered force sums, g/b update,
+ *                      advance, predict_next  (b, g, e, csb, x0, v0, a0, cs* in registers)
+ *         warp  3      control: queue, reb_simulation_integrate bookkeeping, output epochs, convergence and
+ *                      step-size control (sqrt7)
+ *         warps 4-15   workers: one body of the direct term (+ its share of the EIH sums) or one of the
+ *                      single-body terms (Earth J2-J4, solar J2, EIH source block, Marsden, GR variants) per task
+ *         all 16       the Chebyshev fill of the node tables: thread = (slot, node), so the eight nodes of a
+ *                      system read the same one or two coefficient records (broadcast loads instead of 32 lanes
+ *                      gathering 32 records)
+ *
+ * Values are those of the one-thread-per-system path, bit for bit in the strict build: every term is formed
+ * by the same operations, and the sums that the reference accumulates in a fixed order (27 direct terms,
+ * 11 EIH potential terms, the term sequence of the dispatcher) are added in that order by the component warps
+ * from the per-body values left in shared memory.
+ *   reference src/forces.c:49-173 (dispatcher order), :266-344 (direct), :1288-1501 (EIH, real particle),
+ *   src/spk.c:405-547, src/ascii_ephem.c:27-65, 275-384 (Chebyshev), REBOUND IAS15 (see ias15_device.cuh).
+ *
+ * Scope: systems without variational particles, one EIH source, barycentric -- the configuration of the
+ * node-table fast path.  Everything else runs on pp_queue_kernel.
+ *
+ * The code is written as warp-level role functions made of per-lane blocks (ABC_LANES) separated by CTA
+ * barriers (ABC_SYNC).  Built with AB_HOST_EMUL the same source runs on the host, one OS thread per warp
+ * (tests/emul): that is how the control flow was brought up without a GPU.
+ */
+#ifndef AB_COOP_DEVICE_CUH
+#define AB_COOP_DEVICE_CUH
+
+#include "device_types.h"
+#include "ephem_device.cuh"
+#include "forces_device.cuh"
+#include "ias15_device.cuh"
+
+/* node table: entries of one (node, slot) */
+#define ABC_TAB_E 88
+#define ABC_NODE_STRIDE (ABC_TAB_E * ABC_SLOTS + 4)    /* +4: the 8 nodes of a slot fall into different banks (fill stores) */
+#define ABC_E_POS(i, c) ((i) * 3 + (c))
+#define ABC_E_SVEL(c) (81 + (c))
+#define ABC_E_TERM1 84
+#define ABC_E_AR(c) (85 + (c))
+
+/* contribution slots */
+#define ABC_C_NG 0
+#define ABC_C_EARTH 3
+#define ABC_C_SUNJ2 6
+#define ABC_C_M 9          /* (-prefacij) * d_ij */
+#define ABC_C_T 12         /* term1 .. term6 */
+#define ABC_C_E78 18       /* term7_sum * over_C2 + term8_sum * over_C2 */
+#define ABC_C_GRPOT 21
+#define ABC_C_GRSIMPLE 24
+#define ABC_NCON 27
+
+/* shared-memory carve-up (doubles first, then ints) */
+#define ABC_SM_TAB 0
+#define ABC_SM_XV (ABC_SM_TAB + 8 * ABC_NODE_STRIDE)
+#define ABC_SM_PROD (ABC_SM_XV + 6 * ABC_SLOTS)
+#define ABC_SM_Q (ABC_SM_PROD + 81 * ABC_SLOTS)
+#define ABC_SM_CON (ABC_SM_Q + 11 * ABC_SLOTS)
+#define ABC_SM_MON (ABC_SM_CON + ABC_NCON * ABC_SLOTS)       /* |a| x3, |db6| x3, |b6| x3 */
+#define ABC_SM_PRM (ABC_SM_MON + 9 * ABC_SLOTS)
+#define ABC_SM_T0 (ABC_SM_PRM + 3 * ABC_SLOTS)               /* start time of the attempt */
+#define ABC_SM_DT (ABC_SM_T0 + ABC_SLOTS)                    /* step of the attempt */
+#define ABC_SM_RATIO (ABC_SM_DT + ABC_SLOTS)                 /* predict_next ratio */
+#define ABC_SM_DOUBLES (ABC_SM_RATIO + ABC_SLOTS)
+#define ABC_SMI_ACTIVE 0      /* slot takes part in this attempt */
+#define ABC_SMI_NEEDA0 1      /* slot needs the force evaluation at the start of the step */
+#define ABC_SMI_SW 2          /* slot is still sweeping */
+#define ABC_SMI_DEC 3         /* 0 nothing, 1 accepted, 2 rejected, 3 rejected and no previous step */
+#define ABC_SMI_NGON 4        /* Marsden term active for this slot */
+#define ABC_SMI_ERR 5         /* ephemeris status of the fill */
+#define ABC_SM_INTS (6 * ABC_SLOTS)
+#define ABC_SMEM_BYTES ((size_t)ABC_SM_DOUBLES * 8 + (size_t)ABC_SM_INTS * 4)
+
+#ifdef AB_HOST_EMUL
+#define ABC_NL 32
+#define ABC_LANES(l) for (int l = 0; l < 32; ++l)
+#define ABC_LI(l) (l)
+#define ABC_SYNC() abc_emul_sync(ctx)
+#define ABC_SYNC_OR(p) abc_emul_sync_or(ctx, (p))
+#define ABC_CTXARG AbcEmulCtx *ctx,
+#define ABC_CTXPASS ctx,
+#define ABC_BLOCK (ctx->block)
+#else
+#define ABC_NL 1
+#define ABC_LANES(l) for (int l = (int)(threadIdx.x & 31), once_ = 1; once_; once_ = 0)
+#define ABC_LI(l) 0
+#define ABC_SYNC() __syncthreads()
+#define ABC_SYNC_OR(p) (__syncthreads_or(p) != 0)
+#define ABC_CTXARG
+#define ABC_CTXPASS
+#define ABC_BLOCK ((int)blockIdx.x)
+#endif
+
+namespace AB_NS {
+
+/* What the force routines of forces_device.cuh see as "body table": one node of one slot in shared memory. */
+struct AbcRow {
+    const double* p;
+    __device__ __forceinline__ double operator[](int c) const { return p[c * ABC_SLOTS]; }
+};
+struct AbcRows {
+    const double* base;
+    int stride;       /* doubles between consecutive rows */
+    __device__ __forceinline__ AbcRow operator[](int i) const { return AbcRow{base + i * stride}; }
+};
+struct AbcScalars {
+    const double* base;
+    __device__ __forceinline__ double operator[](int) const { return *base; }
+};
+struct AbcTabView {
+    const double* gm;
+    AbcRows pos, vel, eih_ar, eih_av;
+    AbcScalars eih_term1;
+    double earth_acc[3];
+    __device__ __forceinline__ AbcTabView(const double* gm_, const double* node_slot) : gm(gm_) {
+        pos.base = node_slot; pos.stride = 3 * ABC_SLOTS;
+        vel.base = node_slot + ABC_E_SVEL(0) * ABC_SLOTS; vel.stride = 0;
+        eih_ar.base = node_slot + ABC_E_AR(0) * ABC_SLOTS; eih_ar.stride = 0;
+        eih_av = eih_ar;
+        eih_term1.base = node_slot + ABC_E_TERM1 * ABC_SLOTS;
+        earth_acc[0] = earth_acc[1] = earth_acc[2] = 0.0;
+    }
+};
+
+struct AbcSmem {
+    double* d;
+    int* i;
+    __device__ __forceinline__ double* tab(int node, int slot) const { return d + ABC_SM_TAB + node * ABC_NODE_STRIDE + slot; }
+    __device__ __forceinline__ double& xv(int e, int slot) const { return d[ABC_SM_XV + e * ABC_SLOTS + slot]; }
+    __device__ __forceinline__ double& prod(int body, int c, int slot) const { return d[ABC_SM_PROD + (body * 3 + c) * ABC_SLOTS + slot]; }
+    __device__ __forceinline__ double& q(int k, int slot) const { return d[ABC_SM_Q + k * ABC_SLOTS + slot]; }
+    __device__ __forceinline__ double& con(int e, int slot) const { return d[ABC_SM_CON + e * ABC_SLOTS + slot]; }
+    __device__ __forceinline__ double& mon(int e, int slot) const { return d[ABC_SM_MON + e * ABC_SLOTS + slot]; }
+    __device__ __forceinline__ double& prm(int e, int slot) const { return d[ABC_SM_PRM + e * ABC_SLOTS + slot]; }
+    __device__ __forceinline__ double& t0(int slot) const { return d[ABC_SM_T0 + slot]; }
+    __device__ __forceinline__ double& dt(int slot) const { return d[ABC_SM_DT + slot]; }
+    __device__ __forceinline__ double& ratio(int slot) const { return d[ABC_SM_RATIO + slot]; }
+    __device__ __forceinline__ int& flag(int which, int slot) const { return i[which * ABC_SLOTS + slot]; }
+};
+
+/* everything a role function needs, by value */
+struct AbcArgs {
+    AbBatch Bt, W;
+    double tmax;
+    int exact_finish_time;
+    unsigned long long* queue_head;
+    AbSlices SL;
+    const double* times;
+    int n_times;
+    double* out;
+    AbcPlan plan;
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* node-table fill                                                                            */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Coverage and presence checks of a step, as ab_fill_nodes makes them (the two end nodes decide). */
+__device__ int abc_coverage(const AbEphem& E, double t_first, double t_last) {
+    const double jd_ref = E.jd_ref;
+    for (int k = 0; k < 2; k++) {
+        const double jd = jd_ref + (k == 0 ? t_first : t_last);
+        if (E.planets_source == AB_SRC_ASCII) {
+            if (jd < E.a_beg || jd > E.a_end) return AB_ERR_COVERAGE;
+        } else {
+            for (int b = 0; b < AB_NPLANETS; b++) {
+                const int idx = E.p_index[b];
+                if (idx < 0) { if (b != 3) return AB_ERR_NEPHEM; continue; }
+                if (jd < E.p_tgt[idx].beg || jd > E.p_tgt[idx].end) return AB_ERR_COVERAGE;
+            }
+        }
+        for (int m = 0; m < E.n_ast; m++)
+            if (jd < E.a_tgt[m].beg || jd > E.a_tgt[m].end) return AB_ERR_COVERAGE;
+    }
+    return AB_OK;
+}
+
+/* F1: thread = (slot, node, half).  Planet positions in AU, the Sun's velocity, heliocentric asteroid positions. */
+__device__ void abc_fill_f1(const AbEphem& E, const AbcSmem& sm, const AbcPlan& plan, int warp, int lane) {
+    const int slot = 4 * (warp & 7) + (lane >> 3);
+    const int node = lane & 7;
+    const int half = warp >> 3;
+    if (!sm.flag(ABC_SMI_ACTIVE, slot)) return;
+    const double t0 = sm.t0(slot);
+    const double t = (node == 0) ? t0 : (t0 + sm.dt(slot) * c_h[node]);
+    double* tb = sm.tab(node, slot);
+    int err = AB_OK;
+    int m_first, m_last;
+    if (half == 0) {
+        for (int b = 0; b < AB_NPLANETS; b++) {
+            double GM, x[3], v[3], a[3];
+            int flag;
+            if (b == 0) {
+                flag = ab_planet<1>(E, 0, t, &GM, x, v, a);
+                tb[ABC_E_SVEL(0) * ABC_SLOTS] = v[0]; tb[ABC_E_SVEL(1) * ABC_SLOTS] = v[1]; tb[ABC_E_SVEL(2) * ABC_SLOTS] = v[2];
+            } else {
+                flag = ab_planet<0>(E, b, t, &GM, x, v, a);
+            }
+            if (flag != AB_OK && err == AB_OK) err = flag;
+            tb[ABC_E_POS(b, 0) * ABC_SLOTS] = x[0]; tb[ABC_E_POS(b, 1) * ABC_SLOTS] = x[1]; tb[ABC_E_POS(b, 2) * ABC_SLOTS] = x[2];
+        }
+        m_first = 0; m_last = plan.ast_split;
+    } else {
+        m_first = plan.ast_split; m_last = E.n_ast;
+    }
+    for (int m = m_first; m < m_last; m++) {
+        double GM, x[3] = {0.0, 0.0, 0.0};
+        const int flag = ab_asteroid(E, m, t, &GM, x);
+        if (flag != AB_OK && err == AB_OK) err = flag;
+        const int b = AB_NPLANETS + m;
+        tb[ABC_E_POS(b, 0) * ABC_SLOTS] = x[0]; tb[ABC_E_POS(b, 1) * ABC_SLOTS] = x[1]; tb[ABC_E_POS(b, 2) * ABC_SLOTS] = x[2];
+    }
+    if (err != AB_OK) sm.flag(ABC_SMI_ERR, slot) = err;      /* racing writers store valid codes; the pre-check decides what is reported */
+}
+
+/* F2: threads 0..255 = (slot, node): particle-independent EIH sums of the Sun (ab_fill_nodes, same operations);
+ *     threads 256..511 = (slot, node): asteroids heliocentric -> barycentric (reference src/forces.c:213-219). */
+__device__ void abc_fill_f2(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, int warp, int lane) {
+    const int slot = 4 * (warp & 7) + (lane >> 3);
+    const int node = lane & 7;
+    if (!sm.flag(ABC_SMI_ACTIVE, slot)) return;
+    double* tb = sm.tab(node, slot);
+    const double sx = tb[ABC_E_POS(0, 0) * ABC_SLOTS], sy = tb[ABC_E_POS(0, 1) * ABC_SLOTS], sz = tb[ABC_E_POS(0, 2) * ABC_SLOTS];
+    if (warp < 8) {
+        if (!(F.forces & 0x40)) return;
+        double term1 = 0.0, arx = 0.0, ary = 0.0, arz = 0.0;
+        for (int q = 1; q < AB_NPLANETS; q++) {
+            const double GMk = E.gm[q];
+            const double dxjk = sx - tb[ABC_E_POS(q, 0) * ABC_SLOTS];
+            const double dyjk = sy - tb[ABC_E_POS(q, 1) * ABC_SLOTS];
+            const double dzjk = sz - tb[ABC_E_POS(q, 2) * ABC_SLOTS];
+            const double rjk2 = dxjk * dxjk + dyjk * dyjk + dzjk * dzjk;
+            const double _rjk = sqrt(rjk2);
+            term1 += GMk / _rjk;
+            const double fac = GMk / (rjk2 * _rjk);
+            arx -= fac * dxjk; ary -= fac * dyjk; arz -= fac * dzjk;
+        }
+        tb[ABC_E_TERM1 * ABC_SLOTS] = term1;
+        tb[ABC_E_AR(0) * ABC_SLOTS] = arx; tb[ABC_E_AR(1) * ABC_SLOTS] = ary; tb[ABC_E_AR(2) * ABC_SLOTS] = arz;
+    } else {
+        for (int m = 0; m < E.n_ast; m++) {
+            const int b = AB_NPLANETS + m;
+            tb[ABC_E_POS(b, 0) * ABC_SLOTS] = tb[ABC_E_POS(b, 0) * ABC_SLOTS] + sx;
+            tb[ABC_E_POS(b, 1) * ABC_SLOTS] = tb[ABC_E_POS(b, 1) * ABC_SLOTS] + sy;
+            tb[ABC_E_POS(b, 2) * ABC_SLOTS] = tb[ABC_E_POS(b, 2) * ABC_SLOTS] + sz;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* worker tasks (lane = slot)                                                                 */
+/* ------------------------------------------------------------------------------------------ */
+
+__device__ __forceinline__ bool abc_body_on(int i, int fmask) {
+    if (i == 0) return (fmask & 0x01) != 0;
+    if (i < AB_NPLANETS) return (fmask & 0x02) != 0;
+    return (fmask & 0x04) != 0;
+}
+
+/* One body of the direct term (reference src/forces.c:325-344) and, for a planet, its term of the EIH
+ * potential sum (src/forces.c:1400-1416: same separation, same square root). */
+__device__ __forceinline__ void abc_task_body(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, const double* tb,
+                                              int i, int slot) {
+    const double px = sm.xv(0, slot), py = sm.xv(1, slot), pz = sm.xv(2, slot);
+    const double cx = tb[ABC_E_POS(i, 0) * ABC_SLOTS], cy = tb[ABC_E_POS(i, 1) * ABC_SLOTS], cz = tb[ABC_E_POS(i, 2) * ABC_SLOTS];
+    const double GM = E.gm[i];
+    const double xo = 0.0, yo = 0.0, zo = 0.0;
+    const double dx = px + (xo - cx);
+    const double dy = py + (yo - cy);
+    const double dz = pz + (zo - cz);
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const double _r = sqrt(r2);
+    if (abc_body_on(i, F.forces)) {
+        const double prefac = GM / (_r * _r * _r);
+        sm.prod(i, 0, slot) = prefac * dx;
+        sm.prod(i, 1, slot) = prefac * dy;
+        sm.prod(i, 2, slot) = prefac * dz;
+    }
+    if (i < AB_NPLANETS && (F.forces & 0x40)) sm.q(i, slot) = GM / _r;
+}
+
+/* EIH source block of the Sun for the real particle (reference src/forces.c:1319-1501 with j = 0), everything
+ * except the potential sum over the planets, which the component warps add in order.  Same expressions as
+ * ab_force_eih. */
+__device__ void abc_task_eih_source(const AbEphem& E, const AbcSmem& sm, const double* tb, int slot) {
+    const double over_C2 = E.over_c_squared;
+    const double beta = 1.0;
+    const double gamma = 1.0;
+    const double xo = 0.0, yo = 0.0, zo = 0.0, vxo = 0.0, vyo = 0.0, vzo = 0.0, axo = 0.0, ayo = 0.0, azo = 0.0;
+    const double pix = sm.xv(0, slot), piy = sm.xv(1, slot), piz = sm.xv(2, slot);
+    const double pivx = sm.xv(3, slot), pivy = sm.xv(4, slot), pivz = sm.xv(5, slot);
+    double term7x_sum = 0.0, term7y_sum = 0.0, term7z_sum = 0.0;
+    double term8x_sum = 0.0, term8y_sum = 0.0, term8z_sum = 0.0;
+    {
+        const double GMj = E.gm[0];
+        const double xj = tb[ABC_E_POS(0, 0) * ABC_SLOTS], yj = tb[ABC_E_POS(0, 1) * ABC_SLOTS], zj = tb[ABC_E_POS(0, 2) * ABC_SLOTS];
+        const double vxj = tb[ABC_E_SVEL(0) * ABC_SLOTS], vyj = tb[ABC_E_SVEL(1) * ABC_SLOTS], vzj = tb[ABC_E_SVEL(2) * ABC_SLOTS];
+
+        const double dxij = pix + (xo - xj);
+        const double dyij = piy + (yo - yj);
+        const double dzij = piz + (zo - zj);
+        const double rij2 = dxij * dxij + dyij * dyij + dzij * dzij;
+        const double _rij = sqrt(rij2);
+        const double prefacij = GMj / (rij2 * _rij);
+
+        const double vi2 = pivx * pivx + pivy * pivy + pivz * pivz;
+        const double term2 = gamma * over_C2 * vi2;
+        const double vj2 = (vxj - vxo) * (vxj - vxo) + (vyj - vyo) * (vyj - vyo) + (vzj - vzo) * (vzj - vzo);
+        const double term3 = (1 + gamma) * over_C2 * vj2;
+        const double vidotvj = pivx * (vxj - vxo) + pivy * (vyj - vyo) + pivz * (vzj - vzo);
+        const double term4 = -2 * (1 + gamma) * over_C2 * vidotvj;
+        const double rijdotvj = dxij * (vxj - vxo) + dyij * (vyj - vyo) + dzij * (vzj - vzo);
+        const double term5 = -1.5 * over_C2 * (rijdotvj * rijdotvj) / (_rij * _rij);
+
+        const double fx = (2 + 2 * gamma) * pivx - (1 + 2 * gamma) * (vxj - vxo);
+        const double fy = (2 + 2 * gamma) * pivy - (1 + 2 * gamma) * (vyj - vyo);
+        const double fz = (2 + 2 * gamma) * pivz - (1 + 2 * gamma) * (vzj - vzo);
+        const double f = dxij * fx + dyij * fy + dzij * fz;
+
+        const double prefacij_f = prefacij * f;
+        term7x_sum += prefacij_f * (pivx - (vxj - vxo));
+        term7y_sum += prefacij_f * (pivy - (vyj - vyo));
+        term7z_sum += prefacij_f * (pivz - (vzj - vzo));
+
+        double term1 = tb[ABC_E_TERM1 * ABC_SLOTS];
+        const double axj = tb[ABC_E_AR(0) * ABC_SLOTS], ayj = tb[ABC_E_AR(1) * ABC_SLOTS], azj = tb[ABC_E_AR(2) * ABC_SLOTS];
+        term1 *= -(2 * beta - 1) * over_C2;
+
+        const double rijdotaj = dxij * (axj - axo) + dyij * (ayj - ayo) + dzij * (azj - azo);
+        const double term6 = -0.5 * over_C2 * rijdotaj;
+
+        const double term8_fac = GMj / _rij * (3 + 4 * gamma) / 2;
+        term8x_sum += term8_fac * axj;
+        term8y_sum += term8_fac * ayj;
+        term8z_sum += term8_fac * azj;
+
+        sm.con(ABC_C_T + 0, slot) = term1;
+        sm.con(ABC_C_T + 1, slot) = term2;
+        sm.con(ABC_C_T + 2, slot) = term3;
+        sm.con(ABC_C_T + 3, slot) = term4;
+        sm.con(ABC_C_T + 4, slot) = term5;
+        sm.con(ABC_C_T + 5, slot) = term6;
+        sm.con(ABC_C_M + 0, slot) = -prefacij * dxij;
+        sm.con(ABC_C_M + 1, slot) = -prefacij * dyij;
+        sm.con(ABC_C_M + 2, slot) = -prefacij * dzij;
+    }
+    sm.con(ABC_C_E78 + 0, slot) = term7x_sum * over_C2 + term8x_sum * over_C2;
+    sm.con(ABC_C_E78 + 1, slot) = term7y_sum * over_C2 + term8y_sum * over_C2;
+    sm.con(ABC_C_E78 + 2, slot) = term7z_sum * over_C2 + term8z_sum * over_C2;
+}
+
+/* The single-body terms through the routines of forces_device.cuh: the particle of the slot as a one-body system,
+ * accelerations start from zero, what the routine adds is the term. */
+__device__ __forceinline__ void abc_sys_from_slot(const AbcSmem& sm, int slot, AbSysT<1>& S) {
+    S.nv_ = 0;
+    for (int c = 0; c < 3; c++) {
+        S.x[0][c] = sm.xv(c, slot);
+        S.v[0][c] = sm.xv(3 + c, slot);
+        S.a[0][c] = 0.0;
+        S.prm[0][c] = sm.prm(c, slot);
+    }
+}
+
+__device__ void abc_run_task(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, int node, int slot, int kind) {
+    const double* tb = sm.tab(node, slot);
+    if (kind < AB_MAX_BODIES) {
+        abc_task_body(E, F, sm, tb, kind, slot);
+        if (kind == 0 && (F.forces & 0x40)) abc_task_eih_source(E, sm, tb, slot);
+        return;
+    }
+    AbSysT<1> S;
+    abc_sys_from_slot(sm, slot, S);
+    const AbcTabView B(E.gm, tb);
+    int dst;
+    switch (kind) {
+        case ABC_T_EARTHJ: ab_force_earth_harmonics<1, AbcTabView>(E, F, B, S, 0.0, 0.0, 0.0); dst = ABC_C_EARTH; break;
+        case ABC_T_SUNJ2: ab_force_solar_j2<1, AbcTabView>(E, F, B, S, 0.0, 0.0, 0.0); dst = ABC_C_SUNJ2; break;
+        case ABC_T_NG:
+            if (!sm.flag(ABC_SMI_NGON, slot)) return;
+            ab_force_nongrav<1, AbcTabView>(F, B, S, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0); dst = ABC_C_NG; break;
+        case ABC_T_GRPOT: ab_force_potential_gr<1, AbcTabView>(E, B, S, 0.0, 0.0, 0.0); dst = ABC_C_GRPOT; break;
+        case ABC_T_GRSIMPLE: ab_force_simple_gr<1, AbcTabView>(E, B, S, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0); dst = ABC_C_GRSIMPLE; break;
+        default: return;
+    }
+    sm.con(dst + 0, slot) = S.a[0][0];
+    sm.con(dst + 1, slot) = S.a[0][1];
+    sm.con(dst + 2, slot) = S.a[0][2];
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* component warps                                                                            */
+/* ------------------------------------------------------------------------------------------ */
+
+struct AbcComp {
+    double pos, vel, acc, x0, v0, a0, csx, csv, at;
+    double b[7], g[7], e[7], csb[7];
+};
+
+/* Acceleration component c of the slot's particle: the terms in the dispatcher's order, the direct terms in
+ * the reference's body order (src/forces.c:120-147, 281-306). */
+__device__ __forceinline__ double abc_sum_forces(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, int c, int slot) {
+    double a = 0.0;
+    if ((F.forces & 0x08) && sm.flag(ABC_SMI_NGON, slot)) a += sm.con(ABC_C_NG + c, slot);
+    if (F.forces & 0x10) a += sm.con(ABC_C_EARTH + c, slot);
+    if (F.forces & 0x20) a += sm.con(ABC_C_SUNJ2 + c, slot);
+    if (F.forces & 0x40) {
+        const double over_C2 = E.over_c_squared;
+        const double beta = 1.0;
+        const double gamma = 1.0;
+        double term0_sum = 0.0;
+#pragma unroll
+        for (int k = 0; k < AB_NPLANETS; k++) term0_sum += sm.q(k, slot);
+        double term0 = term0_sum;
+        term0 *= -2 * (beta + gamma) * over_C2;
+        const double term1 = sm.con(ABC_C_T + 0, slot), term2 = sm.con(ABC_C_T + 1, slot), term3 = sm.con(ABC_C_T + 2, slot);
+        const double term4 = sm.con(ABC_C_T + 3, slot), term5 = sm.con(ABC_C_T + 4, slot), term6 = sm.con(ABC_C_T + 5, slot);
+        const double factor = term0 + term1 + term2 + term3 + term4 + term5 + term6;
+        a += sm.con(ABC_C_M + c, slot) * factor;
+        a += sm.con(ABC_C_E78 + c, slot);
+    }
+    if (F.forces & 0x100) a += sm.con(ABC_C_GRPOT + c, slot);
+    if (F.forces & 0x80) a += sm.con(ABC_C_GRSIMPLE + c, slot);
+    if (F.forces & (0x01 | 0x02 | 0x04)) {
+        const int ast_num = E.n_ast;
+        if (F.forces & 0x04)
+            for (int k = 0; k < ast_num; k++) a -= sm.prod(AB_NPLANETS + k, c, slot);
+        if (F.forces & 0x02) {
+            a -= sm.prod(10, c, slot); a -= sm.prod(4, c, slot); a -= sm.prod(5, c, slot); a -= sm.prod(1, c, slot);
+            a -= sm.prod(9, c, slot); a -= sm.prod(8, c, slot); a -= sm.prod(3, c, slot); a -= sm.prod(2, c, slot);
+            a -= sm.prod(7, c, slot); a -= sm.prod(6, c, slot);
+        }
+        if (F.forces & 0x01) a -= sm.prod(0, c, slot);
+    }
+    return a;
+}
+
+/* ab_predict for one component held in registers */
+__device__ __forceinline__ void abc_predict(const AbcComp& s, int nn, double dt, double& xk_out, double& vk_out) {
+    const double h = c_h[nn];
+    const double b0 = s.b[0], b1 = s.b[1], b2 = s.b[2], b3 = s.b[3], b4 = s.b[4], b5 = s.b[5], b6 = s.b[6];
+    const double x0 = s.x0, v0 = s.v0, a0 = s.a0, csx = s.csx, csv = s.csv;
+    double px = AB_DIVK(b6 * 7. * h, 9.) + b5;
+    px = px * 3. * h / 4. + b4;
+    px = AB_DIVK(px * 5. * h, 7.) + b3;
+    px = AB_DIVK(px * 2. * h, 3.) + b2;
+    px = AB_DIVK(px * 3. * h, 5.) + b1;
+    px = px * h / 2. + b0;
+    px = AB_DIVK(px * h, 3.) + a0;
+    px = px * dt * h / 2. + v0;
+    const double xk = -csx + px * dt * h;
+    xk_out = xk + x0;
+    double pv = b6 * 7. * h / 8. + b5;
+    pv = AB_DIVK(pv * 6. * h, 7.) + b4;
+    pv = AB_DIVK(pv * 5. * h, 6.) + b3;
+    pv = AB_DIVK(pv * 4. * h, 5.) + b2;
+    pv = pv * 3. * h / 4. + b1;
+    pv = AB_DIVK(pv * 2. * h, 3.) + b0;
+    pv = pv * h / 2. + a0;
+    const double vk = -csv + pv * dt * h;
+    vk_out = vk + v0;
+}
+
+#define ABC_DIVRR(x, k) ab_divc((x), c_rr[k], c_rri[k])
+
+/* ab_update_gb for one component held in registers; returns |change of b6| at node 7 */
+__device__ __forceinline__ double abc_update_gb(AbcComp& s, int nn, double at) {
+    const double gk = at + (-s.a0);
+    double tmp = 0.0, gn;
+    switch (nn) {
+        case 1:
+            tmp = s.g[0];
+            gn = ABC_DIVRR(gk, 0);
+            s.g[0] = gn;
+            ab_add_cs(s.b[0], s.csb[0], gn - tmp);
+            break;
+        case 2:
+            tmp = s.g[1];
+            gn = ABC_DIVRR(ABC_DIVRR(gk, 1) - s.g[0], 2);
+            s.g[1] = gn;
+            tmp = gn - tmp;
+            ab_add_cs(s.b[0], s.csb[0], tmp * c_c[0]);
+            ab_add_cs(s.b[1], s.csb[1], tmp);
+            break;
+        case 3:
+            tmp = s.g[2];
+            gn = ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(gk, 3) - s.g[0], 4) - s.g[1], 5);
+            s.g[2] = gn;
+            tmp = gn - tmp;
+            ab_add_cs(s.b[0], s.csb[0], tmp * c_c[1]);
+            ab_add_cs(s.b[1], s.csb[1], tmp * c_c[2]);
+            ab_add_cs(s.b[2], s.csb[2], tmp);
+            break;
+        case 4:
+            tmp = s.g[3];
+            gn = ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(gk, 6) - s.g[0], 7) - s.g[1], 8) - s.g[2], 9);
+            s.g[3] = gn;
+            tmp = gn - tmp;
+            ab_add_cs(s.b[0], s.csb[0], tmp * c_c[3]);
+            ab_add_cs(s.b[1], s.csb[1], tmp * c_c[4]);
+            ab_add_cs(s.b[2], s.csb[2], tmp * c_c[5]);
+            ab_add_cs(s.b[3], s.csb[3], tmp);
+            break;
+        case 5:
+            tmp = s.g[4];
+            gn = ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(gk, 10) - s.g[0], 11) - s.g[1], 12) - s.g[2], 13) - s.g[3], 14);
+            s.g[4] = gn;
+            tmp = gn - tmp;
+            ab_add_cs(s.b[0], s.csb[0], tmp * c_c[6]);
+            ab_add_cs(s.b[1], s.csb[1], tmp * c_c[7]);
+            ab_add_cs(s.b[2], s.csb[2], tmp * c_c[8]);
+            ab_add_cs(s.b[3], s.csb[3], tmp * c_c[9]);
+            ab_add_cs(s.b[4], s.csb[4], tmp);
+            break;
+        case 6:
+            tmp = s.g[5];
+            gn = ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(gk, 15) - s.g[0], 16) - s.g[1], 17) - s.g[2], 18) - s.g[3], 19) - s.g[4], 20);
+            s.g[5] = gn;
+            tmp = gn - tmp;
+            ab_add_cs(s.b[0], s.csb[0], tmp * c_c[10]);
+            ab_add_cs(s.b[1], s.csb[1], tmp * c_c[11]);
+            ab_add_cs(s.b[2], s.csb[2], tmp * c_c[12]);
+            ab_add_cs(s.b[3], s.csb[3], tmp * c_c[13]);
+            ab_add_cs(s.b[4], s.csb[4], tmp * c_c[14]);
+            ab_add_cs(s.b[5], s.csb[5], tmp);
+            break;
+        default:
+            tmp = s.g[6];
+            gn = ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(ABC_DIVRR(gk, 21) - s.g[0], 22) - s.g[1], 23) - s.g[2], 24) - s.g[3], 25) - s.g[4], 26) - s.g[5], 27);
+            s.g[6] = gn;
+            tmp = gn - tmp;
+            ab_add_cs(s.b[0], s.csb[0], tmp * c_c[15]);
+            ab_add_cs(s.b[1], s.csb[1], tmp * c_c[16]);
+            ab_add_cs(s.b[2], s.csb[2], tmp * c_c[17]);
+            ab_add_cs(s.b[3], s.csb[3], tmp * c_c[18]);
+            ab_add_cs(s.b[4], s.csb[4], tmp * c_c[19]);
+            ab_add_cs(s.b[5], s.csb[5], tmp * c_c[20]);
+            ab_add_cs(s.b[6], s.csb[6], tmp);
+            break;
+    }
+    return fabs(tmp);
+}
+
+/* ab_attempt_begin for one component */
+__device__ __forceinline__ void abc_attempt_begin(AbcComp& s) {
+    s.x0 = s.pos; s.v0 = s.vel; s.a0 = s.acc;
+    const double b0 = s.b[0], b1 = s.b[1], b2 = s.b[2], b3 = s.b[3], b4 = s.b[4], b5 = s.b[5], b6 = s.b[6];
+    for (int j = 0; j < 7; j++) s.csb[j] = 0.;
+    s.g[0] = b6 * c_d[15] + b5 * c_d[10] + b4 * c_d[6] + b3 * c_d[3] + b2 * c_d[1] + b1 * c_d[0] + b0;
+    s.g[1] = b6 * c_d[16] + b5 * c_d[11] + b4 * c_d[7] + b3 * c_d[4] + b2 * c_d[2] + b1;
+    s.g[2] = b6 * c_d[17] + b5 * c_d[12] + b4 * c_d[8] + b3 * c_d[5] + b2;
+    s.g[3] = b6 * c_d[18] + b5 * c_d[13] + b4 * c_d[9] + b3;
+    s.g[4] = b6 * c_d[19] + b5 * c_d[14] + b4;
+    s.g[5] = b6 * c_d[20] + b5;
+    s.g[6] = b6;
+}
+
+/* ab_predict_next for one component: (se, sb) -> s.e, s.b */
+__device__ __forceinline__ void abc_predict_next(AbcComp& s, double ratio, const double* se, const double* sb) {
+    if (ratio > 20.) {
+        for (int j = 0; j < 7; j++) { s.e[j] = 0.; s.b[j] = 0.; }
+        return;
+    }
+    const double q1 = ratio;
+    const double q2 = q1 * q1;
+    const double q3 = q1 * q2;
+    const double q4 = q2 * q2;
+    const double q5 = q2 * q3;
+    const double q6 = q3 * q3;
+    const double q7 = q3 * q4;
+    const double _b0 = sb[0], _b1 = sb[1], _b2 = sb[2], _b3 = sb[3], _b4 = sb[4], _b5 = sb[5], _b6 = sb[6];
+    const double be0 = _b0 - se[0];
+    const double be1 = _b1 - se[1];
+    const double be2 = _b2 - se[2];
+    const double be3 = _b3 - se[3];
+    const double be4 = _b4 - se[4];
+    const double be5 = _b5 - se[5];
+    const double be6 = _b6 - se[6];
+    const double e0 = q1 * (_b6 * 7.0 + _b5 * 6.0 + _b4 * 5.0 + _b3 * 4.0 + _b2 * 3.0 + _b1 * 2.0 + _b0);
+    const double e1 = q2 * (_b6 * 21.0 + _b5 * 15.0 + _b4 * 10.0 + _b3 * 6.0 + _b2 * 3.0 + _b1);
+    const double e2 = q3 * (_b6 * 35.0 + _b5 * 20.0 + _b4 * 10.0 + _b3 * 4.0 + _b2);
+    const double e3 = q4 * (_b6 * 35.0 + _b5 * 15.0 + _b4 * 5.0 + _b3);
+    const double e4 = q5 * (_b6 * 21.0 + _b5 * 6.0 + _b4);
+    const double e5 = q6 * (_b6 * 7.0 + _b5);
+    const double e6 = q7 * _b6;
+    s.e[0] = e0; s.e[1] = e1; s.e[2] = e2; s.e[3] = e3; s.e[4] = e4; s.e[5] = e5; s.e[6] = e6;
+    s.b[0] = e0 + be0; s.b[1] = e1 + be1; s.b[2] = e2 + be2; s.b[3] = e3 + be3;
+    s.b[4] = e4 + be4; s.b[5] = e5 + be5; s.b[6] = e6 + be6;
+}
+
+/* ab_advance for one component (x0, v0 with compensated sums; particles <- x0, v0) */
+__device__ __forceinline__ void abc_advance(AbcComp& s, double dt_done) {
+    const double b0 = s.b[0], b1 = s.b[1], b2 = s.b[2], b3 = s.b[3], b4 = s.b[4], b5 = s.b[5], b6 = s.b[6];
+    double x0 = s.x0, v0 = s.v0;
+    const double a0 = s.a0;
+    double csx = s.csx, csv = s.csv;
+    ab_add_cs(x0, csx, AB_DIVK(b6, 72.) * dt_done * dt_done);
+    ab_add_cs(x0, csx, AB_DIVK(b5, 56.) * dt_done * dt_done);
+    ab_add_cs(x0, csx, AB_DIVK(b4, 42.) * dt_done * dt_done);
+    ab_add_cs(x0, csx, AB_DIVK(b3, 30.) * dt_done * dt_done);
+    ab_add_cs(x0, csx, AB_DIVK(b2, 20.) * dt_done * dt_done);
+    ab_add_cs(x0, csx, AB_DIVK(b1, 12.) * dt_done * dt_done);
+    ab_add_cs(x0, csx, AB_DIVK(b0, 6.) * dt_done * dt_done);
+    ab_add_cs(x0, csx, a0 / 2. * dt_done * dt_done);
+    ab_add_cs(x0, csx, v0 * dt_done);
+    ab_add_cs(v0, csv, b6 / 8. * dt_done);
+    ab_add_cs(v0, csv, AB_DIVK(b5, 7.) * dt_done);
+    ab_add_cs(v0, csv, AB_DIVK(b4, 6.) * dt_done);
+    ab_add_cs(v0, csv, AB_DIVK(b3, 5.) * dt_done);
+    ab_add_cs(v0, csv, b2 / 4. * dt_done);
+    ab_add_cs(v0, csv, AB_DIVK(b1, 3.) * dt_done);
+    ab_add_cs(v0, csv, b0 / 2. * dt_done);
+    ab_add_cs(v0, csv, a0 * dt_done);
+    s.x0 = x0; s.v0 = v0; s.csx = csx; s.csv = csv;
+    s.pos = x0; s.vel = v0;
+}
+
+/* working-batch accessors: component k of the slot's system (C = 3: no variational particles) */
+#define ABC_W1(arr, k) (arr)[(long long)(k) * wn + ws]
+#define ABC_W7(arr, j, k) (arr)[((long long)(j) * 3 + (k)) * wn + ws]
+
+__device__ __forceinline__ void abc_comp_load(const AbBatch& W, long long ws, int c, AbcComp& s) {
+    const long long wn = W.n;
+    s.pos = ABC_W1(W.pos, c); s.vel = ABC_W1(W.vel, c); s.acc = ABC_W1(W.acc, c);
+    s.x0 = ABC_W1(W.x0, c); s.v0 = ABC_W1(W.v0, c); s.a0 = ABC_W1(W.a0, c);
+    s.csx = ABC_W1(W.csx, c); s.csv = ABC_W1(W.csv, c);
+    s.at = 0.0;
+    for (int j = 0; j < 7; j++) {
+        s.b[j] = ABC_W7(W.b, j, c); s.g[j] = ABC_W7(W.g, j, c); s.e[j] = ABC_W7(W.e, j, c); s.csb[j] = ABC_W7(W.csb, j, c);
+    }
+}
+
+__device__ __forceinline__ void abc_comp_store(const AbBatch& W, long long ws, int c, const AbcComp& s) {
+    const long long wn = W.n;
+    ABC_W1(W.pos, c) = s.pos; ABC_W1(W.vel, c) = s.vel; ABC_W1(W.acc, c) = s.acc;
+    ABC_W1(W.x0, c) = s.x0; ABC_W1(W.v0, c) = s.v0; ABC_W1(W.a0, c) = s.a0;
+    ABC_W1(W.csx, c) = s.csx; ABC_W1(W.csv, c) = s.csv;
+    for (int j = 0; j < 7; j++) {
+        ABC_W7(W.b, j, c) = s.b[j]; ABC_W7(W.g, j, c) = s.g[j]; ABC_W7(W.e, j, c) = s.e[j]; ABC_W7(W.csb, j, c) = s.csb[j];
+    }
+}
+
+}  // namespace AB_NS
+#endif

@@ -154,4 +154,29 @@ struct AbShared {
     int err_status;                           /* first ASSIST_STATUS error seen */
 };
 
+/* ---- pp_coop_kernel (coop_device.cuh): CTA geometry and the launch-time plan of its worker warps ---- */
+#define ABC_SLOTS 32
+#define ABC_WARPS 16
+#define ABC_THREADS (ABC_WARPS * 32)
+#define ABC_CTRL_WARP 3
+#define ABC_FIRST_WORKER 4
+#define ABC_NWORK (ABC_WARPS - ABC_FIRST_WORKER)
+#define ABC_MAX_TASKS 4          /* tasks per worker warp */
+
+/* task kinds of the workers */
+#define ABC_T_BODY0 0            /* 0..26: body index */
+#define ABC_T_EARTHJ 27
+#define ABC_T_SUNJ2 28
+#define ABC_T_NG 29
+#define ABC_T_GRPOT 30
+#define ABC_T_GRSIMPLE 31
+#define ABC_T_NONE 255
+
+/* launch-time plan of the worker warps */
+struct AbcPlan {
+    unsigned char task[ABC_NWORK][ABC_MAX_TASKS];
+    int ast_split;            /* fill: asteroids [0, ast_split) are evaluated with the planets' half */
+    long long attempt_budget; /* step attempts per system and call before it is retired with an error; <= 0: none */
+};
+
 #endif

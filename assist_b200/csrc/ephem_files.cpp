@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include "assist_ephem_files.h"
+#include "host_internal.h"
 #include "assist_gpu.h"
 
 namespace {
@@ -102,6 +103,8 @@ int assist_spk_free(struct spk_s* pl) {
             cudaSetDevice(cur);
         }
     }
+    ab_spk_desc_free(pl->b200_host_desc);
+    pl->b200_host_desc = NULL;
     if (pl->targets) {
         for (int m = 0; m < pl->num; m++) { free(pl->targets[m].one); free(pl->targets[m].two); }
         free(pl->targets);

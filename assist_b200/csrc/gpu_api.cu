@@ -3,6 +3,7 @@
  * and kernel launches.  No physics here; the kernels are in kernels.cu.
  */
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <atomic>
 #include <vector>
 #include <math.h>
@@ -68,6 +69,7 @@ static int ensure_device(int* dev_out) {
         CU(ab_upload_constants_strict_tu2()); CU(ab_upload_constants_strict_tu3());
         CU(ab_upload_constants_fast_tu0()); CU(ab_upload_constants_fast_tu1());
         CU(ab_upload_constants_fast_tu2()); CU(ab_upload_constants_fast_tu3());
+        CU(ab_upload_constants_strict_tu4()); CU(ab_upload_constants_fast_tu4());
         g_const_uploaded[dev] = true;
     }
     *dev_out = dev;
@@ -224,11 +226,39 @@ static int fill_target(AbSpkTarget* d, const struct spk_target* t, const struct 
     return 0;
 }
 
-/* Build the kernel-parameter view of an ephemeris on the current device. */
-static int build_ephem(const struct assist_ephem* e, AbEphem* E) {
-    int dev;
-    int rc = ensure_device(&dev);
-    if (rc) return rc;
+/* Per-file cache (struct spk_s::b200_host_desc): where each segment lies in the packed copy and the segment
+ * descriptors.  Building them walks every record of the file once (the uniform-RADIUS check), so it is done
+ * once per file, not once per call. */
+struct AbSpkDesc {
+    std::vector<long long> off;
+    size_t words = 0;
+    std::vector<AbSpkTarget> tg;                                   /* masses are refreshed by the caller */
+    std::vector<double> host_copy;                                 /* packed copy on the host (emulation hook only) */
+    std::vector<double> dev_mass[ASSIST_B200_MAX_DEVICES];         /* masses last sent with the device descriptors */
+};
+
+extern "C" void ab_spk_desc_free(void* desc) { delete (AbSpkDesc*)desc; }
+
+static int spk_desc(struct spk_s* f, AbSpkDesc** out) {
+    if (f->b200_host_desc) { *out = (AbSpkDesc*)f->b200_host_desc; return 0; }
+    AbSpkDesc* d = new AbSpkDesc();
+    int rc = spk_layout(f, d->off, &d->words);
+    if (!rc) {
+        d->tg.resize((size_t)f->num);
+        for (int m = 0; m < f->num && !rc; m++) rc = fill_target(&d->tg[m], &f->targets[m], f, &d->off[(size_t)m * AB_MAXSEG]);
+    }
+    if (rc) { delete d; return rc; }
+    f->b200_host_desc = d;
+    *out = d;
+    return 0;
+}
+
+/* Build the kernel-parameter view of an ephemeris: on the current device, or (host_mode) with HOST pointers
+ * to the same packed tables -- what the CPU emulation of the kernels in tests/emul reads. */
+static int build_ephem_impl(const struct assist_ephem* e, AbEphem* E, bool host_mode) {
+    int dev = 0;
+    int rc;
+    if (!host_mode) { rc = ensure_device(&dev); if (rc) return rc; }
     if (e == NULL) return set_err(ASSIST_GPU_ERR_ARG, "ephem is NULL");
     memset(E, 0, sizeof(*E));
     E->jd_ref = e->jd_ref;
@@ -239,8 +269,12 @@ static int build_ephem(const struct assist_ephem* e, AbEphem* E) {
     E->emb_index = -1;
     if (e->ascii_planets) {
         struct ascii_s* a = e->ascii_planets;
-        if ((rc = upload_image(&a->b200_dev_image[dev], a->map, a->len))) return rc;
-        E->ascii_img = (const double*)a->b200_dev_image[dev];
+        if (host_mode) {
+            E->ascii_img = (const double*)a->map;
+        } else {
+            if ((rc = upload_image(&a->b200_dev_image[dev], a->map, a->len))) return rc;
+            E->ascii_img = (const double*)a->b200_dev_image[dev];
+        }
         E->a_beg = a->beg; E->a_end = a->end; E->a_inc = a->inc; E->a_cau = a->cau; E->a_cem = a->cem;
         E->a_inc_rd = 1.0 / a->inc;
         E->a_f_earth = -1.0 / (1.0 + a->cem);
@@ -255,20 +289,26 @@ static int build_ephem(const struct assist_ephem* e, AbEphem* E) {
         for (int k = 0; k < AB_NPLANETS; k++) E->a_mass[k] = a->mass[k];
     } else if (e->spk_planets) {
         struct spk_s* pl = e->spk_planets;
-        std::vector<long long> poff;
-        size_t pwords = 0;
-        if ((rc = spk_layout(pl, poff, &pwords))) return rc;
-        if ((rc = upload_packed_spk(&pl->b200_dev_image[dev], pl, poff, pwords))) return rc;
-        E->spkp_img = (const double*)pl->b200_dev_image[dev];
+        if (pl->num > AB_MAX_PTGT)
+            return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "planet kernel has %d targets (max %d)", pl->num, AB_MAX_PTGT);
+        AbSpkDesc* pd = nullptr;
+        if ((rc = spk_desc(pl, &pd))) return rc;
+        if (host_mode) {
+            if (pd->host_copy.empty()) { pd->host_copy.assign(pd->words, 0.0); pack_spk(pl, pd->off, pd->host_copy); }
+            E->spkp_img = pd->host_copy.data();
+        } else {
+            if ((rc = upload_packed_spk(&pl->b200_dev_image[dev], pl, pd->off, pd->words))) return rc;
+            E->spkp_img = (const double*)pl->b200_dev_image[dev];
+        }
         {
             const double au = e->AU, seconds_per_day = 86400.;
             E->u_d[0] = au; E->u_d[1] = au / seconds_per_day; E->u_d[2] = au / (seconds_per_day * seconds_per_day);
         }
-        if (pl->num > AB_MAX_PTGT)
-            return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "planet kernel has %d targets (max %d)", pl->num, AB_MAX_PTGT);
         E->n_ptgt = pl->num;
-        for (int m = 0; m < pl->num; m++)
-            if ((rc = fill_target(&E->p_tgt[m], &pl->targets[m], pl, &poff[(size_t)m * AB_MAXSEG]))) return rc;
+        for (int m = 0; m < pl->num; m++) {
+            E->p_tgt[m] = pd->tg[m];
+            E->p_tgt[m].mass = pl->targets[m].mass;        /* masses can be joined after the first build */
+        }
         static const int naif_by_assist[AB_NPLANETS] = {10, 1, 2, 399, 301, 4, 5, 6, 7, 8, 9};
         for (int k = 0; k < AB_NPLANETS; k++) {
             /* precomputed index when it is consistent, else a search by NAIF code (reference src/spk.c:646-659) */
@@ -293,19 +333,29 @@ static int build_ephem(const struct assist_ephem* e, AbEphem* E) {
         struct spk_s* sb = e->spk_asteroids;
         if (sb->num > AB_MAX_AST)
             return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "small-body kernel has %d targets (max %d in this build)", sb->num, AB_MAX_AST);
-        std::vector<long long> aoff;
-        size_t awords = 0;
-        if ((rc = spk_layout(sb, aoff, &awords))) return rc;
-        if ((rc = upload_packed_spk(&sb->b200_dev_image[dev], sb, aoff, awords))) return rc;
-        E->spka_img = (const double*)sb->b200_dev_image[dev];
+        AbSpkDesc* ad = nullptr;
+        if ((rc = spk_desc(sb, &ad))) return rc;
+        for (int m = 0; m < sb->num; m++) ad->tg[m].mass = sb->targets[m].mass;
         E->n_ast = sb->num;
-        AbSpkTarget tg[AB_MAX_AST];
-        for (int m = 0; m < sb->num; m++)
-            if ((rc = fill_target(&tg[m], &sb->targets[m], sb, &aoff[(size_t)m * AB_MAXSEG]))) return rc;
-        if (!sb->b200_dev_targets[dev]) CU(cudaMalloc(&sb->b200_dev_targets[dev], sizeof(AbSpkTarget) * AB_MAX_AST));
-        /* descriptors carry the (joinable) masses, so they are refreshed on every build */
-        CU(cudaMemcpy(sb->b200_dev_targets[dev], tg, sizeof(AbSpkTarget) * sb->num, cudaMemcpyHostToDevice));
-        E->a_tgt = (const AbSpkTarget*)sb->b200_dev_targets[dev];
+        if (host_mode) {
+            if (ad->host_copy.empty()) { ad->host_copy.assign(ad->words, 0.0); pack_spk(sb, ad->off, ad->host_copy); }
+            E->spka_img = ad->host_copy.data();
+            E->a_tgt = ad->tg.data();
+        } else {
+            if ((rc = upload_packed_spk(&sb->b200_dev_image[dev], sb, ad->off, ad->words))) return rc;
+            E->spka_img = (const double*)sb->b200_dev_image[dev];
+            /* the descriptors carry the (joinable) masses: sent again only when a mass has changed */
+            std::vector<double>& sent = ad->dev_mass[dev];
+            bool same = sb->b200_dev_targets[dev] != nullptr && sent.size() == (size_t)sb->num;
+            for (int m = 0; same && m < sb->num; m++) same = (sent[m] == sb->targets[m].mass);
+            if (!same) {
+                if (!sb->b200_dev_targets[dev]) CU(cudaMalloc(&sb->b200_dev_targets[dev], sizeof(AbSpkTarget) * AB_MAX_AST));
+                CU(cudaMemcpy(sb->b200_dev_targets[dev], ad->tg.data(), sizeof(AbSpkTarget) * sb->num, cudaMemcpyHostToDevice));
+                sent.resize((size_t)sb->num);
+                for (int m = 0; m < sb->num; m++) sent[m] = sb->targets[m].mass;
+            }
+            E->a_tgt = (const AbSpkTarget*)sb->b200_dev_targets[dev];
+        }
         for (int m = 0; m < sb->num; m++) E->gm[AB_NPLANETS + m] = sb->targets[m].mass;
     }
     for (int k = 0; k < AB_NPLANETS; k++) {
@@ -313,6 +363,15 @@ static int build_ephem(const struct assist_ephem* e, AbEphem* E) {
         else E->gm[k] = (E->p_index[k] >= 0) ? E->p_tgt[E->p_index[k]].mass : 0.0;   /* Earth-from-EMB fallback reports GM = 0 */
     }
     return 0;
+}
+
+static int build_ephem(const struct assist_ephem* e, AbEphem* E) { return build_ephem_impl(e, E, false); }
+
+/* Host-only test hook (no device needed): the kernel-parameter view with host pointers, plus the force options
+ * as the launches build them.  tests/emul runs the kernels' source on the CPU with these. */
+extern "C" int ab_gpu_build_ephem_host(const struct assist_ephem* e, void* E_out, size_t E_bytes) {
+    if (E_bytes != sizeof(AbEphem)) return set_err(ASSIST_GPU_ERR_ARG, "AbEphem is %zu bytes, caller expects %zu", sizeof(AbEphem), E_bytes);
+    return build_ephem_impl(e, (AbEphem*)E_out, true);
 }
 
 static void build_force_opts(const struct assist_gpu_options* o, int has_params, AbForceOpts* F) {
@@ -437,7 +496,12 @@ struct assist_gpu_batch {
     int* d_slice_epoch;     /* [n] next output epoch per system */
     double* d_trange;       /* [2] min / max of the systems' times */
     double slice_days;      /* length of a time slice; 0: one slice */
-    int sched_queue;        /* 1: work-queue kernel (default), 0: capped launches + straggler packing */
+    int sched_queue;        /* 1: work-queue kernel, 0: capped launches + straggler packing */
+    int sched_coop;         /* 1 (default): pp_coop_kernel wherever it applies (no variational particles, one EIH source, barycentric) */
+    AbBatch wc;             /* working slots of pp_coop_kernel: 32 per CTA */
+    char* wcblock;
+    int coop_grid;
+    long long attempt_budget; /* step attempts per system and call (pp_coop_kernel); <= 0: unlimited */
     int* d_active[2];       /* ping-pong lists of systems still integrating */
     int* d_count;           /* length of the list being built */
     long long step_cap;     /* accepted steps per system per launch (per-particle mode) */
@@ -543,6 +607,9 @@ extern "C" assist_gpu_batch* assist_gpu_batch_create(const struct assist_ephem* 
     {
         const char* sc = getenv("ASSIST_B200_SCHED");
         b->sched_queue = !(sc && !strcmp(sc, "capped"));
+        b->sched_coop = !(sc && (!strcmp(sc, "capped") || !strcmp(sc, "queue")));
+        const char* ab = getenv("ASSIST_B200_ATTEMPT_BUDGET");
+        b->attempt_budget = ab ? atoll(ab) : 50000000LL;
         const char* sd = getenv("ASSIST_B200_SLICE_DAYS");
         b->slice_days = sd ? atof(sd) : AB_DEFAULT_SLICE_DAYS;
         if (!(b->slice_days >= 0.0)) b->slice_days = 0.0;
@@ -573,6 +640,7 @@ extern "C" void assist_gpu_batch_free(assist_gpu_batch* b) {
     if (!b) return;
     cudaFree(b->block); cudaFree(b->snapshot); cudaFree(b->d_stage); cudaFree(b->d_stage_prm); cudaFree(b->d_out);
     cudaFree(b->d_active[0]); cudaFree(b->d_active[1]); cudaFree(b->d_count);
+    cudaFree(b->wcblock);
     cudaFree(b->wblock); cudaFree(b->d_queue); cudaFree(b->d_slice_done); cudaFree(b->d_slice_epoch); cudaFree(b->d_trange);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -767,12 +835,102 @@ static int ensure_working_batch(assist_gpu_batch* b) {
         CU(cudaMalloc((void**)&b->wblock, batch_bytes(slots, b->C)));
         CU(cudaMemset(b->wblock, 0, batch_bytes(slots, b->C)));
         layout_batch(b->w, b->wblock, slots, b->K, b->mode);
-        CU(cudaMalloc((void**)&b->d_queue, sizeof(unsigned long long)));
-        CU(cudaMalloc((void**)&b->d_slice_done, sizeof(int) * (size_t)b->n));
-        CU(cudaMalloc((void**)&b->d_slice_epoch, sizeof(int) * (size_t)b->n));
-        CU(cudaMalloc((void**)&b->d_trange, sizeof(double) * 2));
+        if (!b->d_queue) CU(cudaMalloc((void**)&b->d_queue, sizeof(unsigned long long)));
+        if (!b->d_slice_done) CU(cudaMalloc((void**)&b->d_slice_done, sizeof(int) * (size_t)b->n));
+        if (!b->d_slice_epoch) CU(cudaMalloc((void**)&b->d_slice_epoch, sizeof(int) * (size_t)b->n));
+        if (!b->d_trange) CU(cudaMalloc((void**)&b->d_trange, sizeof(double) * 2));
     }
     b->w.epsilon = b->d.epsilon; b->w.min_dt = b->d.min_dt; b->w.has_params = b->d.has_params;
+    return 0;
+}
+
+
+/* ---- pp_coop_kernel: who runs it, its working slots and the plan of its worker warps ---- */
+
+static bool coop_applies(const assist_gpu_batch* b, const AbForceOpts& F) {
+    return b->sched_coop && b->mode == ASSIST_GPU_PER_PARTICLE && b->K == 1 && F.gr_eih_sources == 1 && !F.geocentric;
+}
+
+/* Spread the force terms over the worker warps: longest task first onto the least loaded warp.  The weights
+ * are rough FP64 instruction counts of the strict build. */
+static void build_coop_plan(const AbEphem& E, const AbForceOpts& F, long long budget, AbcPlan* plan) {
+    struct Task { int kind; int cost; };
+    std::vector<Task> tasks;
+    const int nb = AB_NPLANETS + E.n_ast;
+    const bool eih = (F.forces & 0x40) != 0;
+    for (int i = 0; i < nb; i++) {
+        int cost = 66;
+        if (i < AB_NPLANETS && eih) cost += 26;
+        if (i == 0 && eih) cost += 250;
+        tasks.push_back({ABC_T_BODY0 + i, cost});
+    }
+    if (F.forces & 0x10) tasks.push_back({ABC_T_EARTHJ, 250});
+    if (F.forces & 0x20) tasks.push_back({ABC_T_SUNJ2, 150});
+    if ((F.forces & 0x08) && F.has_params) tasks.push_back({ABC_T_NG, 700});
+    if (F.forces & 0x100) tasks.push_back({ABC_T_GRPOT, 80});
+    if (F.forces & 0x80) tasks.push_back({ABC_T_GRSIMPLE, 100});
+    std::sort(tasks.begin(), tasks.end(), [](const Task& a, const Task& b) { return a.cost > b.cost; });
+    int load[ABC_NWORK] = {0}, cnt[ABC_NWORK] = {0};
+    memset(plan->task, ABC_T_NONE, sizeof(plan->task));
+    for (const Task& t : tasks) {
+        int best = -1;
+        for (int w = 0; w < ABC_NWORK; w++)
+            if (cnt[w] < ABC_MAX_TASKS && (best < 0 || load[w] < load[best])) best = w;
+        plan->task[best][cnt[best]++] = (unsigned char)t.kind;      /* 12 x 4 slots >= 32 tasks: always room */
+        load[best] += t.cost;
+    }
+    /* fill: half of the threads take the planets and the first asteroids, the other half the remaining asteroids */
+    int split = E.n_ast / 4;
+    const char* sp = getenv("ASSIST_B200_AST_SPLIT");
+    if (sp) split = atoi(sp);
+    if (split < 0) split = 0;
+    if (split > E.n_ast) split = E.n_ast;
+    plan->ast_split = split;
+    plan->attempt_budget = budget;
+}
+
+static int ensure_coop_batch(assist_gpu_batch* b, bool fast) {
+    if (!b->wcblock) {
+        int g1 = 0, g2 = 0;
+        cudaError_t eo = ab_pp_coop_max_grid_strict(&g1);
+        if (eo != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "pp_coop occupancy query failed: %s", cudaGetErrorString(eo));
+        eo = ab_pp_coop_max_grid_fast(&g2);
+        if (eo != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "pp_coop occupancy query failed: %s", cudaGetErrorString(eo));
+        int grid = g1 < g2 ? g1 : g2;
+        const int need = (b->n + ABC_SLOTS - 1) / ABC_SLOTS;
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        b->coop_grid = grid;
+        const size_t slots = (size_t)grid * ABC_SLOTS;
+        CU(cudaMalloc((void**)&b->wcblock, batch_bytes(slots, b->C)));
+        CU(cudaMemset(b->wcblock, 0, batch_bytes(slots, b->C)));
+        layout_batch(b->wc, b->wcblock, slots, b->K, b->mode);
+        if (!b->d_queue) CU(cudaMalloc((void**)&b->d_queue, sizeof(unsigned long long)));
+        if (!b->d_slice_done) CU(cudaMalloc((void**)&b->d_slice_done, sizeof(int) * (size_t)b->n));
+        if (!b->d_slice_epoch) CU(cudaMalloc((void**)&b->d_slice_epoch, sizeof(int) * (size_t)b->n));
+        if (!b->d_trange) CU(cudaMalloc((void**)&b->d_trange, sizeof(double) * 2));
+    }
+    (void)fast;
+    b->wc.epsilon = b->d.epsilon; b->wc.min_dt = b->d.min_dt; b->wc.has_params = b->d.has_params;
+    return 0;
+}
+
+
+/* Host-only test hooks for tests/emul (no device needed): the launch-time structures exactly as the launches build them. */
+extern "C" int ab_gpu_build_force_opts_host(const struct assist_gpu_options* o, int has_params, void* F_out, size_t F_bytes) {
+    if (F_bytes != sizeof(AbForceOpts)) return set_err(ASSIST_GPU_ERR_ARG, "AbForceOpts size mismatch");
+    build_force_opts(o, has_params, (AbForceOpts*)F_out);
+    return 0;
+}
+extern "C" int ab_gpu_build_coop_plan_host(const void* E, const void* F, long long budget, void* plan_out, size_t plan_bytes) {
+    if (plan_bytes != sizeof(AbcPlan)) return set_err(ASSIST_GPU_ERR_ARG, "AbcPlan size mismatch");
+    build_coop_plan(*(const AbEphem*)E, *(const AbForceOpts*)F, budget, (AbcPlan*)plan_out);
+    return 0;
+}
+extern "C" size_t ab_gpu_batch_bytes_host(size_t n, size_t C) { return batch_bytes(n, C); }
+extern "C" int ab_gpu_layout_batch_host(void* d, size_t d_bytes, char* block, size_t n, int K, int mode) {
+    if (d_bytes != sizeof(AbBatch)) return set_err(ASSIST_GPU_ERR_ARG, "AbBatch size mismatch");
+    layout_batch(*(AbBatch*)d, block, n, K, mode);
     return 0;
 }
 
@@ -791,6 +949,24 @@ extern "C" int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int 
          * whose integrate() has not returned are then packed into a dense list and relaunched.  This
          * keeps the lanes of a warp busy although step counts differ by 10x between particles. */
         const bool k1 = (b->K == 1);
+        if (coop_applies(b, F)) {
+            /* a CTA per 32 systems, working set on chip (coop_device.cuh) */
+            rc = ensure_coop_batch(b, fast);
+            if (rc) return rc;
+            AbSlices SL;
+            const double keep = b->slice_days;
+            if (!getenv("ASSIST_B200_SLICE_DAYS")) b->slice_days = 0.0;      /* whole systems: a system is ~30 us per step here, no tail to cut */
+            rc = build_slices(b, E, t_end, &SL);
+            b->slice_days = keep;
+            if (rc) return rc;
+            AbcPlan plan;
+            build_coop_plan(E, F, b->attempt_budget, &plan);
+            CU(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), 0));
+            CU(cudaEventRecord(b->ev0, 0));
+            e = fast ? ab_launch_pp_coop_fast(E, F, b->d, b->wc, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, &plan, b->coop_grid, 0)
+                     : ab_launch_pp_coop_strict(E, F, b->d, b->wc, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, &plan, b->coop_grid, 0);
+            return finish_launch(b, e, "pp_coop");
+        }
         if (b->sched_queue) {
             /* work-queue scheduling: a resident grid of threads pulls systems until the queue is empty */
             rc = ensure_working_batch(b);
@@ -878,7 +1054,27 @@ extern "C" int assist_gpu_batch_integrate_or_interpolate(assist_gpu_batch* b, co
     CU(cudaMemsetAsync(b->d_out, 0xFF, out_bytes, 0));
     const bool fastm = (b->opt.math == ASSIST_GPU_MATH_FAST);
     cudaError_t e;
-    if (b->sched_queue) {
+    if (coop_applies(b, F)) {
+        rc = ensure_coop_batch(b, fastm);
+        if (rc) return rc;
+        bool mono = true;
+        const double dir = (n_times > 1) ? (times[n_times - 1] - times[0]) : 0.0;
+        for (int q = 1; q < n_times; q++)
+            if ((times[q] - times[q - 1]) * dir < 0.0 || !(times[q] == times[q])) mono = false;
+        AbSlices SL;
+        const double keep = b->slice_days;
+        if (!mono || !getenv("ASSIST_B200_SLICE_DAYS")) b->slice_days = 0.0;
+        rc = build_slices(b, E, times[n_times - 1], &SL);
+        b->slice_days = keep;
+        if (rc) return rc;
+        if (SL.n_win > 1 && n_times > 1 && SL.wlen * dir < 0.0) SL.n_win = 1;
+        AbcPlan plan;
+        build_coop_plan(E, F, b->attempt_budget, &plan);
+        CU(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), 0));
+        CU(cudaEventRecord(b->ev0, 0));
+        e = fastm ? ab_launch_pp_coop_fast(E, F, b->d, b->wc, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, &plan, b->coop_grid, 0)
+                  : ab_launch_pp_coop_strict(E, F, b->d, b->wc, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, &plan, b->coop_grid, 0);
+    } else if (b->sched_queue) {
         rc = ensure_working_batch(b);
         if (rc) return rc;
         /* slices need epochs that run in one direction; anything else is one slice */

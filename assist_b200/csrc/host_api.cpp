@@ -44,8 +44,9 @@ const char* assist_error_messages[] = {
     "The requested planet ID has not been found.",
     "The requested time is outside the coverage provided by the ephemeris file.",
     "No usable CUDA device: assist-b200 evaluates everything on the GPU and has no CPU path.",
+    "The integration cannot advance: the timestep is zero or the particle exceeded its step budget.",
 };
-const int assist_error_messages_N = 7;
+const int assist_error_messages_N = 8;
 
 /* ---- format detection and discovery (reference src/assist.c:66-154) ------ */
 

@@ -24,6 +24,8 @@ void ab_host_pre_timestep_marker(struct reb_simulation* r);
 int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int exact_finish_time, long max_steps, int flags);
 int ab_gpu_batch_update_params(assist_gpu_batch* b, const double* params);
 int ab_gpu_batch_get_last_state(assist_gpu_batch* b, double* state, double* acc);
+/* frees the cached descriptor block of an SPK file (struct spk_s::b200_host_desc) */
+void ab_spk_desc_free(void* desc);
 
 #ifdef __cplusplus
 }

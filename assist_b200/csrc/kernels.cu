@@ -6,6 +6,7 @@
  *   -DAB_TU=1  pp_* kernels for systems without variational particles (state in registers)
  *   -DAB_TU=2  pp_* kernels for systems with up to AB_NVMAX variational particles
  *   -DAB_TU=3  sh_* kernels: shared-step IAS15 (persistent cooperative kernel) + dense output
+ *   -DAB_TU=4  pp_coop_kernel: per-particle IAS15, a CTA steps 32 systems together with their working set on chip
  * The launchers at the bottom are what gpu_api.cu calls.
  */
 #include <cuda_runtime.h>
@@ -32,6 +33,10 @@
 #include "ephem_device.cuh"
 #include "forces_device.cuh"
 #include "ias15_device.cuh"
+#include "pp_common.cuh"
+#if AB_TU == 4
+#include "coop_roles.cuh"
+#endif
 #include "launchers.h"
 
 namespace AB_NS {
@@ -115,12 +120,6 @@ __global__ void force_eval_kernel(const __grid_constant__ AbEphem E, const __gri
 #else
 #define PP_KM AB_KMAX
 #endif
-
-struct PPState {
-    double t, dt, dt_last, last_full_dt;
-    int status;
-    unsigned long long steps, rejected, iters, evals;
-};
 
 /* One reb_simulation_step of system i: force evaluation at the current state, then
  * IAS15 attempts until one is accepted.  Each thread owns its times, so the body
@@ -285,16 +284,6 @@ __device__ bool pp_integrate_to(const AbEphem& E, const AbForceOpts& F, const Ab
     return true;
 }
 
-__device__ __forceinline__ void pp_load(const AbBatch& Bt, long long i, PPState& P) {
-    P.t = Bt.t[i]; P.dt = Bt.dt[i]; P.dt_last = Bt.dt_last[i]; P.last_full_dt = Bt.last_full_dt[i]; P.status = Bt.status[i];
-    P.steps = Bt.steps[i]; P.rejected = Bt.rejected[i]; P.iters = Bt.iters[i]; P.evals = Bt.evals[i];
-}
-__device__ __forceinline__ void pp_store(const AbBatch& Bt, long long i, const PPState& P) {
-    Bt.t[i] = P.t; Bt.dt[i] = P.dt; Bt.dt_last[i] = P.dt_last; Bt.last_full_dt[i] = P.last_full_dt;
-    if (Bt.status[i] < 1000) Bt.status[i] = P.status;
-    Bt.steps[i] = P.steps; Bt.rejected[i] = P.rejected; Bt.iters[i] = P.iters; Bt.evals[i] = P.evals;
-}
-
 #ifndef AB_PP_BLOCK
 #define AB_PP_BLOCK 128
 #endif
@@ -346,81 +335,6 @@ pp_integrate_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ A
         }
     }
     if (owns) pp_store(Bt, i, P);
-}
-
-/* Move one system between the population arrays (index `i`, stride src.n) and a working slot
- * (index `s`, stride dst.n): 54 * C doubles.  CG: the source is read past L1 (another SM may have
- * written it earlier in the same launch: time slices of one system run on whatever thread is free). */
-template <bool CG>
-__device__ __forceinline__ double pp_ld(const double* p) { return CG ? __ldcg(p) : *p; }
-
-template <bool CG>
-__device__ void pp_copy_system(const AbBatch& src, long long i, const AbBatch& dst, long long s, int nv) {
-    const long long ns = src.n, nd = dst.n;
-    const int C = src.C;
-    const int Ca = 3 * (1 + nv);
-    double* const s1[12] = {src.pos, src.vel, src.acc, src.x0, src.v0, src.a0, src.csx, src.csv, src.ls_pos, src.ls_vel, src.ls_acc, src.prm};
-    double* const d1[12] = {dst.pos, dst.vel, dst.acc, dst.x0, dst.v0, dst.a0, dst.csx, dst.csv, dst.ls_pos, dst.ls_vel, dst.ls_acc, dst.prm};
-    double* const s7[6] = {src.b, src.g, src.e, src.csb, src.br, src.er};
-    double* const d7[6] = {dst.b, dst.g, dst.e, dst.csb, dst.br, dst.er};
-    /* a body (3 components) at a time: 36 / 21 independent loads before the stores, so that the trips to L2 overlap */
-    for (int k0 = 0; k0 < Ca; k0 += 3) {
-        double tmp[12][3];
-#pragma unroll
-        for (int a = 0; a < 12; a++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) tmp[a][c] = pp_ld<CG>(s1[a] + (long long)(k0 + c) * ns + i);
-#pragma unroll
-        for (int a = 0; a < 12; a++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) d1[a][(long long)(k0 + c) * nd + s] = tmp[a][c];
-    }
-    for (int a = 0; a < 6; a++)
-        for (int k0 = 0; k0 < Ca; k0 += 3) {
-            double tmp[7][3];
-#pragma unroll
-            for (int j = 0; j < 7; j++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) tmp[j][c] = pp_ld<CG>(s7[a] + ((long long)j * C + k0 + c) * ns + i);
-#pragma unroll
-            for (int j = 0; j < 7; j++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) d7[a][((long long)j * C + k0 + c) * nd + s] = tmp[j][c];
-        }
-}
-
-__device__ __forceinline__ void pp_load_cg(const AbBatch& Bt, long long i, PPState& P) {
-    P.t = __ldcg(Bt.t + i); P.dt = __ldcg(Bt.dt + i); P.dt_last = __ldcg(Bt.dt_last + i); P.last_full_dt = __ldcg(Bt.last_full_dt + i);
-    P.status = __ldcg(Bt.status + i);
-    P.steps = __ldcg(Bt.steps + i); P.rejected = __ldcg(Bt.rejected + i); P.iters = __ldcg(Bt.iters + i); P.evals = __ldcg(Bt.evals + i);
-}
-
-/* State at one output epoch of assist_integrate_or_interpolate (reference src/assist.c:642-680, 556-597):
- * the system sits in slot `s` of W at time P.t, its last completed step was P.dt_last long. */
-__device__ void pp_emit(const AbBatch& W, long long s, int nv, const PPState& P, double t, double* __restrict__ o) {
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    const double h = 1.0 - (P.t - t) / P.dt_last;
-    if (P.status > 0) {
-        for (int q = 0; q < 6 * (1 + nv); q++) o[q] = nan;
-    } else if (P.t - t == 0.) {
-        for (int j = 0; j <= nv; j++)
-            for (int c = 0; c < 3; c++) {
-                o[6 * j + c] = W.pos[(long long)(3 * j + c) * W.n + s];
-                o[6 * j + 3 + c] = W.vel[(long long)(3 * j + c) * W.n + s];
-            }
-    } else if (h < 0.0 || h >= 1.0 || !ab_isnormal(h)) {
-        for (int q = 0; q < 6 * (1 + nv); q++) o[q] = nan;
-    } else {
-        ab_interpolate(W, s, nv, P.dt_last, h, o);
-    }
-}
-
-/* entry of reb_simulation_integrate(tmax) */
-__device__ __forceinline__ void pp_integrate_entry(PPState& P, double tmax) {
-    if (tmax != P.t) P.dt = copysign(P.dt, (tmax > P.t) ? 1.0 : -1.0);
-    P.last_full_dt = P.dt;
-    P.dt_last = 0.;
-    P.status = -1;
 }
 
 /* Time slices: the span of the call is cut into n_win windows [.., origin + (w + 1) * wlen) and the queue
@@ -794,6 +708,23 @@ __global__ void sh_interpolate_kernel(const __grid_constant__ AbBatch Bt, double
 }
 #endif  /* AB_TU == 3 */
 
+#if AB_TU == 4
+/* ------------------------------------------------------------------------ */
+/* per-particle IAS15, one CTA per 32 systems (coop_device.cuh, coop_roles.cuh) */
+/* ------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(ABC_THREADS, 1)
+pp_coop_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F, const __grid_constant__ AbcArgs A) {
+    extern __shared__ double abc_shared[];
+    AbcSmem sm;
+    sm.d = abc_shared;
+    sm.i = reinterpret_cast<int*>(abc_shared + ABC_SM_DOUBLES);
+    const int warp = (int)(threadIdx.x >> 5);
+    if (warp < 3) abc_comp_main(E, F, A, sm, warp);
+    else if (warp == ABC_CTRL_WARP) abc_control_main(E, F, A, sm);
+    else abc_worker_main(E, F, A, sm, warp);
+}
+#endif  /* AB_TU == 4 */
+
 }  // namespace AB_NS
 
 /* ------------------------------------------------------------------------ */
@@ -895,6 +826,34 @@ cudaError_t AB_CAT2(ab_launch_sh_integrate, AB_SFX)(const AbEphem& E, const AbFo
 cudaError_t AB_CAT2(ab_launch_sh_interpolate, AB_SFX)(const AbBatch& Bt, double dt_last_done, double h, double* out, cudaStream_t st) {
     const int grid = (Bt.n + AB_BLOCK - 1) / AB_BLOCK;
     sh_interpolate_kernel<<<grid, AB_BLOCK, 0, st>>>(Bt, dt_last_done, h, out);
+    return cudaGetLastError();
+}
+#endif
+
+#if AB_TU == 4
+cudaError_t AB_CAT2(ab_pp_coop_max_grid, AB_SFX)(int* max_grid) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(pp_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ABC_SMEM_BYTES)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pp_coop_kernel, ABC_THREADS, ABC_SMEM_BYTES)) != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    *max_grid = sms * per_sm;
+    return cudaSuccess;
+}
+
+cudaError_t AB_CAT2(ab_launch_pp_coop, AB_SFX)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const AbBatch& W, double tmax, int exact,
+                                               unsigned long long* queue_head, const AbSlices& SL, const double* times, int n_times, double* out,
+                                               const void* plan, int grid, cudaStream_t st) {
+    if (grid < 1) return cudaSuccess;
+    AbcArgs A;
+    A.Bt = Bt; A.W = W; A.tmax = tmax; A.exact_finish_time = exact; A.queue_head = queue_head; A.SL = SL;
+    A.times = times; A.n_times = n_times; A.out = out;
+    A.plan = *reinterpret_cast<const AbcPlan*>(plan);
+    cudaError_t e = cudaFuncSetAttribute(pp_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ABC_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    pp_coop_kernel<<<grid, ABC_THREADS, ABC_SMEM_BYTES, st>>>(E, F, A);
     return cudaGetLastError();
 }
 #endif

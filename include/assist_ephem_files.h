@@ -60,6 +60,8 @@ struct spk_s {
     /* assist-b200: device copies of the file image, one per CUDA device, made lazily */
     void* b200_dev_image[ASSIST_B200_MAX_DEVICES];
     void* b200_dev_targets[ASSIST_B200_MAX_DEVICES];
+    /* assist-b200: layout + segment descriptors of the packed device copy, built once per file (gpu_api.cu) */
+    void* b200_host_desc;
 };
 
 int assist_spk_free(struct spk_s* pl);
