@@ -60,18 +60,22 @@
 #define ABC_C_GRSIMPLE 24
 #define ABC_NCON 27
 
-/* shared-memory carve-up (doubles first, then ints) */
+/* shared-memory carve-up (doubles first, then ints).  XV .. EXTRA are free while the node tables are being filled
+ * and double as the staging area of the coefficient records (ABC_SM_STAGE); the total is the 227 KB a CTA can have. */
 #define ABC_SM_TAB 0
 #define ABC_SM_XV (ABC_SM_TAB + 8 * ABC_NODE_STRIDE)
 #define ABC_SM_PROD (ABC_SM_XV + 6 * ABC_SLOTS)
 #define ABC_SM_Q (ABC_SM_PROD + 81 * ABC_SLOTS)
 #define ABC_SM_CON (ABC_SM_Q + 11 * ABC_SLOTS)
 #define ABC_SM_MON (ABC_SM_CON + ABC_NCON * ABC_SLOTS)       /* |a| x3, |db6| x3, |b6| x3 */
-#define ABC_SM_PRM (ABC_SM_MON + 9 * ABC_SLOTS)
+#define ABC_SM_EXTRA (ABC_SM_MON + 9 * ABC_SLOTS)            /* staging only */
+#define ABC_SM_PRM (ABC_SM_EXTRA + 1920)
 #define ABC_SM_T0 (ABC_SM_PRM + 3 * ABC_SLOTS)               /* start time of the attempt */
 #define ABC_SM_DT (ABC_SM_T0 + ABC_SLOTS)                    /* step of the attempt */
 #define ABC_SM_RATIO (ABC_SM_DT + ABC_SLOTS)                 /* predict_next ratio */
 #define ABC_SM_DOUBLES (ABC_SM_RATIO + ABC_SLOTS)
+#define ABC_SM_STAGE ABC_SM_XV
+#define ABC_STAGE_DOUBLES (ABC_SM_PRM - ABC_SM_XV)           /* 6208: 32 slots x (cap_p + cap_a), cap_p + cap_a <= 194 */
 #define ABC_SMI_ACTIVE 0      /* slot takes part in this attempt */
 #define ABC_SMI_NEEDA0 1      /* slot needs the force evaluation at the start of the step */
 #define ABC_SMI_SW 2          /* slot is still sweeping */
@@ -168,6 +172,10 @@ struct AbcArgs {
 /* Coverage and presence checks of a step, as ab_fill_nodes makes them (the two end nodes decide). */
 __device__ int abc_coverage(const AbEphem& E, double t_first, double t_last) {
     const double jd_ref = E.jd_ref;
+    if (E.cov_simple) {     /* the common window, prepared on the host: same comparisons, folded */
+        const double j0 = jd_ref + t_first, j1 = jd_ref + t_last;
+        if (j0 >= E.cov_lo && j0 <= E.cov_hi && j1 >= E.cov_lo && j1 <= E.cov_hi) return AB_OK;
+    }
     for (int k = 0; k < 2; k++) {
         const double jd = jd_ref + (k == 0 ? t_first : t_last);
         if (E.planets_source == AB_SRC_ASCII) {
@@ -185,75 +193,284 @@ __device__ int abc_coverage(const AbEphem& E, double t_first, double t_last) {
     return AB_OK;
 }
 
-/* F1: thread = (slot, node, half).  Planet positions in AU, the Sun's velocity, heliocentric asteroid positions. */
-__device__ void abc_fill_f1(const AbEphem& E, const AbcSmem& sm, const AbcPlan& plan, int warp, int lane) {
-    const int slot = 4 * (warp & 7) + (lane >> 3);
-    const int node = lane & 7;
-    const int half = warp >> 3;
-    if (!sm.flag(ABC_SMI_ACTIVE, slot)) return;
-    const double t0 = sm.t0(slot);
-    const double t = (node == 0) ? t0 : (t0 + sm.dt(slot) * c_h[node]);
-    double* tb = sm.tab(node, slot);
-    int err = AB_OK;
-    int m_first, m_last;
-    if (half == 0) {
-        for (int b = 0; b < AB_NPLANETS; b++) {
-            double GM, x[3], v[3], a[3];
-            int flag;
-            if (b == 0) {
-                flag = ab_planet<1>(E, 0, t, &GM, x, v, a);
-                tb[ABC_E_SVEL(0) * ABC_SLOTS] = v[0]; tb[ABC_E_SVEL(1) * ABC_SLOTS] = v[1]; tb[ABC_E_SVEL(2) * ABC_SLOTS] = v[2];
-            } else {
-                flag = ab_planet<0>(E, b, t, &GM, x, v, a);
-            }
-            if (flag != AB_OK && err == AB_OK) err = flag;
-            tb[ABC_E_POS(b, 0) * ABC_SLOTS] = x[0]; tb[ABC_E_POS(b, 1) * ABC_SLOTS] = x[1]; tb[ABC_E_POS(b, 2) * ABC_SLOTS] = x[2];
-        }
-        m_first = 0; m_last = plan.ast_split;
+/* ---- the fill: thread = (slot, node); warps 0-7 take the planets, a few asteroids (plan.ast_split) and then the
+ * particle-independent EIH sums of their node, warps 8-15 the other asteroids of the same slots.
+ * Lane = 8 * (slot within the warp's four) + node.
+ *
+ * Every series is an SPK type-2 target (DE-binary planets: see the one-time path below).  The eight node times of a slot
+ * fall into one, two, seldom more consecutive records of a target, and consecutive records are contiguous in the
+ * packed image.  So the eight lanes of a slot copy that range (16-byte loads, every lane different pieces: up to seven
+ * independent loads in flight per lane, no two lanes fetching the same bytes) into the slot's staging area, and each
+ * lane evaluates its node from there.  Thirty-two lanes gathering from 32 records -- the access pattern of the
+ * one-thread-per-system kernel -- becomes four coalesced range copies per warp.  The copy of series s + 1 is in
+ * flight (in registers) while series s is evaluated.  What does not fit the pattern (nodes of a slot in different
+ * segments, a range longer than the staging area, a record larger than it) is read straight from the image by the
+ * lanes concerned, with the one-time routine.  Arithmetic per (series, time) is that of ephem_device.cuh. */
+#define ABC_FILL_PRE 7              /* 16-byte pieces a lane keeps in flight: staging areas of up to 112 doubles per slot */
+
+#ifdef AB_HOST_EMUL
+#define ABC_WARPSYNC()
+#define ABC_XDECL int wx_seg[32], wx_rec[32];
+#define ABC_XPUT(l, n, b) { wx_seg[l] = (n); wx_rec[l] = (b); }
+#define ABC_XSEG(selfval, src) wx_seg[src]
+#define ABC_XREC(selfval, src) wx_rec[src]
+#else
+#define ABC_WARPSYNC() __syncwarp()
+#define ABC_XDECL
+#define ABC_XPUT(l, n, b)
+#define ABC_XSEG(selfval, src) __shfl_sync(0xffffffffu, (selfval), (src))
+#define ABC_XREC(selfval, src) __shfl_sync(0xffffffffu, (selfval), (src))
+#endif
+
+struct AbcSeriesRef {
+    const double* img;
+    const AbSpkTarget* tg;
+    int kind;              /* 0 EMB, 1 Sun (with velocity), 2 planet `idx`, 3 asteroid `idx` */
+    int idx;
+};
+
+struct AbcFillLane {
+    double t;
+    int active;
+    int seg, rec, staged, lo, k;          /* series being evaluated: segment / record of this lane's node, staged range */
+    int nseg, nrec, nstaged, nlo, nk;     /* series being fetched */
+    double2 pre[ABC_FILL_PRE];
+    double emb[3];
+};
+
+/* series s of a warp's list */
+__device__ __forceinline__ AbcSeriesRef abc_series_ref(const AbEphem& E, const AbcPlan& plan, bool planets_half, int s) {
+    AbcSeriesRef r;
+    if (planets_half && s < 1 + AB_NPLANETS) {
+        r.img = E.spkp_img;
+        if (s == 0) { r.kind = 0; r.idx = -1; r.tg = &E.p_tgt[E.emb_index]; }
+        else { r.idx = s - 1; r.kind = (s == 1) ? 1 : 2; r.tg = &E.p_tgt[E.p_index[s - 1]]; }
     } else {
-        m_first = plan.ast_split; m_last = E.n_ast;
+        const int m = planets_half ? (s - 1 - AB_NPLANETS) : (plan.ast_split + s);
+        r.img = E.spka_img; r.kind = 3; r.idx = m; r.tg = &E.a_tgt[m];
     }
-    for (int m = m_first; m < m_last; m++) {
-        double GM, x[3] = {0.0, 0.0, 0.0};
-        const int flag = ab_asteroid(E, m, t, &GM, x);
-        if (flag != AB_OK && err == AB_OK) err = flag;
-        const int b = AB_NPLANETS + m;
-        tb[ABC_E_POS(b, 0) * ABC_SLOTS] = x[0]; tb[ABC_E_POS(b, 1) * ABC_SLOTS] = x[1]; tb[ABC_E_POS(b, 2) * ABC_SLOTS] = x[2];
-    }
-    if (err != AB_OK) sm.flag(ABC_SMI_ERR, slot) = err;      /* racing writers store valid codes; the pre-check decides what is reported */
+    return r;
 }
 
-/* F2: threads 0..255 = (slot, node): particle-independent EIH sums of the Sun (ab_fill_nodes, same operations);
- *     threads 256..511 = (slot, node): asteroids heliocentric -> barycentric (reference src/forces.c:213-219). */
-__device__ void abc_fill_f2(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, int warp, int lane) {
+/* where the nodes of every slot lie in series R, and the copy of that range into registers */
+__device__ __forceinline__ void abc_fill_fetch(const AbcSeriesRef& R, double jd_ref, AbcFillLane* L, int cap) {
+    ABC_XDECL
+    const AbSpkTarget& tg = *R.tg;
+    ABC_LANES(l) {
+        AbcFillLane& q = L[ABC_LI(l)];
+        int n = 0, b = 0;
+        if (q.active) {
+            n = ab_spk_segment(tg, jd_ref, q.t);
+            const AbSpkSeg& sg = tg.seg[n];
+            b = (int)ab_divc((jd_ref - sg.jul_init) + q.t, sg.intlen_d, sg.intlen_rd);
+            if (b > sg.nrec - 1) b = sg.nrec - 1;
+            if (b < 0) b = 0;
+        }
+        q.nseg = n; q.nrec = b;
+        ABC_XPUT(l, n, b)
+    }
+    ABC_WARPSYNC();
+    ABC_LANES(l) {
+        AbcFillLane& q = L[ABC_LI(l)];
+        const int g = l & ~7;
+        const int n0 = ABC_XSEG(q.nseg, g), b0 = ABC_XREC(q.nrec, g), n7 = ABC_XSEG(q.nseg, g + 7), b7 = ABC_XREC(q.nrec, g + 7);
+        q.nstaged = 0; q.nlo = 0; q.nk = 0;
+        if (q.active && n0 == n7) {
+            const AbSpkSeg& sg = tg.seg[n0];
+            const int cnt = (b0 < b7 ? b7 - b0 : b0 - b7) + 1;
+            int k = cap / sg.R;
+            if (k > cnt) k = cnt;
+            if (k >= 1) {
+                q.nstaged = 1; q.nlo = b0 < b7 ? b0 : b7; q.nk = k;
+                const double2* src = reinterpret_cast<const double2*>(R.img + (sg.one - 1) + (long long)q.nlo * sg.R);
+                const int chunks = (k * sg.R) >> 1;
+#pragma unroll
+                for (int i = 0; i < ABC_FILL_PRE; i++) {
+                    const int c = (l & 7) + 8 * i;
+                    if (c < chunks) q.pre[i] = __ldg(src + c);
+                }
+            }
+        }
+    }
+}
+
+/* registers -> the slot's staging area; the fetched series becomes the current one */
+__device__ __forceinline__ void abc_fill_stage(const AbcSeriesRef& R, AbcFillLane* L, double* wbuf, int cap) {
+    ABC_LANES(l) {
+        AbcFillLane& q = L[ABC_LI(l)];
+        if (q.nstaged) {
+            double2* dst = reinterpret_cast<double2*>(wbuf + (l >> 3) * cap);
+            const int chunks = (q.nk * R.tg->seg[q.nseg].R) >> 1;
+#pragma unroll
+            for (int i = 0; i < ABC_FILL_PRE; i++) {
+                const int c = (l & 7) + 8 * i;
+                if (c < chunks) dst[c] = q.pre[i];
+            }
+        }
+        q.seg = q.nseg; q.rec = q.nrec; q.staged = q.nstaged; q.lo = q.nlo; q.k = q.nk;
+    }
+}
+
+/* Chebyshev sums of this lane's node for series R (file units) and what becomes of them */
+__device__ __forceinline__ void abc_fill_eval(const AbEphem& E, const AbcSeriesRef& R, double jd_ref, AbcFillLane& q, const double* sbuf, double* tb) {
+    const AbSpkTarget& tg = *R.tg;
+    double u[3], uv[3] = {0.0, 0.0, 0.0}, uw[3];
+    if (q.staged && q.rec >= q.lo && q.rec < q.lo + q.k) {
+        const AbSpkSeg& sg = tg.seg[q.seg];
+        const double* rec = sbuf + (q.rec - q.lo) * sg.R;
+        const double jul_mid = rec[0];
+        double z, c;
+        if (sg.uniform) {
+            z = ab_divc((jd_ref - jul_mid) + q.t, sg.radius_d, sg.radius_rd);
+            c = sg.radius_inv;
+        } else {
+            const double radius = rec[1];
+            z = ((jd_ref - jul_mid) + q.t) / AB_DIVK(radius, 86400.0);
+            c = 1.0 / radius;
+        }
+        if (R.kind == 1) ab_cheb3<1, true, false>(rec + 2, sg.P, z, c, u, uv, uw);
+        else ab_cheb3<0, true, false>(rec + 2, sg.P, z, c, u, uv, uw);
+    } else {
+        if (R.kind == 1) ab_spk_target_pos<1>(R.img, tg, jd_ref, q.t, u, uv, uw);
+        else ab_spk_target_pos<0>(R.img, tg, jd_ref, q.t, u, uv, uw);
+    }
+    if (R.kind == 0) {
+        q.emb[0] = u[0]; q.emb[1] = u[1]; q.emb[2] = u[2];
+    } else if (R.kind == 3) {
+        /* heliocentric position / 149597870.7 (reference src/spk.c:470); the Sun is added after the barrier */
+        const int b = AB_NPLANETS + R.idx;
+        tb[ABC_E_POS(b, 0) * ABC_SLOTS] = AB_DIVK(u[0], 149597870.7);
+        tb[ABC_E_POS(b, 1) * ABC_SLOTS] = AB_DIVK(u[1], 149597870.7);
+        tb[ABC_E_POS(b, 2) * ABC_SLOTS] = AB_DIVK(u[2], 149597870.7);
+    } else {
+        const int b = R.idx;
+        if (b == 3 || b == 4) { u[0] += q.emb[0]; u[1] += q.emb[1]; u[2] += q.emb[2]; }    /* relative to the EMB (reference src/spk.c:572-587) */
+        tb[ABC_E_POS(b, 0) * ABC_SLOTS] = ab_divc(u[0], E.u_d[0], E.u_rd[0]);
+        tb[ABC_E_POS(b, 1) * ABC_SLOTS] = ab_divc(u[1], E.u_d[0], E.u_rd[0]);
+        tb[ABC_E_POS(b, 2) * ABC_SLOTS] = ab_divc(u[2], E.u_d[0], E.u_rd[0]);
+        if (R.kind == 1) {
+            tb[ABC_E_SVEL(0) * ABC_SLOTS] = ab_divc(uv[0], E.u_d[1], E.u_rd[1]);
+            tb[ABC_E_SVEL(1) * ABC_SLOTS] = ab_divc(uv[1], E.u_d[1], E.u_rd[1]);
+            tb[ABC_E_SVEL(2) * ABC_SLOTS] = ab_divc(uv[2], E.u_d[1], E.u_rd[1]);
+        }
+    }
+}
+
+__device__ __noinline__ void abc_fill_warp(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, const AbcPlan& plan, int warp) {
+    AbcFillLane L[ABC_NL];
+    const double jd_ref = E.jd_ref;
+    const bool planets_half = (warp < 8);
+    const int cap = planets_half ? plan.cap_p : plan.cap_a;
+    double* wbuf = sm.d + ABC_SM_STAGE + (planets_half ? warp * 4 * plan.cap_p : 32 * plan.cap_p + (warp - 8) * 4 * plan.cap_a);
+    ABC_LANES(l) {
+        AbcFillLane& q = L[ABC_LI(l)];
+        const int slot = 4 * (warp & 7) + (l >> 3);
+        const int node = l & 7;
+        q.active = sm.flag(ABC_SMI_ACTIVE, slot);
+        const double t0 = sm.t0(slot);
+        q.t = (node == 0) ? t0 : (t0 + sm.dt(slot) * c_h[node]);
+        q.emb[0] = q.emb[1] = q.emb[2] = 0.0;
+    }
+    /* usual SPK layout: every body and the EMB have a target */
+    bool spk_regular = (E.planets_source != AB_SRC_ASCII) && E.emb_index >= 0;
+    for (int b = 0; b < AB_NPLANETS && spk_regular; b++) if (E.p_index[b] < 0) spk_regular = false;
+    int s_first = 0;
+    if (planets_half && !spk_regular) {
+        /* DE-binary planets or a kernel without Earth / EMB target: the one-time routines, lane by lane */
+        ABC_LANES(l) {
+            AbcFillLane& q = L[ABC_LI(l)];
+            if (q.active) {
+                const int slot = 4 * (warp & 7) + (l >> 3);
+                double* tb = sm.tab(l & 7, slot);
+                int err = AB_OK;
+                for (int b = 0; b < AB_NPLANETS; b++) {
+                    double GM, x[3], v[3], a[3];
+                    int flag;
+                    if (b == 0) {
+                        flag = ab_planet<1>(E, 0, q.t, &GM, x, v, a);
+                        tb[ABC_E_SVEL(0) * ABC_SLOTS] = v[0]; tb[ABC_E_SVEL(1) * ABC_SLOTS] = v[1]; tb[ABC_E_SVEL(2) * ABC_SLOTS] = v[2];
+                    } else {
+                        flag = ab_planet<0>(E, b, q.t, &GM, x, v, a);
+                    }
+                    if (flag != AB_OK && err == AB_OK) err = flag;
+                    tb[ABC_E_POS(b, 0) * ABC_SLOTS] = x[0]; tb[ABC_E_POS(b, 1) * ABC_SLOTS] = x[1]; tb[ABC_E_POS(b, 2) * ABC_SLOTS] = x[2];
+                }
+                if (err != AB_OK) sm.flag(ABC_SMI_ERR, slot) = err;      /* the lanes of a slot may race: every value written is a valid code */
+            }
+        }
+        s_first = 1 + AB_NPLANETS;
+    }
+    const int s_end = planets_half ? (1 + AB_NPLANETS + plan.ast_split) : (E.n_ast - plan.ast_split);
+    if (s_first < s_end) {
+        AbcSeriesRef cur = abc_series_ref(E, plan, planets_half, s_first);
+        abc_fill_fetch(cur, jd_ref, L, cap);
+        for (int s = s_first; s < s_end; s++) {
+            abc_fill_stage(cur, L, wbuf, cap);
+            ABC_WARPSYNC();
+            AbcSeriesRef nxt = cur;
+            if (s + 1 < s_end) {      /* the next range travels while this one is evaluated */
+                nxt = abc_series_ref(E, plan, planets_half, s + 1);
+                abc_fill_fetch(nxt, jd_ref, L, cap);
+            }
+            ABC_LANES(l) {
+                AbcFillLane& q = L[ABC_LI(l)];
+                if (q.active) abc_fill_eval(E, cur, jd_ref, q, wbuf + (l >> 3) * cap, sm.tab(l & 7, 4 * (warp & 7) + (l >> 3)));
+            }
+            ABC_WARPSYNC();
+            cur = nxt;
+        }
+    }
+    /* particle-independent EIH sums of the Sun at this node (ab_fill_nodes, same operations): the lane reads back
+     * the eleven positions it has just written */
+    if (planets_half && (F.forces & 0x40)) {
+        ABC_LANES(l) {
+            const AbcFillLane& q = L[ABC_LI(l)];
+            if (q.active) {
+                double* tb = sm.tab(l & 7, 4 * (warp & 7) + (l >> 3));
+                const double sx = tb[ABC_E_POS(0, 0) * ABC_SLOTS], sy = tb[ABC_E_POS(0, 1) * ABC_SLOTS], sz = tb[ABC_E_POS(0, 2) * ABC_SLOTS];
+                double term1 = 0.0, arx = 0.0, ary = 0.0, arz = 0.0;
+#pragma unroll 1
+                for (int k0 = 1; k0 < AB_NPLANETS; k0 += 5) {
+                    /* five terms at a time: the square roots and divisions of a group are independent and overlap,
+                     * then the group is added in order */
+                    double t1[5], fx[5], fy[5], fz[5];
+#pragma unroll
+                    for (int j = 0; j < 5; j++) {
+                        const int k = k0 + j;
+                        const double GMk = E.gm[k];
+                        const double dxjk = sx - tb[ABC_E_POS(k, 0) * ABC_SLOTS];
+                        const double dyjk = sy - tb[ABC_E_POS(k, 1) * ABC_SLOTS];
+                        const double dzjk = sz - tb[ABC_E_POS(k, 2) * ABC_SLOTS];
+                        const double rjk2 = dxjk * dxjk + dyjk * dyjk + dzjk * dzjk;
+                        const double _rjk = sqrt(rjk2);
+                        t1[j] = GMk / _rjk;
+                        const double fac = GMk / (rjk2 * _rjk);
+                        fx[j] = fac * dxjk; fy[j] = fac * dyjk; fz[j] = fac * dzjk;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 5; j++) { term1 += t1[j]; arx -= fx[j]; ary -= fy[j]; arz -= fz[j]; }
+                }
+                tb[ABC_E_TERM1 * ABC_SLOTS] = term1;
+                tb[ABC_E_AR(0) * ABC_SLOTS] = arx; tb[ABC_E_AR(1) * ABC_SLOTS] = ary; tb[ABC_E_AR(2) * ABC_SLOTS] = arz;
+            }
+        }
+    }
+}
+
+/* after the barrier: asteroids heliocentric -> barycentric (reference src/forces.c:213-219); thread = (slot, node, half) */
+__device__ void abc_fill_shift(const AbEphem& E, const AbcSmem& sm, int warp, int lane) {
     const int slot = 4 * (warp & 7) + (lane >> 3);
     const int node = lane & 7;
     if (!sm.flag(ABC_SMI_ACTIVE, slot)) return;
     double* tb = sm.tab(node, slot);
     const double sx = tb[ABC_E_POS(0, 0) * ABC_SLOTS], sy = tb[ABC_E_POS(0, 1) * ABC_SLOTS], sz = tb[ABC_E_POS(0, 2) * ABC_SLOTS];
-    if (warp < 8) {
-        if (!(F.forces & 0x40)) return;
-        double term1 = 0.0, arx = 0.0, ary = 0.0, arz = 0.0;
-        for (int q = 1; q < AB_NPLANETS; q++) {
-            const double GMk = E.gm[q];
-            const double dxjk = sx - tb[ABC_E_POS(q, 0) * ABC_SLOTS];
-            const double dyjk = sy - tb[ABC_E_POS(q, 1) * ABC_SLOTS];
-            const double dzjk = sz - tb[ABC_E_POS(q, 2) * ABC_SLOTS];
-            const double rjk2 = dxjk * dxjk + dyjk * dyjk + dzjk * dzjk;
-            const double _rjk = sqrt(rjk2);
-            term1 += GMk / _rjk;
-            const double fac = GMk / (rjk2 * _rjk);
-            arx -= fac * dxjk; ary -= fac * dyjk; arz -= fac * dzjk;
-        }
-        tb[ABC_E_TERM1 * ABC_SLOTS] = term1;
-        tb[ABC_E_AR(0) * ABC_SLOTS] = arx; tb[ABC_E_AR(1) * ABC_SLOTS] = ary; tb[ABC_E_AR(2) * ABC_SLOTS] = arz;
-    } else {
-        for (int m = 0; m < E.n_ast; m++) {
-            const int b = AB_NPLANETS + m;
-            tb[ABC_E_POS(b, 0) * ABC_SLOTS] = tb[ABC_E_POS(b, 0) * ABC_SLOTS] + sx;
-            tb[ABC_E_POS(b, 1) * ABC_SLOTS] = tb[ABC_E_POS(b, 1) * ABC_SLOTS] + sy;
-            tb[ABC_E_POS(b, 2) * ABC_SLOTS] = tb[ABC_E_POS(b, 2) * ABC_SLOTS] + sz;
-        }
+    const int half = (E.n_ast + 1) / 2;
+    const int m0 = (warp < 8) ? 0 : half, m1 = (warp < 8) ? half : E.n_ast;
+    for (int m = m0; m < m1; m++) {
+        const int b = AB_NPLANETS + m;
+        tb[ABC_E_POS(b, 0) * ABC_SLOTS] = tb[ABC_E_POS(b, 0) * ABC_SLOTS] + sx;
+        tb[ABC_E_POS(b, 1) * ABC_SLOTS] = tb[ABC_E_POS(b, 1) * ABC_SLOTS] + sy;
+        tb[ABC_E_POS(b, 2) * ABC_SLOTS] = tb[ABC_E_POS(b, 2) * ABC_SLOTS] + sz;
     }
 }
 
@@ -267,26 +484,52 @@ __device__ __forceinline__ bool abc_body_on(int i, int fmask) {
     return (fmask & 0x04) != 0;
 }
 
-/* One body of the direct term (reference src/forces.c:325-344) and, for a planet, its term of the EIH
- * potential sum (src/forces.c:1400-1416: same separation, same square root). */
-__device__ __forceinline__ void abc_task_body(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, const double* tb,
-                                              int i, int slot) {
+/* N bodies of the direct term (reference src/forces.c:325-344) and, for planets, their terms of the EIH potential
+ * sum (src/forces.c:1400-1416: same separation, same square root).  The bodies are independent until the component
+ * warps add them up, so their chains (difference, square root, division) are laid side by side. */
+template <int N, bool PLANETS>
+__device__ __forceinline__ void abc_task_bodies(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, const double* tb,
+                                                const unsigned char* ids, int slot) {
     const double px = sm.xv(0, slot), py = sm.xv(1, slot), pz = sm.xv(2, slot);
-    const double cx = tb[ABC_E_POS(i, 0) * ABC_SLOTS], cy = tb[ABC_E_POS(i, 1) * ABC_SLOTS], cz = tb[ABC_E_POS(i, 2) * ABC_SLOTS];
-    const double GM = E.gm[i];
     const double xo = 0.0, yo = 0.0, zo = 0.0;
-    const double dx = px + (xo - cx);
-    const double dy = py + (yo - cy);
-    const double dz = pz + (zo - cz);
-    const double r2 = dx * dx + dy * dy + dz * dz;
-    const double _r = sqrt(r2);
-    if (abc_body_on(i, F.forces)) {
-        const double prefac = GM / (_r * _r * _r);
-        sm.prod(i, 0, slot) = prefac * dx;
-        sm.prod(i, 1, slot) = prefac * dy;
-        sm.prod(i, 2, slot) = prefac * dz;
+    double dx[N], dy[N], dz[N], _r[N], GM[N];
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+        const int i = ids[n];
+        const double cx = tb[ABC_E_POS(i, 0) * ABC_SLOTS], cy = tb[ABC_E_POS(i, 1) * ABC_SLOTS], cz = tb[ABC_E_POS(i, 2) * ABC_SLOTS];
+        GM[n] = E.gm[i];
+        dx[n] = px + (xo - cx);
+        dy[n] = py + (yo - cy);
+        dz[n] = pz + (zo - cz);
+        const double r2 = dx[n] * dx[n] + dy[n] * dy[n] + dz[n] * dz[n];
+        _r[n] = sqrt(r2);
     }
-    if (i < AB_NPLANETS && (F.forces & 0x40)) sm.q(i, slot) = GM / _r;
+    const bool eih = PLANETS && (F.forces & 0x40);
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+        const int i = ids[n];
+        const double prefac = GM[n] / (_r[n] * _r[n] * _r[n]);
+        const double p0 = prefac * dx[n], p1 = prefac * dy[n], p2 = prefac * dz[n];
+        if (abc_body_on(i, F.forces)) { sm.prod(i, 0, slot) = p0; sm.prod(i, 1, slot) = p1; sm.prod(i, 2, slot) = p2; }
+        if (PLANETS) {
+            const double qv = GM[n] / _r[n];
+            if (eih) sm.q(i, slot) = qv;
+        }
+    }
+}
+
+template <bool PLANETS>
+__device__ __forceinline__ void abc_task_group(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, const double* tb,
+                                               const AbcWorkerPlan& wp, int slot) {
+    switch (wp.nbody) {
+        case 1: abc_task_bodies<1, PLANETS>(E, F, sm, tb, wp.body, slot); break;
+        case 2: abc_task_bodies<2, PLANETS>(E, F, sm, tb, wp.body, slot); break;
+        case 3: abc_task_bodies<3, PLANETS>(E, F, sm, tb, wp.body, slot); break;
+        case 4: abc_task_bodies<4, PLANETS>(E, F, sm, tb, wp.body, slot); break;
+        case 5: abc_task_bodies<5, PLANETS>(E, F, sm, tb, wp.body, slot); break;
+        case 6: abc_task_bodies<6, PLANETS>(E, F, sm, tb, wp.body, slot); break;
+        default: break;
+    }
 }
 
 /* EIH source block of the Sun for the real particle (reference src/forces.c:1319-1501 with j = 0), everything
@@ -373,11 +616,7 @@ __device__ __forceinline__ void abc_sys_from_slot(const AbcSmem& sm, int slot, A
 
 __device__ void abc_run_task(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, int node, int slot, int kind) {
     const double* tb = sm.tab(node, slot);
-    if (kind < AB_MAX_BODIES) {
-        abc_task_body(E, F, sm, tb, kind, slot);
-        if (kind == 0 && (F.forces & 0x40)) abc_task_eih_source(E, sm, tb, slot);
-        return;
-    }
+    if (kind == ABC_T_EIHSRC) { abc_task_eih_source(E, sm, tb, slot); return; }
     AbSysT<1> S;
     abc_sys_from_slot(sm, slot, S);
     const AbcTabView B(E.gm, tb);

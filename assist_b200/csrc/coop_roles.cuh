@@ -6,9 +6,10 @@
  *   -------  -------------  ----------------------------------------------------------------------
  *            control        bookkeeping per slot (queue, integrate() entry / exit, output epochs, windows)
  *   B1 (or)  all            anything left to do?  no -> the CTA retires
- *            all 16 warps   F1: Chebyshev sums of the 8 node times
+ *            all 16 warps   fill: Chebyshev sums of the 8 node times (warps 0-7 planets + EIH pair sums of the Sun,
+ *                           warps 8-15 asteroids), records staged through shared memory
  *   B2
- *            all 16 warps   F2: EIH pair sums of the Sun, asteroids to barycentric
+ *            all 16 warps   asteroids to barycentric
  *   B3
  *            control        ephemeris errors of the fill, sweep state of the attempt
  *   B4 (or)  all            does any slot need the force evaluation at the start of its step?
@@ -200,9 +201,9 @@ __device__ void abc_control_main(ABC_CTXARG const AbEphem& E, const AbForceOpts&
             if (C.have || C.pending) alive = 1;
         }
         if (!ABC_SYNC_OR(alive)) return;                                         /* B1 */
-        ABC_LANES(l) { abc_fill_f1(E, sm, A.plan, ABC_CTRL_WARP, l); }
+        abc_fill_warp(E, F, sm, A.plan, ABC_CTRL_WARP);
         ABC_SYNC();                                                              /* B2 */
-        ABC_LANES(l) { abc_fill_f2(E, F, sm, ABC_CTRL_WARP, l); }
+        ABC_LANES(l) { abc_fill_shift(E, sm, ABC_CTRL_WARP, l); }
         ABC_SYNC();                                                              /* B3 */
         int anya0 = 0;
         ABC_LANES(l) {
@@ -329,17 +330,17 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
     const long long wn = W.n;
     for (;;) {
         if (!ABC_SYNC_OR(0)) return;                                             /* B1 */
-        ABC_LANES(l) { abc_fill_f1(E, sm, A.plan, c, l); }
+        abc_fill_warp(E, F, sm, A.plan, c);
         ABC_SYNC();                                                              /* B2 */
-        ABC_LANES(l) { abc_fill_f2(E, F, sm, c, l); }
+        ABC_LANES(l) { abc_fill_shift(E, sm, c, l); }
         ABC_SYNC();                                                              /* B3 */
         const bool a0_round = ABC_SYNC_OR(0);                                    /* B4 */
         ABC_LANES(l) {
-            if (sm.flag(ABC_SMI_ACTIVE, l)) {
-                AbcComp& s = st[ABC_LI(l)];
-                abc_comp_load(W, (long long)ABC_BLOCK * ABC_SLOTS + l, c, s);
-                if (sm.flag(ABC_SMI_NEEDA0, l)) { sm.xv(c, l) = s.pos; sm.xv(3 + c, l) = s.vel; }
-            }
+            /* every lane loads (an idle slot reads its stale working copy and never uses it): the registers carry
+             * nothing from one attempt to the next, so they are free during the fill */
+            AbcComp& s = st[ABC_LI(l)];
+            abc_comp_load(W, (long long)ABC_BLOCK * ABC_SLOTS + l, c, s);
+            if (sm.flag(ABC_SMI_NEEDA0, l)) { sm.xv(c, l) = s.pos; sm.xv(3 + c, l) = s.vel; }
         }
         if (a0_round) {
             ABC_SYNC();                                                          /* B5 */
@@ -429,21 +430,22 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
 __device__ __forceinline__ void abc_worker_tasks(const AbEphem& E, const AbForceOpts& F, const AbcArgs& A, const AbcSmem& sm,
                                                  int widx, int node, int which_flag, int l) {
     if (!sm.flag(which_flag, l)) return;
-#pragma unroll 1
-    for (int q = 0; q < ABC_MAX_TASKS; q++) {
-        const int kind = A.plan.task[widx][q];
-        if (kind == ABC_T_NONE) break;
-        abc_run_task(E, F, sm, node, l, kind);
+    const AbcWorkerPlan& wp = A.plan.w[widx];
+    if (wp.nbody) {
+        if (wp.planets) abc_task_group<true>(E, F, sm, sm.tab(node, l), wp, l);
+        else abc_task_group<false>(E, F, sm, sm.tab(node, l), wp, l);
     }
+    if (wp.scalar[0] != ABC_T_NONE) abc_run_task(E, F, sm, node, l, wp.scalar[0]);
+    if (wp.scalar[1] != ABC_T_NONE) abc_run_task(E, F, sm, node, l, wp.scalar[1]);
 }
 
 __device__ void abc_worker_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F, const AbcArgs& A, const AbcSmem& sm, int warp) {
     const int widx = warp - ABC_FIRST_WORKER;
     for (;;) {
         if (!ABC_SYNC_OR(0)) return;                                             /* B1 */
-        ABC_LANES(l) { abc_fill_f1(E, sm, A.plan, warp, l); }
+        abc_fill_warp(E, F, sm, A.plan, warp);
         ABC_SYNC();                                                              /* B2 */
-        ABC_LANES(l) { abc_fill_f2(E, F, sm, warp, l); }
+        ABC_LANES(l) { abc_fill_shift(E, sm, warp, l); }
         ABC_SYNC();                                                              /* B3 */
         const bool a0_round = ABC_SYNC_OR(0);                                    /* B4 */
         if (a0_round) {

@@ -69,6 +69,10 @@ struct AbEphem {
     /* SPK asteroids: descriptors live in global memory */
     const double* spka_img;
     const AbSpkTarget* a_tgt;
+    /* Julian dates every body the force model reads is covered for (intersection over the targets), so that the
+     * per-step coverage check is two comparisons; cov_simple == 0: a target is missing, ask the full check */
+    double cov_lo, cov_hi;
+    int cov_simple;
 };
 
 /* Force-model switches, snapshot of struct assist_extras at launch (reference src/assist.h:177-195). */
@@ -161,7 +165,6 @@ struct AbShared {
 #define ABC_CTRL_WARP 3
 #define ABC_FIRST_WORKER 4
 #define ABC_NWORK (ABC_WARPS - ABC_FIRST_WORKER)
-#define ABC_MAX_TASKS 4          /* tasks per worker warp */
 
 /* task kinds of the workers */
 #define ABC_T_BODY0 0            /* 0..26: body index */
@@ -170,12 +173,22 @@ struct AbShared {
 #define ABC_T_NG 29
 #define ABC_T_GRPOT 30
 #define ABC_T_GRSIMPLE 31
+#define ABC_T_EIHSRC 32          /* EIH source block of the Sun (everything but the potential sum over the planets) */
 #define ABC_T_NONE 255
 
-/* launch-time plan of the worker warps */
+/* launch-time plan of the worker warps: a group of bodies of the direct term evaluated side by side (their square
+ * roots and divisions are independent and overlap) plus up to two of the single-body terms */
+#define ABC_MAX_GROUP 6
+struct AbcWorkerPlan {
+    unsigned char scalar[2];          /* ABC_T_EARTHJ ..., ABC_T_NONE */
+    unsigned char nbody;              /* bodies in the group */
+    unsigned char planets;            /* the group holds planets: also their terms of the EIH potential sum */
+    unsigned char body[ABC_MAX_GROUP];
+};
 struct AbcPlan {
-    unsigned char task[ABC_NWORK][ABC_MAX_TASKS];
-    int ast_split;            /* fill: asteroids [0, ast_split) are evaluated with the planets' half */
+    AbcWorkerPlan w[ABC_NWORK];
+    int ast_split;            /* fill: asteroids [0, ast_split) are evaluated by the warps that take the planets */
+    int cap_p, cap_a;         /* fill: doubles of staging area per slot for the two halves (cap_p + cap_a <= 194, both even) */
     long long attempt_budget; /* step attempts per system and call before it is retired with an error; <= 0: none */
 };
 

@@ -39,7 +39,9 @@ __device__ __forceinline__ double ab_jul(double eph) { return 2451545.0 + AB_DIV
  * derivative scale c.  LEVEL 0: position, 1: +velocity, 2: +acceleration. */
 /* PACKED: the device copy of an SPK kernel holds the coefficients of a record as [p][x y z] (gpu_api.cu,
  * upload_packed_spk); DE-binary images keep the file's [x y z][p]. */
-template <int LEVEL, bool PACKED>
+/* LDG: the coefficients are read-only global memory (non-coherent loads); false: any address space (the staged
+ * copies of pp_coop_kernel live in shared memory). */
+template <int LEVEL, bool PACKED, bool LDG = true>
 __device__ __forceinline__ void ab_cheb3(const double* __restrict__ cf, int P, double z, double c,
                                          double u[3], double v[3], double w[3]) {
     double u0 = 0.0, u1 = 0.0, u2 = 0.0;
@@ -59,7 +61,9 @@ __device__ __forceinline__ void ab_cheb3(const double* __restrict__ cf, int P, d
             if (LEVEL >= 1) S = 2.0 * z * Sm1 + 2.0 * Tm1 - Sm2;
             if (LEVEL >= 2) U = (p == 2) ? 4.0 : (2.0 * z * Um1 + 4.0 * Sm1 - Um2);
         }
-        const double ax = __ldg(cx + stride * p), ay = __ldg(cy + stride * p), az = __ldg(cz + stride * p);
+        const double ax = LDG ? __ldg(cx + stride * p) : cx[stride * p];
+        const double ay = LDG ? __ldg(cy + stride * p) : cy[stride * p];
+        const double az = LDG ? __ldg(cz + stride * p) : cz[stride * p];
         u0 += ax * T; u1 += ay * T; u2 += az * T;
         if (LEVEL >= 1) { v0 += ax * S * c; v1 += ay * S * c; v2 += az * S * c; }
         if (LEVEL >= 2) { w0 += ax * U * c * c; w1 += ay * U * c * c; w2 += az * U * c * c; }

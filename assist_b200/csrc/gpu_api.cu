@@ -358,6 +358,25 @@ static int build_ephem_impl(const struct assist_ephem* e, AbEphem* E, bool host_
         }
         for (int m = 0; m < sb->num; m++) E->gm[AB_NPLANETS + m] = sb->targets[m].mass;
     }
+    /* common coverage window (the checks of ab_fill_nodes / abc_coverage, folded) */
+    E->cov_lo = -1e300; E->cov_hi = 1e300; E->cov_simple = 1;
+    if (e->ascii_planets) {
+        E->cov_lo = E->a_beg; E->cov_hi = E->a_end;
+    } else {
+        for (int k = 0; k < AB_NPLANETS; k++) {
+            const int idx = E->p_index[k];
+            if (idx < 0) { if (k != 3) E->cov_simple = 0; continue; }
+            if (E->p_tgt[idx].beg > E->cov_lo) E->cov_lo = E->p_tgt[idx].beg;
+            if (E->p_tgt[idx].end < E->cov_hi) E->cov_hi = E->p_tgt[idx].end;
+        }
+    }
+    if (e->spk_asteroids) {
+        for (int m = 0; m < e->spk_asteroids->num; m++) {
+            const struct spk_target* t = &e->spk_asteroids->targets[m];
+            if (t->beg > E->cov_lo) E->cov_lo = t->beg;
+            if (t->end < E->cov_hi) E->cov_hi = t->end;
+        }
+    }
     for (int k = 0; k < AB_NPLANETS; k++) {
         if (e->ascii_planets) E->gm[k] = e->ascii_planets->mass[k];
         else E->gm[k] = (E->p_index[k] >= 0) ? E->p_tgt[E->p_index[k]].mass : 0.0;   /* Earth-from-EMB fallback reports GM = 0 */
@@ -466,6 +485,52 @@ extern "C" int assist_gpu_eval_forces(const struct assist_ephem* ephem, const st
     cudaFree(d_t); cudaFree(d_state); cudaFree(d_prm); cudaFree(d_acc); cudaFree(d_st);
     if (e != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "eval_forces: %s", cudaGetErrorString(e));
     if (first_err) return set_err(first_err, "%s", assist_error_messages[first_err]);
+    return 0;
+}
+
+
+/* ---- single-target evaluators behind the reference's spk.h / ascii_ephem.h entry points ------------------- */
+
+/* out[9] = u v w of one SPK target (index into file->targets) at jd_ref + jd_rel.  mode as spk_target_kernel;
+ * emb_index >= 0: that target is added first (Earth and Moon are given relative to the EMB). */
+extern "C" int ab_gpu_spk_target_eval(struct spk_s* file, int target_index, int emb_index, double jd_ref, double jd_rel,
+                                      int mode, const double* ud, double* out) {
+    int dev;
+    int rc = ensure_device(&dev);
+    if (rc) return rc;
+    if (!file || target_index < 0 || target_index >= file->num) return set_err(ASSIST_GPU_ERR_ARG, "bad SPK target");
+    AbSpkDesc* d = nullptr;
+    if ((rc = spk_desc(file, &d))) return rc;
+    if ((rc = upload_packed_spk(&file->b200_dev_image[dev], file, d->off, d->words))) return rc;
+    double* d_out = nullptr;
+    CU(cudaMalloc((void**)&d_out, sizeof(double) * 9));
+    const double one[3] = {1.0, 1.0, 1.0};
+    const AbSpkTarget& tg = d->tg[target_index];
+    const AbSpkTarget& emb = d->tg[emb_index >= 0 ? emb_index : target_index];
+    cudaError_t e = ab_launch_spk_target_strict((const double*)file->b200_dev_image[dev], tg, emb_index >= 0 ? 1 : 0, emb,
+                                                jd_ref, jd_rel, mode, ud ? ud : one, d_out, 0);
+    AB_COUNT(1);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * 9, cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "spk_target_eval: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+/* assist_ascii_work on the device: P holds niv * ncm * ncf coefficients (host memory); out[3][ncm]. */
+extern "C" int ab_gpu_ascii_work(const double* P, int ncm, int ncf, int niv, double t0, double t1, double* out) {
+    int dev;
+    int rc = ensure_device(&dev);
+    if (rc) return rc;
+    if (!P || ncm < 1 || ncm > 3 || ncf < 2 || ncf > 32 || niv < 1) return set_err(ASSIST_GPU_ERR_ARG, "assist_ascii_work: bad shape");
+    const size_t n = (size_t)ncm * ncf * niv;
+    double *d_P = nullptr, *d_out = nullptr;
+    CU(cudaMalloc((void**)&d_P, sizeof(double) * n));
+    CU(cudaMalloc((void**)&d_out, sizeof(double) * 9));
+    cudaError_t e = cudaMemcpy(d_P, P, sizeof(double) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { e = ab_launch_ascii_work_strict(d_P, ncm, ncf, niv, t0, t1, d_out, 0); AB_COUNT(1); }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * 3 * ncm, cudaMemcpyDeviceToHost);
+    cudaFree(d_P); cudaFree(d_out);
+    if (e != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "ascii_work: %s", cudaGetErrorString(e));
     return 0;
 }
 
@@ -853,39 +918,103 @@ static bool coop_applies(const assist_gpu_batch* b, const AbForceOpts& F) {
 
 /* Spread the force terms over the worker warps: longest task first onto the least loaded warp.  The weights
  * are rough FP64 instruction counts of the strict build. */
-static void build_coop_plan(const AbEphem& E, const AbForceOpts& F, long long budget, AbcPlan* plan) {
-    struct Task { int kind; int cost; };
-    std::vector<Task> tasks;
+#define ABC_FILL_PRE_HOST 7      /* coop_device.cuh: ABC_FILL_PRE */
+static void build_coop_plan(const struct assist_ephem* e, const AbEphem& E, const AbForceOpts& F, long long budget, AbcPlan* plan) {
+    /* rough latencies (cycles) of the chains: the phase ends with its slowest warp */
+    struct Scalar { int kind; int cost; };
+    std::vector<Scalar> sc;
     const int nb = AB_NPLANETS + E.n_ast;
     const bool eih = (F.forces & 0x40) != 0;
-    for (int i = 0; i < nb; i++) {
-        int cost = 66;
-        if (i < AB_NPLANETS && eih) cost += 26;
-        if (i == 0 && eih) cost += 250;
-        tasks.push_back({ABC_T_BODY0 + i, cost});
+    if ((F.forces & 0x08) && F.has_params) sc.push_back({ABC_T_NG, 3000});
+    if (F.forces & 0x10) sc.push_back({ABC_T_EARTHJ, 1000});
+    if (eih) sc.push_back({ABC_T_EIHSRC, 800});
+    if (F.forces & 0x20) sc.push_back({ABC_T_SUNJ2, 700});
+    if (F.forces & 0x80) sc.push_back({ABC_T_GRSIMPLE, 600});
+    if (F.forces & 0x100) sc.push_back({ABC_T_GRPOT, 500});
+    memset(plan->w, 0, sizeof(plan->w));
+    int load[ABC_NWORK] = {0};
+    for (int w = 0; w < ABC_NWORK; w++) { plan->w[w].scalar[0] = ABC_T_NONE; plan->w[w].scalar[1] = ABC_T_NONE; }
+    /* the single-body terms: one warp each, at most half of the warps (the others pair up on the lightest ones) */
+    const int scalar_warps = (int)sc.size() < ABC_NWORK / 2 ? (int)sc.size() : ABC_NWORK / 2;
+    for (size_t k = 0; k < sc.size(); k++) {
+        int best = 0;
+        for (int w = 1; w < scalar_warps; w++) if (load[w] < load[best]) best = w;
+        if ((int)k < scalar_warps) best = (int)k;
+        AbcWorkerPlan& wp = plan->w[best];
+        if (wp.scalar[0] == ABC_T_NONE) wp.scalar[0] = (unsigned char)sc[k].kind; else wp.scalar[1] = (unsigned char)sc[k].kind;
+        load[best] += sc[k].cost;
     }
-    if (F.forces & 0x10) tasks.push_back({ABC_T_EARTHJ, 250});
-    if (F.forces & 0x20) tasks.push_back({ABC_T_SUNJ2, 150});
-    if ((F.forces & 0x08) && F.has_params) tasks.push_back({ABC_T_NG, 700});
-    if (F.forces & 0x100) tasks.push_back({ABC_T_GRPOT, 80});
-    if (F.forces & 0x80) tasks.push_back({ABC_T_GRSIMPLE, 100});
-    std::sort(tasks.begin(), tasks.end(), [](const Task& a, const Task& b) { return a.cost > b.cost; });
-    int load[ABC_NWORK] = {0}, cnt[ABC_NWORK] = {0};
-    memset(plan->task, ABC_T_NONE, sizeof(plan->task));
-    for (const Task& t : tasks) {
+    /* the bodies of the direct term: homogeneous groups (planets / asteroids) over the remaining warps */
+    const int group_warps = ABC_NWORK - scalar_warps;
+    int gp = (int)((double)group_warps * (AB_NPLANETS * 1.3) / (AB_NPLANETS * 1.3 + E.n_ast) + 0.5);
+    if (gp < 1) gp = 1;
+    if (E.n_ast > 0 && gp > group_warps - 1) gp = group_warps - 1;
+    if (E.n_ast == 0) gp = group_warps;
+    while ((AB_NPLANETS + gp - 1) / gp > ABC_MAX_GROUP) gp++;       /* never more than ABC_MAX_GROUP bodies in a group */
+    int ga = group_warps - gp;
+    int w = scalar_warps;
+    for (int g = 0; g < gp; g++, w++) {
+        AbcWorkerPlan& wp = plan->w[w];
+        wp.planets = 1;
+        for (int i = g; i < AB_NPLANETS; i += gp) wp.body[wp.nbody++] = (unsigned char)i;
+    }
+    /* asteroid groups; what does not fit goes to the lightest scalar warp as an extra group */
+    std::vector<int> ast;
+    for (int i = AB_NPLANETS; i < nb; i++) ast.push_back(i);
+    size_t next = 0;
+    for (int g = 0; g < ga && next < ast.size(); g++, w++) {
+        AbcWorkerPlan& wp = plan->w[w];
+        wp.planets = 0;
+        const size_t take = (ast.size() - next + (size_t)(ga - g) - 1) / (size_t)(ga - g);
+        for (size_t q = 0; q < take && q < ABC_MAX_GROUP; q++) wp.body[wp.nbody++] = (unsigned char)ast[next++];
+    }
+    while (next < ast.size()) {          /* leftovers: scalar warps that have no group yet, lightest first */
         int best = -1;
-        for (int w = 0; w < ABC_NWORK; w++)
-            if (cnt[w] < ABC_MAX_TASKS && (best < 0 || load[w] < load[best])) best = w;
-        plan->task[best][cnt[best]++] = (unsigned char)t.kind;      /* 12 x 4 slots >= 32 tasks: always room */
-        load[best] += t.cost;
+        for (int q = 0; q < scalar_warps; q++) if (plan->w[q].nbody < ABC_MAX_GROUP && !plan->w[q].planets && (best < 0 || load[q] < load[best])) best = q;
+        if (best < 0) break;
+        plan->w[best].body[plan->w[best].nbody++] = (unsigned char)ast[next++];
+        load[best] += 100;
     }
-    /* fill: half of the threads take the planets and the first asteroids, the other half the remaining asteroids */
-    int split = E.n_ast / 4;
+    /* fill: warps 0-7 take the planets, the first ast_split asteroids and the EIH sums of the Sun, warps 8-15 the other
+     * asteroids; the split balances rough instruction counts (60 per series + 9 per Chebyshev term, 900 for the sums).
+     * Staging areas: two records of the largest record size of each half when that fits the 194 doubles a slot can
+     * have for both, sizes = 6 or 10 mod 16 so that the four slots of a warp start in different banks. */
+    int maxRp = 0, maxRa = 0, pa = 0;
+    double cost_p = (F.forces & 0x40) ? 900.0 : 0.0;
+    if (!e->ascii_planets && e->spk_planets && e->spk_planets->b200_host_desc) {
+        const AbSpkDesc* pd = (const AbSpkDesc*)e->spk_planets->b200_host_desc;
+        for (int k = -1; k < AB_NPLANETS; k++) {
+            const int idx = (k < 0) ? E.emb_index : E.p_index[k];
+            if (idx < 0) continue;
+            int P = 0;
+            for (int q = 0; q < pd->tg[idx].nseg; q++) { if (pd->tg[idx].seg[q].R > maxRp) maxRp = pd->tg[idx].seg[q].R; if (pd->tg[idx].seg[q].P > P) P = pd->tg[idx].seg[q].P; }
+            cost_p += 60.0 + 9.0 * P * (k == 0 ? 1.6 : 1.0);
+        }
+    } else {
+        cost_p += 12 * 200.0;       /* DE-binary planets: the one-time routines */
+    }
+    if (e->spk_asteroids && e->spk_asteroids->b200_host_desc) {
+        const AbSpkDesc* ad = (const AbSpkDesc*)e->spk_asteroids->b200_host_desc;
+        for (int m = 0; m < E.n_ast; m++)
+            for (int q = 0; q < ad->tg[m].nseg; q++) { if (ad->tg[m].seg[q].R > maxRa) maxRa = ad->tg[m].seg[q].R; if (ad->tg[m].seg[q].P > pa) pa = ad->tg[m].seg[q].P; }
+    }
+    const double cost_a = 60.0 + 9.0 * pa;
+    int split = 0;
+    while (split < E.n_ast && cost_p + (split + 1) * cost_a <= (E.n_ast - split - 1) * cost_a) split++;
     const char* sp = getenv("ASSIST_B200_AST_SPLIT");
     if (sp) split = atoi(sp);
     if (split < 0) split = 0;
     if (split > E.n_ast) split = E.n_ast;
     plan->ast_split = split;
+    auto bank_friendly = [](int want) { int c = want < 2 ? 2 : want; while (!((c % 16) == 6 || (c % 16) == 10)) c++; return c; };
+    const int Rp_need = (split > 0 && maxRa > maxRp) ? maxRa : maxRp;
+    int cap_p = bank_friendly(2 * Rp_need), cap_a = bank_friendly(2 * maxRa);
+    if (cap_p + cap_a > 194) { cap_p = bank_friendly(Rp_need); }
+    if (cap_p + cap_a > 194) { cap_a = bank_friendly(maxRa); }
+    if (cap_p + cap_a > 194) { cap_p = 90; cap_a = 102; }      /* oversized records are read straight from the image */
+    if (cap_p > 8 * 2 * ABC_FILL_PRE_HOST) cap_p = 8 * 2 * ABC_FILL_PRE_HOST - 6;
+    if (cap_a > 8 * 2 * ABC_FILL_PRE_HOST) cap_a = 8 * 2 * ABC_FILL_PRE_HOST - 6;
+    plan->cap_p = cap_p; plan->cap_a = cap_a;
     plan->attempt_budget = budget;
 }
 
@@ -922,9 +1051,9 @@ extern "C" int ab_gpu_build_force_opts_host(const struct assist_gpu_options* o, 
     build_force_opts(o, has_params, (AbForceOpts*)F_out);
     return 0;
 }
-extern "C" int ab_gpu_build_coop_plan_host(const void* E, const void* F, long long budget, void* plan_out, size_t plan_bytes) {
+extern "C" int ab_gpu_build_coop_plan_host(const struct assist_ephem* e, const void* E, const void* F, long long budget, void* plan_out, size_t plan_bytes) {
     if (plan_bytes != sizeof(AbcPlan)) return set_err(ASSIST_GPU_ERR_ARG, "AbcPlan size mismatch");
-    build_coop_plan(*(const AbEphem*)E, *(const AbForceOpts*)F, budget, (AbcPlan*)plan_out);
+    build_coop_plan(e, *(const AbEphem*)E, *(const AbForceOpts*)F, budget, (AbcPlan*)plan_out);
     return 0;
 }
 extern "C" size_t ab_gpu_batch_bytes_host(size_t n, size_t C) { return batch_bytes(n, C); }
@@ -960,7 +1089,7 @@ extern "C" int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int 
             b->slice_days = keep;
             if (rc) return rc;
             AbcPlan plan;
-            build_coop_plan(E, F, b->attempt_budget, &plan);
+            build_coop_plan(b->ephem, E, F, b->attempt_budget, &plan);
             CU(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), 0));
             CU(cudaEventRecord(b->ev0, 0));
             e = fast ? ab_launch_pp_coop_fast(E, F, b->d, b->wc, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, &plan, b->coop_grid, 0)
@@ -1069,7 +1198,7 @@ extern "C" int assist_gpu_batch_integrate_or_interpolate(assist_gpu_batch* b, co
         if (rc) return rc;
         if (SL.n_win > 1 && n_times > 1 && SL.wlen * dir < 0.0) SL.n_win = 1;
         AbcPlan plan;
-        build_coop_plan(E, F, b->attempt_budget, &plan);
+        build_coop_plan(b->ephem, E, F, b->attempt_budget, &plan);
         CU(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), 0));
         CU(cudaEventRecord(b->ev0, 0));
         e = fastm ? ab_launch_pp_coop_fast(E, F, b->d, b->wc, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, &plan, b->coop_grid, 0)

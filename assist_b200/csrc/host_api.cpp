@@ -16,6 +16,8 @@
 
 #include "assist.h"
 #include "assist_ephem_files.h"
+#include "spk.h"
+#include "ascii_ephem.h"
 #include "assist_gpu.h"
 #include "host_internal.h"
 
@@ -320,6 +322,95 @@ enum ASSIST_STATUS assist_ascii_calc_from_ephem(const struct assist_ephem* ephem
                                                 double* const ax, double* const ay, double* const az) {
     if (!ephem || !ephem->ascii_planets) return ASSIST_ERROR_EPHEM_FILE;
     return planets_calc_gpu(ephem, jd_ref, jd_rel, body, GM, x, y, z, vx, vy, vz, ax, ay, az);
+}
+
+/* ---- the evaluator entry points of the reference's spk.h / ascii_ephem.h (src/spk.h:113-122, src/ascii_ephem.h:15-22).
+ * Same names, arguments and status codes; every value is computed by a CUDA launch. */
+
+static enum ASSIST_STATUS gpu_status(int rc) { return (enum ASSIST_STATUS)map_gpu_error(rc); }
+
+struct mpos_s assist_spk_target_pos(const struct spk_s* pl, const struct spk_target* target, double jd_ref, double jd_rel) {
+    struct mpos_s pos;
+    const double nan = NAN;
+    for (int i = 0; i < 3; i++) pos.u[i] = pos.v[i] = pos.w[i] = nan;
+    if (!pl || !target) return pos;
+    double out[9];
+    if (ab_gpu_spk_target_eval((struct spk_s*)pl, (int)(target - pl->targets), -1, jd_ref, jd_rel, 0, NULL, out)) {
+        fprintf(stderr, "(ASSIST) %s\n", assist_gpu_last_error());
+        return pos;
+    }
+    for (int i = 0; i < 3; i++) { pos.u[i] = out[i]; pos.v[i] = out[3 + i]; pos.w[i] = out[6 + i]; }
+    return pos;
+}
+
+enum ASSIST_STATUS assist_spk_calc(const struct spk_s* pl, double jd_ref, double jd_rel, int m, double* GM,
+                                   double* out_x, double* out_y, double* out_z) {
+    if (pl == NULL) return ASSIST_ERROR_AST_FILE;
+    if (m < 0 || m >= pl->num) return ASSIST_ERROR_NAST;
+    const struct spk_target* target = &pl->targets[m];
+    if (jd_ref + jd_rel < target->beg || jd_ref + jd_rel > target->end) return ASSIST_ERROR_COVERAGE;
+    *GM = target->mass;
+    double out[9];
+    const int rc = ab_gpu_spk_target_eval((struct spk_s*)pl, m, -1, jd_ref, jd_rel, 2, NULL, out);
+    if (rc) return gpu_status(rc);
+    *out_x = out[0]; *out_y = out[1]; *out_z = out[2];
+    return ASSIST_SUCCESS;
+}
+
+enum ASSIST_STATUS assist_spk_calc_planets(const struct assist_ephem* ephem, double jd_ref, double jd_rel, int code, double* GM,
+                                           double* out_x, double* out_y, double* out_z, double* out_vx, double* out_vy, double* out_vz,
+                                           double* out_ax, double* out_ay, double* out_az) {
+    if (!ephem) return ASSIST_ERROR_NEPHEM;
+    struct spk_s* pl = ephem->spk_planets;
+    if (!pl) return ASSIST_ERROR_NEPHEM;
+    const struct spk_target* target = assist_spk_find_target(pl, code);
+    if (target == NULL) return ASSIST_ERROR_NEPHEM;
+    if (jd_ref + jd_rel < target->beg || jd_ref + jd_rel > target->end) return ASSIST_ERROR_COVERAGE;
+    *GM = target->mass;
+    int emb_index = -1;
+    if (code == 301 || code == 399) {       /* relative to the Earth-Moon barycentre (reference src/spk.c:572-587) */
+        const struct spk_target* emb = NULL;
+        if (ephem->spk_emb_index >= 0 && ephem->spk_emb_index < pl->num && pl->targets[ephem->spk_emb_index].code == 3) emb = &pl->targets[ephem->spk_emb_index];
+        else emb = assist_spk_find_target(pl, 3);
+        if (!emb) return ASSIST_ERROR_NEPHEM;
+        emb_index = (int)(emb - pl->targets);
+    }
+    const double au = ephem->AU, seconds_per_day = 86400.;
+    const double ud[3] = {au, au / seconds_per_day, au / (seconds_per_day * seconds_per_day)};
+    double out[9];
+    const int rc = ab_gpu_spk_target_eval(pl, (int)(target - pl->targets), emb_index, jd_ref, jd_rel, 1, ud, out);
+    if (rc) return gpu_status(rc);
+    *out_x = out[0]; *out_y = out[1]; *out_z = out[2];
+    *out_vx = out[3]; *out_vy = out[4]; *out_vz = out[5];
+    *out_ax = out[6]; *out_ay = out[7]; *out_az = out[8];
+    return ASSIST_SUCCESS;
+}
+
+enum ASSIST_STATUS assist_ascii_calc(struct ascii_s* pl, double jd_ref, double jd_rel, int body, double* const GM,
+                                     double* const x, double* const y, double* const z,
+                                     double* const vx, double* const vy, double* const vz,
+                                     double* const ax, double* const ay, double* const az) {
+    if (!pl) return ASSIST_ERROR_EPHEM_FILE;
+    /* a bare file handle: wrap it the way assist_ephem_init does for the planets provider */
+    struct assist_ephem tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    tmp.ascii_planets = pl;
+    tmp.planets_source = FILE_FORMAT_ASCII_BIN;
+    tmp.jd_ref = 0.0;
+    tmp.AU = pl->AU; tmp.EMRAT = pl->cem;
+    for (int k = 0; k < ASSIST_BODY_NPLANETS; k++) tmp.spk_target_index[k] = -1;
+    tmp.spk_emb_index = -1;
+    return planets_calc_gpu(&tmp, jd_ref, jd_rel, body, GM, x, y, z, vx, vy, vz, ax, ay, az);
+}
+
+void assist_ascii_work(double* P, int ncm, int ncf, int niv, double t0, double t1, double* u, double* v, double* w) {
+    double out[9];
+    if (ab_gpu_ascii_work(P, ncm, ncf, niv, t0, t1, out)) {
+        fprintf(stderr, "(ASSIST) %s\n", assist_gpu_last_error());
+        for (int m = 0; m < ncm && m < 3; m++) u[m] = v[m] = w[m] = NAN;
+        return;
+    }
+    for (int m = 0; m < ncm; m++) { u[m] = out[m]; v[m] = out[ncm + m]; w[m] = out[2 * ncm + m]; }
 }
 
 /* ---- attach / detach (reference src/assist.c:379-501) --------------------- */

@@ -24,6 +24,10 @@ void ab_host_pre_timestep_marker(struct reb_simulation* r);
 int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int exact_finish_time, long max_steps, int flags);
 int ab_gpu_batch_update_params(assist_gpu_batch* b, const double* params);
 int ab_gpu_batch_get_last_state(assist_gpu_batch* b, double* state, double* acc);
+struct spk_s;
+int ab_gpu_spk_target_eval(struct spk_s* file, int target_index, int emb_index, double jd_ref, double jd_rel,
+                           int mode, const double* ud, double* out);
+int ab_gpu_ascii_work(const double* P, int ncm, int ncf, int niv, double t0, double t1, double* out);
 /* frees the cached descriptor block of an SPK file (struct spk_s::b200_host_desc) */
 void ab_spk_desc_free(void* desc);
 

@@ -51,7 +51,9 @@ __device__ double ab_sqrt7(double a) {
     double x = 1.;
     for (int k = 0; k < 20; k++) {
         double x6 = x * x * x * x * x * x;
-        x += AB_DIVK(a / x6 - x, 7.);
+        const double xn = x + AB_DIVK(a / x6 - x, 7.);
+        if (xn == x) break;      /* a fixed point: the remaining iterations of REBOUND's 20 would reproduce it */
+        x = xn;
     }
     return x * scale;
 }

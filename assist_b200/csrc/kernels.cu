@@ -109,6 +109,56 @@ __global__ void force_eval_kernel(const __grid_constant__ AbEphem E, const __gri
         for (int c = 0; c < 3; c++) acc[(i * K + j) * 3 + c] = S.a[j][c];
     status[i] = B.status;
 }
+
+/* One SPK target at one time, straight from the packed image (reference src/spk.c:492-547 assist_spk_target_pos,
+ * :405-481 assist_spk_calc, :590-597 unit conversion).  mode 0: the file's units (km, km/s, km/s^2);
+ * mode 1: AU, AU/day, AU/day^2 with the divisors u_d / u_rd, `emb` added first when has_emb (targets 399 / 301);
+ * mode 2: position / 149597870.7 (the small-body convention).  out[9] = u[3] v[3] w[3]. */
+__global__ void spk_target_kernel(const double* __restrict__ img, const AbSpkTarget tg, int has_emb, const AbSpkTarget emb,
+                                  double jd_ref, double t, int mode, double ud0, double ud1, double ud2,
+                                  double* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double u[3], v[3], w[3];
+    ab_spk_target_pos<2>(img, tg, jd_ref, t, u, v, w);
+    if (has_emb) {
+        double e[3], ev[3], ew[3];
+        ab_spk_target_pos<2>(img, emb, jd_ref, t, e, ev, ew);
+        for (int i = 0; i < 3; i++) { u[i] += e[i]; v[i] += ev[i]; w[i] += ew[i]; }
+    }
+    for (int i = 0; i < 3; i++) {
+        if (mode == 1) { u[i] = u[i] / ud0; v[i] = v[i] / ud1; w[i] = w[i] / ud2; }
+        else if (mode == 2) { u[i] = AB_DIVK(u[i], 149597870.7); }
+        out[i] = u[i]; out[3 + i] = v[i]; out[6 + i] = w[i];
+    }
+}
+
+/* One column of a DE-binary record given by the caller (reference src/ascii_ephem.c:27-65 assist_ascii_work):
+ * P[niv][ncm][ncf] coefficients, t0 the fraction of the record, t1 its length in days.  out[3][ncm]. */
+__global__ void ascii_work_kernel(const double* __restrict__ P, int ncm, int ncf, int niv, double t0, double t1,
+                                  double* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double T[32], S[32], U[32];
+    const double t = t0 * (double)niv;
+    const int b = (int)t;
+    const double z = 2.0 * (t - (double)b) - 1.0;          /* == 2 fmod(t, 1) - 1 for t >= 0, exactly */
+    const double c = (double)(niv * 2) / t1 / 86400.0;
+    T[0] = 1.0; T[1] = z; S[0] = 0.0; S[1] = 1.0; U[0] = 0.0; U[1] = 0.0; U[2] = 4.0;
+    for (int p = 2; p < ncf; p++) {
+        T[p] = 2.0 * z * T[p - 1] - T[p - 2];
+        S[p] = 2.0 * z * S[p - 1] + 2.0 * T[p - 1] - S[p - 2];
+    }
+    for (int p = 3; p < ncf; p++) U[p] = 2.0 * z * U[p - 1] + 4.0 * S[p - 1] - U[p - 2];
+    for (int m = 0; m < ncm; m++) {
+        double u = 0.0, v = 0.0, w = 0.0;
+        const int n = ncf * (m + b * ncm);
+        for (int p = 0; p < ncf; p++) {
+            u += T[p] * P[n + p];
+            v += S[p] * P[n + p] * c;
+            w += U[p] * P[n + p] * c * c;
+        }
+        out[m] = u; out[ncm + m] = v; out[2 * ncm + m] = w;
+    }
+}
 #endif  /* AB_TU == 0 */
 
 #if AB_TU == 1 || AB_TU == 2
@@ -757,6 +807,16 @@ cudaError_t AB_CAT2(ab_launch_force_eval, AB_SFX)(const AbEphem& E, const AbForc
                                                   const double* state, const double* params, double* acc, int* status, cudaStream_t st) {
     const int grid = (n + AB_BLOCK - 1) / AB_BLOCK;
     force_eval_kernel<<<grid, AB_BLOCK, 0, st>>>(E, F, n, K, t, t_per_system, state, params, acc, status);
+    return cudaGetLastError();
+}
+cudaError_t AB_CAT2(ab_launch_spk_target, AB_SFX)(const double* img, const AbSpkTarget& tg, int has_emb, const AbSpkTarget& emb, double jd_ref, double t,
+                                                  int mode, const double* ud, double* out, cudaStream_t st) {
+    spk_target_kernel<<<1, 32, 0, st>>>(img, tg, has_emb, emb, jd_ref, t, mode, ud[0], ud[1], ud[2], out);
+    return cudaGetLastError();
+}
+
+cudaError_t AB_CAT2(ab_launch_ascii_work, AB_SFX)(const double* P, int ncm, int ncf, int niv, double t0, double t1, double* out, cudaStream_t st) {
+    ascii_work_kernel<<<1, 32, 0, st>>>(P, ncm, ncf, niv, t0, t1, out);
     return cudaGetLastError();
 }
 #endif

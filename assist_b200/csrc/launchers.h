@@ -21,6 +21,11 @@
     cudaError_t ab_launch_force_eval_##sfx(const AbEphem& E, const AbForceOpts& F, int n, int K, const double* t,  \
                                            int t_per_system, const double* state, const double* params,            \
                                            double* acc, int* status, cudaStream_t st);                             \
+    cudaError_t ab_launch_spk_target_##sfx(const double* img, const AbSpkTarget& tg, int has_emb, const AbSpkTarget& emb, \
+                                           double jd_ref, double t, int mode, const double* ud, double* out,         \
+                                           cudaStream_t st);                                                        \
+    cudaError_t ab_launch_ascii_work_##sfx(const double* P, int ncm, int ncf, int niv, double t0, double t1,          \
+                                           double* out, cudaStream_t st);                                            \
     cudaError_t ab_launch_pp_integrate_k1_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt,         \
                                                 double tmax, int exact, int resume, long long step_cap,            \
                                                 const int* active, int n_active, cudaStream_t st);                 \

@@ -30,6 +30,7 @@
 #include <stddef.h>
 #include <stdio.h>
 #include <math.h>
+#include <sys/time.h>      /* REBOUND's header brings struct timeval along (reference unit_tests/benchmark/problem.c relies on it) */
 
 #ifdef __cplusplus
 extern "C" {

@@ -74,8 +74,8 @@ class EmulBatch:
         f.argtypes = [c_void_p, c_int, c_void_p, c_size_t]
         assert f(byref(self.opt), self.has_params, self.F, len(self.F)) == 0
         g = self.plib.ab_gpu_build_coop_plan_host
-        g.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p, c_size_t]
-        assert g(self.E, self.F, self.budget, self.P, len(self.P)) == 0
+        g.argtypes = [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_size_t]
+        assert g(ctypes.cast(self.ephem.ptr, c_void_p), self.E, self.F, self.budget, self.P, len(self.P)) == 0
 
     def set_state(self, t0, state, params=None, dt0=0.001):
         state = np.ascontiguousarray(state, dtype=np.float64).reshape(self.n, 6)

@@ -212,3 +212,17 @@ def test_packed_spk_copy_is_a_pure_rearrangement(lib, paths):
                 assert (dst[:, 2 + 3 * P:] == 0).all()
                 expect_words += nrec * Rp
         assert words.value == expect_words + 2 and (packed[expect_words:] == 0).all()
+
+
+def test_reference_programs_compile_and_link_unmodified():
+    """Every C program of the reference (unit_tests/*/problem.c, examples/*/problem.c) compiles UNMODIFIED against
+    include/ and links with the product library; only the two that need REBOUND's SimulationArchive do not
+    (SURVEY 8f rank 4).  Covers the header names spk.h / ascii_ephem.h / forces.h / tools.h and the evaluator
+    entry points of reference src/spk.h:113-122, src/ascii_ephem.h:15-22."""
+    import ref_programs
+    if not os.path.isdir(ref_programs.REF):
+        pytest.skip("needs the reference tree")
+    res = ref_programs.build_all()
+    assert len(res) >= 34
+    failed = {k for k, v in res.items() if not v[0]}
+    assert failed == ref_programs.NEED_ARCHIVE, {k: res[k][1] for k in failed}
