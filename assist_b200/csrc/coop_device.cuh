@@ -107,6 +107,16 @@
 
 namespace AB_NS {
 
+/* Launch-time copies in CONSTANT memory for the out-of-line fill routine: a kernel parameter reached through a
+ * reference is read with generic loads (hundreds of cycles each, one after the other in the record look-up); these
+ * are read through the constant cache.  The asteroid descriptors, which AbEphem keeps in global memory, come along. */
+static __constant__ AbEphem c_abcE;
+static __constant__ AbForceOpts c_abcF;
+static __constant__ AbSpkTarget c_abc_ast[AB_MAX_AST];
+#ifndef AB_HOST_EMUL
+extern __shared__ double abc_shared[];
+#endif
+
 /* What the force routines of forces_device.cuh see as "body table": one node of one slot in shared memory. */
 struct AbcRow {
     const double* p;
@@ -163,6 +173,7 @@ struct AbcArgs {
     int n_times;
     double* out;
     AbcPlan plan;
+    unsigned long long* timing;      /* optional: 16 cycle counters of the phases (coop_roles.cuh, ABC_TICK) */
 };
 
 /* ------------------------------------------------------------------------------------------ */
@@ -197,171 +208,127 @@ __device__ int abc_coverage(const AbEphem& E, double t_first, double t_last) {
  * particle-independent EIH sums of their node, warps 8-15 the other asteroids of the same slots.
  * Lane = 8 * (slot within the warp's four) + node.
  *
- * Every series is an SPK type-2 target (DE-binary planets: see the one-time path below).  The eight node times of a slot
- * fall into one, two, seldom more consecutive records of a target, and consecutive records are contiguous in the
- * packed image.  So the eight lanes of a slot copy that range (16-byte loads, every lane different pieces: up to seven
- * independent loads in flight per lane, no two lanes fetching the same bytes) into the slot's staging area, and each
- * lane evaluates its node from there.  Thirty-two lanes gathering from 32 records -- the access pattern of the
- * one-thread-per-system kernel -- becomes four coalesced range copies per warp.  The copy of series s + 1 is in
- * flight (in registers) while series s is evaluated.  What does not fit the pattern (nodes of a slot in different
- * segments, a range longer than the staging area, a record larger than it) is read straight from the image by the
- * lanes concerned, with the one-time routine.  Arithmetic per (series, time) is that of ephem_device.cuh. */
-#define ABC_FILL_PRE 7              /* 16-byte pieces a lane keeps in flight: staging areas of up to 112 doubles per slot */
-
-#ifdef AB_HOST_EMUL
-#define ABC_WARPSYNC()
-#define ABC_XDECL int wx_seg[32], wx_rec[32];
-#define ABC_XPUT(l, n, b) { wx_seg[l] = (n); wx_rec[l] = (b); }
-#define ABC_XSEG(selfval, src) wx_seg[src]
-#define ABC_XREC(selfval, src) wx_rec[src]
-#else
-#define ABC_WARPSYNC() __syncwarp()
-#define ABC_XDECL
-#define ABC_XPUT(l, n, b)
-#define ABC_XSEG(selfval, src) __shfl_sync(0xffffffffu, (selfval), (src))
-#define ABC_XREC(selfval, src) __shfl_sync(0xffffffffu, (selfval), (src))
-#endif
-
+ * The kernel is bound by the latency of each warp's own dependent chain (16 warps per SM, FP64 results 8 cycles
+ * apart), so a lane evaluates FOUR series side by side: four record look-ups, four MID loads and four Chebyshev
+ * recurrences in flight at once, 16-byte coefficient loads from the packed image (the eight node-lanes of a slot
+ * read the same one or two records: the loads of a warp touch a handful of lines).  Arithmetic per (series, time) is
+ * that of ephem_device.cuh: same sums, same order.
+ * (A variant that copied the records of a slot cooperatively into shared memory first measured slower: the copy and
+ * its bookkeeping cost more instructions than the gather it avoided.) */
 struct AbcSeriesRef {
     const double* img;
     const AbSpkTarget* tg;
-    int kind;              /* 0 EMB, 1 Sun (with velocity), 2 planet `idx`, 3 asteroid `idx` */
+    int kind;              /* 0 EMB, 2 planet `idx`, 3 asteroid `idx`, -1 none */
     int idx;
 };
 
-struct AbcFillLane {
-    double t;
-    int active;
-    int seg, rec, staged, lo, k;          /* series being evaluated: segment / record of this lane's node, staged range */
-    int nseg, nrec, nstaged, nlo, nk;     /* series being fetched */
-    double2 pre[ABC_FILL_PRE];
-    double emb[3];
-};
-
-/* series s of a warp's list */
-__device__ __forceinline__ AbcSeriesRef abc_series_ref(const AbEphem& E, const AbcPlan& plan, bool planets_half, int s) {
+/* series s of a warp's list: EMB, Mercury .. Pluto (the Sun is evaluated on its own, with velocity), then asteroids */
+__device__ __forceinline__ AbcSeriesRef abc_series_ref(int ast_split, bool planets_half, int s, int s_end) {
+    const AbEphem& E = c_abcE;
     AbcSeriesRef r;
-    if (planets_half && s < 1 + AB_NPLANETS) {
+    if (s >= s_end) { r.img = E.spka_img; r.tg = &c_abc_ast[0]; r.kind = -1; r.idx = 0; return r; }
+    if (planets_half && s < AB_NPLANETS) {
         r.img = E.spkp_img;
         if (s == 0) { r.kind = 0; r.idx = -1; r.tg = &E.p_tgt[E.emb_index]; }
-        else { r.idx = s - 1; r.kind = (s == 1) ? 1 : 2; r.tg = &E.p_tgt[E.p_index[s - 1]]; }
+        else { r.idx = s; r.kind = 2; r.tg = &E.p_tgt[E.p_index[s]]; }
     } else {
-        const int m = planets_half ? (s - 1 - AB_NPLANETS) : (plan.ast_split + s);
-        r.img = E.spka_img; r.kind = 3; r.idx = m; r.tg = &E.a_tgt[m];
+        const int m = planets_half ? (s - AB_NPLANETS) : (ast_split + s);
+        r.img = E.spka_img; r.kind = 3; r.idx = m; r.tg = &c_abc_ast[m];
     }
     return r;
 }
 
-/* where the nodes of every slot lie in series R, and the copy of that range into registers */
-__device__ __forceinline__ void abc_fill_fetch(const AbcSeriesRef& R, double jd_ref, AbcFillLane* L, int cap) {
-    ABC_XDECL
-    const AbSpkTarget& tg = *R.tg;
-    ABC_LANES(l) {
-        AbcFillLane& q = L[ABC_LI(l)];
-        int n = 0, b = 0;
-        if (q.active) {
-            n = ab_spk_segment(tg, jd_ref, q.t);
-            const AbSpkSeg& sg = tg.seg[n];
-            b = (int)ab_divc((jd_ref - sg.jul_init) + q.t, sg.intlen_d, sg.intlen_rd);
-            if (b > sg.nrec - 1) b = sg.nrec - 1;
-            if (b < 0) b = 0;
-        }
-        q.nseg = n; q.nrec = b;
-        ABC_XPUT(l, n, b)
-    }
-    ABC_WARPSYNC();
-    ABC_LANES(l) {
-        AbcFillLane& q = L[ABC_LI(l)];
-        const int g = l & ~7;
-        const int n0 = ABC_XSEG(q.nseg, g), b0 = ABC_XREC(q.nrec, g), n7 = ABC_XSEG(q.nseg, g + 7), b7 = ABC_XREC(q.nrec, g + 7);
-        q.nstaged = 0; q.nlo = 0; q.nk = 0;
-        if (q.active && n0 == n7) {
-            const AbSpkSeg& sg = tg.seg[n0];
-            const int cnt = (b0 < b7 ? b7 - b0 : b0 - b7) + 1;
-            int k = cap / sg.R;
-            if (k > cnt) k = cnt;
-            if (k >= 1) {
-                q.nstaged = 1; q.nlo = b0 < b7 ? b0 : b7; q.nk = k;
-                const double2* src = reinterpret_cast<const double2*>(R.img + (sg.one - 1) + (long long)q.nlo * sg.R);
-                const int chunks = (k * sg.R) >> 1;
+/* Position sums (file units) of four series at time t, the four recurrences side by side. */
+__device__ __forceinline__ void abc_quad_eval(const AbcSeriesRef* R, double jd_ref, double t, double (*u)[3]) {
+    const double2* q[4];
+    int P[4];
+    double z[4], T1[4], T2[4], a0[4], a1[4], a2[4];
+    int Pmax = 0;
 #pragma unroll
-                for (int i = 0; i < ABC_FILL_PRE; i++) {
-                    const int c = (l & 7) + 8 * i;
-                    if (c < chunks) q.pre[i] = __ldg(src + c);
+    for (int s = 0; s < 4; s++) {
+        if (R[s].kind < 0) { P[s] = 0; z[s] = 0.0; q[s] = nullptr; continue; }      /* past the end of the list */
+        const AbSpkTarget& tg = *R[s].tg;
+        const AbSpkSeg& sg = tg.seg[ab_spk_segment(tg, jd_ref, t)];
+        double c;
+        const double* cf = ab_spk_record_in(R[s].img, sg, jd_ref, t, &z[s], &c);
+        q[s] = reinterpret_cast<const double2*>(cf);
+        P[s] = sg.P;
+        if (P[s] > Pmax) Pmax = P[s];
+    }
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        /* p = 0 (T = 1) and p = 1 (T = z) */
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        if (P[s] > 0) {
+            const double2 A = __ldg(q[s]), B = __ldg(q[s] + 1), C = __ldg(q[s] + 2);      /* x0 y0 | z0 x1 | y1 z1 */
+            s0 += A.x * 1.0; s1 += A.y * 1.0; s2 += B.x * 1.0;
+            s0 += B.y * z[s]; s1 += C.x * z[s]; s2 += C.y * z[s];
+        }
+        a0[s] = s0; a1[s] = s1; a2[s] = s2;
+        T2[s] = 1.0; T1[s] = z[s];
+    }
+#pragma unroll 1
+    for (int p = 2; p < Pmax; p += 2) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            if (p < P[s]) {
+                const double2* qq = q[s] + 3 * (p >> 1);
+                const double2 A = __ldg(qq), B = __ldg(qq + 1);                          /* xp yp | zp xp+1 */
+                const double Ta = 2.0 * z[s] * T1[s] - T2[s];
+                a0[s] += A.x * Ta; a1[s] += A.y * Ta; a2[s] += B.x * Ta;
+                if (p + 1 < P[s]) {      /* an odd number of terms: the second half of the last pair is padding */
+                    const double2 C = __ldg(qq + 2);                                      /* yp+1 zp+1 */
+                    const double Tb = 2.0 * z[s] * Ta - T1[s];
+                    a0[s] += B.y * Tb; a1[s] += C.x * Tb; a2[s] += C.y * Tb;
+                    T2[s] = Ta; T1[s] = Tb;
                 }
             }
         }
     }
-}
-
-/* registers -> the slot's staging area; the fetched series becomes the current one */
-__device__ __forceinline__ void abc_fill_stage(const AbcSeriesRef& R, AbcFillLane* L, double* wbuf, int cap) {
-    ABC_LANES(l) {
-        AbcFillLane& q = L[ABC_LI(l)];
-        if (q.nstaged) {
-            double2* dst = reinterpret_cast<double2*>(wbuf + (l >> 3) * cap);
-            const int chunks = (q.nk * R.tg->seg[q.nseg].R) >> 1;
 #pragma unroll
-            for (int i = 0; i < ABC_FILL_PRE; i++) {
-                const int c = (l & 7) + 8 * i;
-                if (c < chunks) dst[c] = q.pre[i];
-            }
-        }
-        q.seg = q.nseg; q.rec = q.nrec; q.staged = q.nstaged; q.lo = q.nlo; q.k = q.nk;
-    }
+    for (int s = 0; s < 4; s++) { u[s][0] = a0[s]; u[s][1] = a1[s]; u[s][2] = a2[s]; }
 }
 
-/* Chebyshev sums of this lane's node for series R (file units) and what becomes of them */
-__device__ __forceinline__ void abc_fill_eval(const AbEphem& E, const AbcSeriesRef& R, double jd_ref, AbcFillLane& q, const double* sbuf, double* tb) {
-    const AbSpkTarget& tg = *R.tg;
-    double u[3], uv[3] = {0.0, 0.0, 0.0}, uw[3];
-    if (q.staged && q.rec >= q.lo && q.rec < q.lo + q.k) {
-        const AbSpkSeg& sg = tg.seg[q.seg];
-        const double* rec = sbuf + (q.rec - q.lo) * sg.R;
-        const double jul_mid = rec[0];
-        double z, c;
-        if (sg.uniform) {
-            z = ab_divc((jd_ref - jul_mid) + q.t, sg.radius_d, sg.radius_rd);
-            c = sg.radius_inv;
-        } else {
-            const double radius = rec[1];
-            z = ((jd_ref - jul_mid) + q.t) / AB_DIVK(radius, 86400.0);
-            c = 1.0 / radius;
-        }
-        if (R.kind == 1) ab_cheb3<1, true, false>(rec + 2, sg.P, z, c, u, uv, uw);
-        else ab_cheb3<0, true, false>(rec + 2, sg.P, z, c, u, uv, uw);
-    } else {
-        if (R.kind == 1) ab_spk_target_pos<1>(R.img, tg, jd_ref, q.t, u, uv, uw);
-        else ab_spk_target_pos<0>(R.img, tg, jd_ref, q.t, u, uv, uw);
-    }
+/* what becomes of the sums of one series: EMB kept, planets and asteroids into the table */
+__device__ __forceinline__ void abc_fill_store(const AbcSeriesRef& R, double* u, double* emb, double* tb) {
+    const AbEphem& E = c_abcE;
     if (R.kind == 0) {
-        q.emb[0] = u[0]; q.emb[1] = u[1]; q.emb[2] = u[2];
+        emb[0] = u[0]; emb[1] = u[1]; emb[2] = u[2];
     } else if (R.kind == 3) {
         /* heliocentric position / 149597870.7 (reference src/spk.c:470); the Sun is added after the barrier */
         const int b = AB_NPLANETS + R.idx;
         tb[ABC_E_POS(b, 0) * ABC_SLOTS] = AB_DIVK(u[0], 149597870.7);
         tb[ABC_E_POS(b, 1) * ABC_SLOTS] = AB_DIVK(u[1], 149597870.7);
         tb[ABC_E_POS(b, 2) * ABC_SLOTS] = AB_DIVK(u[2], 149597870.7);
-    } else {
+    } else if (R.kind == 2) {
         const int b = R.idx;
-        if (b == 3 || b == 4) { u[0] += q.emb[0]; u[1] += q.emb[1]; u[2] += q.emb[2]; }    /* relative to the EMB (reference src/spk.c:572-587) */
+        if (b == 3 || b == 4) { u[0] += emb[0]; u[1] += emb[1]; u[2] += emb[2]; }    /* relative to the EMB (reference src/spk.c:572-587) */
         tb[ABC_E_POS(b, 0) * ABC_SLOTS] = ab_divc(u[0], E.u_d[0], E.u_rd[0]);
         tb[ABC_E_POS(b, 1) * ABC_SLOTS] = ab_divc(u[1], E.u_d[0], E.u_rd[0]);
         tb[ABC_E_POS(b, 2) * ABC_SLOTS] = ab_divc(u[2], E.u_d[0], E.u_rd[0]);
-        if (R.kind == 1) {
-            tb[ABC_E_SVEL(0) * ABC_SLOTS] = ab_divc(uv[0], E.u_d[1], E.u_rd[1]);
-            tb[ABC_E_SVEL(1) * ABC_SLOTS] = ab_divc(uv[1], E.u_d[1], E.u_rd[1]);
-            tb[ABC_E_SVEL(2) * ABC_SLOTS] = ab_divc(uv[2], E.u_d[1], E.u_rd[1]);
-        }
     }
 }
 
-__device__ __noinline__ void abc_fill_warp(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, const AbcPlan& plan, int warp) {
+#ifdef AB_HOST_EMUL
+#define ABC_SM_HERE(sm) const AbcSmem& sm = *ctx->sm
+#else
+#define ABC_SM_HERE(sm) AbcSmem sm; sm.d = abc_shared; sm.i = reinterpret_cast<int*>(abc_shared + ABC_SM_DOUBLES)
+#endif
+
+struct AbcFillLane {
+    double t;
+    int active;
+    double emb[3];
+};
+
+__device__ __noinline__ void abc_fill_warp(ABC_CTXARG int ast_split, int cap_p, int cap_a, int warp) {
+    const AbEphem& E = c_abcE;
+    const AbForceOpts& F = c_abcF;
+    ABC_SM_HERE(sm);
+    (void)cap_p; (void)cap_a;
     AbcFillLane L[ABC_NL];
     const double jd_ref = E.jd_ref;
     const bool planets_half = (warp < 8);
-    const int cap = planets_half ? plan.cap_p : plan.cap_a;
-    double* wbuf = sm.d + ABC_SM_STAGE + (planets_half ? warp * 4 * plan.cap_p : 32 * plan.cap_p + (warp - 8) * 4 * plan.cap_a);
     ABC_LANES(l) {
         AbcFillLane& q = L[ABC_LI(l)];
         const int slot = 4 * (warp & 7) + (l >> 3);
@@ -375,15 +342,16 @@ __device__ __noinline__ void abc_fill_warp(const AbEphem& E, const AbForceOpts& 
     bool spk_regular = (E.planets_source != AB_SRC_ASCII) && E.emb_index >= 0;
     for (int b = 0; b < AB_NPLANETS && spk_regular; b++) if (E.p_index[b] < 0) spk_regular = false;
     int s_first = 0;
-    if (planets_half && !spk_regular) {
-        /* DE-binary planets or a kernel without Earth / EMB target: the one-time routines, lane by lane */
+    if (planets_half) {
         ABC_LANES(l) {
             AbcFillLane& q = L[ABC_LI(l)];
             if (q.active) {
                 const int slot = 4 * (warp & 7) + (l >> 3);
                 double* tb = sm.tab(l & 7, slot);
                 int err = AB_OK;
-                for (int b = 0; b < AB_NPLANETS; b++) {
+                /* the Sun with its velocity; every planet when the layout is unusual (DE-binary planets, a kernel
+                 * without Earth or EMB target): the one-time routines */
+                for (int b = 0; b < (spk_regular ? 1 : AB_NPLANETS); b++) {
                     double GM, x[3], v[3], a[3];
                     int flag;
                     if (b == 0) {
@@ -398,26 +366,23 @@ __device__ __noinline__ void abc_fill_warp(const AbEphem& E, const AbForceOpts& 
                 if (err != AB_OK) sm.flag(ABC_SMI_ERR, slot) = err;      /* the lanes of a slot may race: every value written is a valid code */
             }
         }
-        s_first = 1 + AB_NPLANETS;
+        if (!spk_regular) s_first = AB_NPLANETS;
     }
-    const int s_end = planets_half ? (1 + AB_NPLANETS + plan.ast_split) : (E.n_ast - plan.ast_split);
-    if (s_first < s_end) {
-        AbcSeriesRef cur = abc_series_ref(E, plan, planets_half, s_first);
-        abc_fill_fetch(cur, jd_ref, L, cap);
-        for (int s = s_first; s < s_end; s++) {
-            abc_fill_stage(cur, L, wbuf, cap);
-            ABC_WARPSYNC();
-            AbcSeriesRef nxt = cur;
-            if (s + 1 < s_end) {      /* the next range travels while this one is evaluated */
-                nxt = abc_series_ref(E, plan, planets_half, s + 1);
-                abc_fill_fetch(nxt, jd_ref, L, cap);
+    const int s_end = planets_half ? (AB_NPLANETS + ast_split) : (E.n_ast - ast_split);
+#pragma unroll 1
+    for (int s = s_first; s < s_end; s += 4) {
+        AbcSeriesRef R[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) R[j] = abc_series_ref(ast_split, planets_half, s + j, s_end);
+        ABC_LANES(l) {
+            AbcFillLane& q = L[ABC_LI(l)];
+            if (q.active) {
+                double u[4][3];
+                abc_quad_eval(R, jd_ref, q.t, u);
+                double* tb = sm.tab(l & 7, 4 * (warp & 7) + (l >> 3));
+#pragma unroll
+                for (int j = 0; j < 4; j++) abc_fill_store(R[j], u[j], q.emb, tb);
             }
-            ABC_LANES(l) {
-                AbcFillLane& q = L[ABC_LI(l)];
-                if (q.active) abc_fill_eval(E, cur, jd_ref, q, wbuf + (l >> 3) * cap, sm.tab(l & 7, 4 * (warp & 7) + (l >> 3)));
-            }
-            ABC_WARPSYNC();
-            cur = nxt;
         }
     }
     /* particle-independent EIH sums of the Sun at this node (ab_fill_nodes, same operations): the lane reads back
@@ -511,25 +476,17 @@ __device__ __forceinline__ void abc_task_bodies(const AbEphem& E, const AbForceO
         const double prefac = GM[n] / (_r[n] * _r[n] * _r[n]);
         const double p0 = prefac * dx[n], p1 = prefac * dy[n], p2 = prefac * dz[n];
         if (abc_body_on(i, F.forces)) { sm.prod(i, 0, slot) = p0; sm.prod(i, 1, slot) = p1; sm.prod(i, 2, slot) = p2; }
-        if (PLANETS) {
-            const double qv = GM[n] / _r[n];
-            if (eih) sm.q(i, slot) = qv;
-        }
+        if (PLANETS && i < AB_NPLANETS && eih) sm.q(i, slot) = GM[n] / _r[n];
     }
 }
 
-template <bool PLANETS>
+/* The group of a worker warp, one body after the other through the same few hundred bytes of code: nine warps walk
+ * through it at the same time, so it is fetched once per SM and not once per warp (the kernel's hot code has to fit
+ * the instruction cache: unrolled per-warp variants of this loop made the force phase twice as long). */
 __device__ __forceinline__ void abc_task_group(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, const double* tb,
-                                               const AbcWorkerPlan& wp, int slot) {
-    switch (wp.nbody) {
-        case 1: abc_task_bodies<1, PLANETS>(E, F, sm, tb, wp.body, slot); break;
-        case 2: abc_task_bodies<2, PLANETS>(E, F, sm, tb, wp.body, slot); break;
-        case 3: abc_task_bodies<3, PLANETS>(E, F, sm, tb, wp.body, slot); break;
-        case 4: abc_task_bodies<4, PLANETS>(E, F, sm, tb, wp.body, slot); break;
-        case 5: abc_task_bodies<5, PLANETS>(E, F, sm, tb, wp.body, slot); break;
-        case 6: abc_task_bodies<6, PLANETS>(E, F, sm, tb, wp.body, slot); break;
-        default: break;
-    }
+                                            const AbcWorkerPlan& wp, int slot) {
+#pragma unroll 1
+    for (int n = 0; n < wp.nbody; n++) abc_task_bodies<1, true>(E, F, sm, tb, wp.body + n, slot);
 }
 
 /* EIH source block of the Sun for the real particle (reference src/forces.c:1319-1501 with j = 0), everything
@@ -642,6 +599,7 @@ __device__ void abc_run_task(const AbEphem& E, const AbForceOpts& F, const AbcSm
 
 struct AbcComp {
     double pos, vel, acc, x0, v0, a0, csx, csv, at;
+    double hx, hv;         /* head of the next prediction (abc_predict_stages) */
     double b[7], g[7], e[7], csb[7];
 };
 
@@ -683,30 +641,35 @@ __device__ __forceinline__ double abc_sum_forces(const AbEphem& E, const AbForce
     return a;
 }
 
-/* ab_predict for one component held in registers */
+/* ab_predict for one component held in registers, in stages: stage j = 6..0 multiplies the running sum into the
+ * next power of h and adds b_{j-1} (a0 for j = 0); "final" adds v0 and x0.  An update at node n changes b_0..b_{n-1}
+ * only, so the stages 6..n+1 of the prediction for node n + 1 are formed BEFORE the forces of node n have arrived
+ * (abc_predict_head, while the workers are busy) and the rest after the update (abc_predict_tail).  Same operations
+ * in the same order as the one-piece form (ias15_device.cuh: ab_predict). */
+__device__ __forceinline__ void abc_predict_stages(const AbcComp& s, double h, int from, int to, double& px, double& pv) {
+    if (from >= 6 && 6 >= to) { px = AB_DIVK(s.b[6] * 7. * h, 9.) + s.b[5];   pv = s.b[6] * 7. * h / 8. + s.b[5]; }
+    if (from >= 5 && 5 >= to) { px = px * 3. * h / 4. + s.b[4];               pv = AB_DIVK(pv * 6. * h, 7.) + s.b[4]; }
+    if (from >= 4 && 4 >= to) { px = AB_DIVK(px * 5. * h, 7.) + s.b[3];       pv = AB_DIVK(pv * 5. * h, 6.) + s.b[3]; }
+    if (from >= 3 && 3 >= to) { px = AB_DIVK(px * 2. * h, 3.) + s.b[2];       pv = AB_DIVK(pv * 4. * h, 5.) + s.b[2]; }
+    if (from >= 2 && 2 >= to) { px = AB_DIVK(px * 3. * h, 5.) + s.b[1];       pv = pv * 3. * h / 4. + s.b[1]; }
+    if (from >= 1 && 1 >= to) { px = px * h / 2. + s.b[0];                    pv = AB_DIVK(pv * 2. * h, 3.) + s.b[0]; }
+    if (from >= 0 && 0 >= to) { px = AB_DIVK(px * h, 3.) + s.a0;              pv = pv * h / 2. + s.a0; }
+}
+
+__device__ __forceinline__ void abc_predict_final(const AbcComp& s, double h, double dt, double px, double pv, double& xk_out, double& vk_out) {
+    px = px * dt * h / 2. + s.v0;
+    const double xk = -s.csx + px * dt * h;
+    xk_out = xk + s.x0;
+    const double vk = -s.csv + pv * dt * h;
+    vk_out = vk + s.v0;
+}
+
+/* the whole prediction at node nn */
 __device__ __forceinline__ void abc_predict(const AbcComp& s, int nn, double dt, double& xk_out, double& vk_out) {
     const double h = c_h[nn];
-    const double b0 = s.b[0], b1 = s.b[1], b2 = s.b[2], b3 = s.b[3], b4 = s.b[4], b5 = s.b[5], b6 = s.b[6];
-    const double x0 = s.x0, v0 = s.v0, a0 = s.a0, csx = s.csx, csv = s.csv;
-    double px = AB_DIVK(b6 * 7. * h, 9.) + b5;
-    px = px * 3. * h / 4. + b4;
-    px = AB_DIVK(px * 5. * h, 7.) + b3;
-    px = AB_DIVK(px * 2. * h, 3.) + b2;
-    px = AB_DIVK(px * 3. * h, 5.) + b1;
-    px = px * h / 2. + b0;
-    px = AB_DIVK(px * h, 3.) + a0;
-    px = px * dt * h / 2. + v0;
-    const double xk = -csx + px * dt * h;
-    xk_out = xk + x0;
-    double pv = b6 * 7. * h / 8. + b5;
-    pv = AB_DIVK(pv * 6. * h, 7.) + b4;
-    pv = AB_DIVK(pv * 5. * h, 6.) + b3;
-    pv = AB_DIVK(pv * 4. * h, 5.) + b2;
-    pv = pv * 3. * h / 4. + b1;
-    pv = AB_DIVK(pv * 2. * h, 3.) + b0;
-    pv = pv * h / 2. + a0;
-    const double vk = -csv + pv * dt * h;
-    vk_out = vk + v0;
+    double px = 0.0, pv = 0.0;
+    abc_predict_stages(s, h, 6, 0, px, pv);
+    abc_predict_final(s, h, dt, px, pv, xk_out, vk_out);
 }
 
 #define ABC_DIVRR(x, k) ab_divc((x), c_rr[k], c_rri[k])
@@ -793,7 +756,7 @@ __device__ __forceinline__ double abc_update_gb(AbcComp& s, int nn, double at) {
 __device__ __forceinline__ void abc_attempt_begin(AbcComp& s) {
     s.x0 = s.pos; s.v0 = s.vel; s.a0 = s.acc;
     const double b0 = s.b[0], b1 = s.b[1], b2 = s.b[2], b3 = s.b[3], b4 = s.b[4], b5 = s.b[5], b6 = s.b[6];
-    for (int j = 0; j < 7; j++) s.csb[j] = 0.;
+    s.csb[0] = 0.; s.csb[1] = 0.; s.csb[2] = 0.; s.csb[3] = 0.; s.csb[4] = 0.; s.csb[5] = 0.; s.csb[6] = 0.;
     s.g[0] = b6 * c_d[15] + b5 * c_d[10] + b4 * c_d[6] + b3 * c_d[3] + b2 * c_d[1] + b1 * c_d[0] + b0;
     s.g[1] = b6 * c_d[16] + b5 * c_d[11] + b4 * c_d[7] + b3 * c_d[4] + b2 * c_d[2] + b1;
     s.g[2] = b6 * c_d[17] + b5 * c_d[12] + b4 * c_d[8] + b3 * c_d[5] + b2;
@@ -803,10 +766,14 @@ __device__ __forceinline__ void abc_attempt_begin(AbcComp& s) {
     s.g[6] = b6;
 }
 
-/* ab_predict_next for one component: (se, sb) -> s.e, s.b */
-__device__ __forceinline__ void abc_predict_next(AbcComp& s, double ratio, const double* se, const double* sb) {
+/* ab_predict_next for one component: (e_j, b_j given as scalars) -> s.e, s.b.  Scalars, not pointers: an array whose
+ * address is taken would put the whole register state of the component warps into local memory. */
+__device__ __forceinline__ void abc_predict_next(AbcComp& s, double ratio,
+                                                 double se0, double se1, double se2, double se3, double se4, double se5, double se6,
+                                                 double _b0, double _b1, double _b2, double _b3, double _b4, double _b5, double _b6) {
     if (ratio > 20.) {
-        for (int j = 0; j < 7; j++) { s.e[j] = 0.; s.b[j] = 0.; }
+        s.e[0] = 0.; s.e[1] = 0.; s.e[2] = 0.; s.e[3] = 0.; s.e[4] = 0.; s.e[5] = 0.; s.e[6] = 0.;
+        s.b[0] = 0.; s.b[1] = 0.; s.b[2] = 0.; s.b[3] = 0.; s.b[4] = 0.; s.b[5] = 0.; s.b[6] = 0.;
         return;
     }
     const double q1 = ratio;
@@ -816,14 +783,13 @@ __device__ __forceinline__ void abc_predict_next(AbcComp& s, double ratio, const
     const double q5 = q2 * q3;
     const double q6 = q3 * q3;
     const double q7 = q3 * q4;
-    const double _b0 = sb[0], _b1 = sb[1], _b2 = sb[2], _b3 = sb[3], _b4 = sb[4], _b5 = sb[5], _b6 = sb[6];
-    const double be0 = _b0 - se[0];
-    const double be1 = _b1 - se[1];
-    const double be2 = _b2 - se[2];
-    const double be3 = _b3 - se[3];
-    const double be4 = _b4 - se[4];
-    const double be5 = _b5 - se[5];
-    const double be6 = _b6 - se[6];
+    const double be0 = _b0 - se0;
+    const double be1 = _b1 - se1;
+    const double be2 = _b2 - se2;
+    const double be3 = _b3 - se3;
+    const double be4 = _b4 - se4;
+    const double be5 = _b5 - se5;
+    const double be6 = _b6 - se6;
     const double e0 = q1 * (_b6 * 7.0 + _b5 * 6.0 + _b4 * 5.0 + _b3 * 4.0 + _b2 * 3.0 + _b1 * 2.0 + _b0);
     const double e1 = q2 * (_b6 * 21.0 + _b5 * 15.0 + _b4 * 10.0 + _b3 * 6.0 + _b2 * 3.0 + _b1);
     const double e2 = q3 * (_b6 * 35.0 + _b5 * 20.0 + _b4 * 10.0 + _b3 * 4.0 + _b2);
@@ -873,6 +839,7 @@ __device__ __forceinline__ void abc_comp_load(const AbBatch& W, long long ws, in
     s.x0 = ABC_W1(W.x0, c); s.v0 = ABC_W1(W.v0, c); s.a0 = ABC_W1(W.a0, c);
     s.csx = ABC_W1(W.csx, c); s.csv = ABC_W1(W.csv, c);
     s.at = 0.0;
+#pragma unroll
     for (int j = 0; j < 7; j++) {
         s.b[j] = ABC_W7(W.b, j, c); s.g[j] = ABC_W7(W.g, j, c); s.e[j] = ABC_W7(W.e, j, c); s.csb[j] = ABC_W7(W.csb, j, c);
     }
@@ -883,6 +850,7 @@ __device__ __forceinline__ void abc_comp_store(const AbBatch& W, long long ws, i
     ABC_W1(W.pos, c) = s.pos; ABC_W1(W.vel, c) = s.vel; ABC_W1(W.acc, c) = s.acc;
     ABC_W1(W.x0, c) = s.x0; ABC_W1(W.v0, c) = s.v0; ABC_W1(W.a0, c) = s.a0;
     ABC_W1(W.csx, c) = s.csx; ABC_W1(W.csv, c) = s.csv;
+#pragma unroll
     for (int j = 0; j < 7; j++) {
         ABC_W7(W.b, j, c) = s.b[j]; ABC_W7(W.g, j, c) = s.g[j]; ABC_W7(W.e, j, c) = s.e[j]; ABC_W7(W.csb, j, c) = s.csb[j];
     }

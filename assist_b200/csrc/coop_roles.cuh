@@ -34,6 +34,14 @@
 
 namespace AB_NS {
 
+/* Optional phase timing (A.timing != NULL): the control warp passes every barrier, so the time between two barrier
+ * exits is the length of a phase of the CTA.  Lane 0 adds the cycles to 16 global counters (scratch/phase_times.py). */
+#ifdef AB_HOST_EMUL
+#define ABC_TICK(slot_) do { } while (0)
+#else
+#define ABC_TICK(slot_) do { if (A.timing && (threadIdx.x & 31) == 0) { const long long now_ = clock64(); tacc[slot_] += (unsigned long long)(now_ - tlast); tlast = now_; } } while (0)
+#endif
+
 #define ABC_ERR_BUDGET 7      /* index into assist_error_messages: step budget exhausted / dt == 0 */
 
 struct AbcCtl {
@@ -161,6 +169,11 @@ __device__ bool abc_bookkeeping(const AbcArgs& A, AbcCtl& C, long long slot) {
 __device__ void abc_control_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F, const AbcArgs& A, const AbcSmem& sm) {
     AbcCtl ctl[ABC_NL];
     const AbBatch& W = A.W;
+#ifndef AB_HOST_EMUL
+    unsigned long long tacc[16];
+    for (int q = 0; q < 16; q++) tacc[q] = 0ULL;
+    long long tlast = clock64();
+#endif
     ABC_LANES(l) {
         AbcCtl& C = ctl[ABC_LI(l)];
         C.have = C.pending = C.exhausted = C.integrating = C.in_step = C.have_a0 = false;
@@ -200,11 +213,19 @@ __device__ void abc_control_main(ABC_CTXARG const AbEphem& E, const AbForceOpts&
             sm.dt(l) = C.P.dt;
             if (C.have || C.pending) alive = 1;
         }
-        if (!ABC_SYNC_OR(alive)) return;                                         /* B1 */
-        abc_fill_warp(E, F, sm, A.plan, ABC_CTRL_WARP);
+        if (!ABC_SYNC_OR(alive)) {                                               /* B1 */
+#ifndef AB_HOST_EMUL
+            if (A.timing && (threadIdx.x & 31) == 0) for (int q = 0; q < 16; q++) atomicAdd(A.timing + q, tacc[q]);
+#endif
+            return;
+        }
+        ABC_TICK(0);
+        abc_fill_warp(ABC_CTXPASS A.plan.ast_split, A.plan.cap_p, A.plan.cap_a, ABC_CTRL_WARP);
         ABC_SYNC();                                                              /* B2 */
+        ABC_TICK(1);
         ABC_LANES(l) { abc_fill_shift(E, sm, ABC_CTRL_WARP, l); }
         ABC_SYNC();                                                              /* B3 */
+        ABC_TICK(2);
         int anya0 = 0;
         ABC_LANES(l) {
             AbcCtl& C = ctl[ABC_LI(l)];
@@ -230,16 +251,31 @@ __device__ void abc_control_main(ABC_CTXARG const AbEphem& E, const AbForceOpts&
             }
         }
         const bool a0_round = ABC_SYNC_OR(anya0);                                /* B4 */
+        ABC_TICK(3);
         if (a0_round) {
             ABC_SYNC();                                                          /* B5 */
+            ABC_TICK(6);
             ABC_SYNC();                                                          /* B6 */
+            ABC_TICK(5);
+#ifndef AB_HOST_EMUL
+            tacc[11]++;
+#endif
         }
+#ifndef AB_HOST_EMUL
+        tacc[10]++;
+#endif
         for (;;) {
             for (int nn = 1; nn < 8; nn++) {
                 ABC_SYNC();                                                      /* B7 */
+                ABC_TICK(6);
                 ABC_SYNC();                                                      /* B8 */
+                ABC_TICK(5);
+#ifndef AB_HOST_EMUL
+                tacc[11]++;
+#endif
             }
             ABC_SYNC();                                                          /* B9 */
+            ABC_TICK(6);
             int more = 0;
             ABC_LANES(l) {
                 AbcCtl& C = ctl[ABC_LI(l)];
@@ -267,7 +303,9 @@ __device__ void abc_control_main(ABC_CTXARG const AbEphem& E, const AbForceOpts&
                     sm.flag(ABC_SMI_SW, l) = cont ? 1 : 0;
                 }
             }
-            if (!ABC_SYNC_OR(more)) break;                                       /* B10 */
+            const bool again = ABC_SYNC_OR(more);                                /* B10 */
+            ABC_TICK(7);
+            if (!again) break;
         }
         /* step-size control (per system: adaptive_mode 1 over the real particle) */
         ABC_LANES(l) {
@@ -318,7 +356,9 @@ __device__ void abc_control_main(ABC_CTXARG const AbEphem& E, const AbForceOpts&
             }
         }
         ABC_SYNC();                                                              /* B11 */
+        ABC_TICK(8);
         ABC_SYNC();                                                              /* B12 */
+        ABC_TICK(9);
     }
 }
 
@@ -330,7 +370,7 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
     const long long wn = W.n;
     for (;;) {
         if (!ABC_SYNC_OR(0)) return;                                             /* B1 */
-        abc_fill_warp(E, F, sm, A.plan, c);
+        abc_fill_warp(ABC_CTXPASS A.plan.ast_split, A.plan.cap_p, A.plan.cap_a, c);
         ABC_SYNC();                                                              /* B2 */
         ABC_LANES(l) { abc_fill_shift(E, sm, c, l); }
         ABC_SYNC();                                                              /* B3 */
@@ -370,6 +410,17 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
         for (;;) {
             for (int nn = 1; nn < 8; nn++) {
                 ABC_SYNC();                                                      /* B7 */
+                if (nn < 6) {
+                    /* while the workers evaluate node nn: the part of the prediction for node nn + 1 that the
+                     * coming update cannot change (it touches b_0 .. b_{nn-1}) */
+                    ABC_LANES(l) {
+                        if (sm.flag(ABC_SMI_SW, l)) {
+                            AbcComp& s = st[ABC_LI(l)];
+                            s.hx = 0.0; s.hv = 0.0;
+                            abc_predict_stages(s, c_h[nn + 1], 6, nn + 1, s.hx, s.hv);
+                        }
+                    }
+                }
                 ABC_SYNC();                                                      /* B8 */
                 ABC_LANES(l) {
                     if (sm.flag(ABC_SMI_SW, l)) {
@@ -379,7 +430,10 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
                         const double db6 = abc_update_gb(s, nn, at);
                         if (nn < 7) {
                             double xk, vk;
-                            abc_predict(s, nn + 1, sm.dt(l), xk, vk);
+                            const double h = c_h[nn + 1];
+                            double px = s.hx, pv = s.hv;
+                            abc_predict_stages(s, h, (nn < 6) ? nn : 6, 0, px, pv);
+                            abc_predict_final(s, h, sm.dt(l), px, pv, xk, vk);
                             sm.xv(c, l) = xk; sm.xv(3 + c, l) = vk;
                         } else {
                             sm.mon(c, l) = fabs(at);
@@ -408,14 +462,18 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
                 const int dec = sm.flag(ABC_SMI_DEC, l);
                 if (dec == 1) {
                     abc_advance(s, sm.dt(l));
+#pragma unroll
                     for (int j = 0; j < 7; j++) { ABC_W7(W.er, j, c) = s.e[j]; ABC_W7(W.br, j, c) = s.b[j]; }
-                    abc_predict_next(s, sm.ratio(l), s.e, s.b);
+                    abc_predict_next(s, sm.ratio(l), s.e[0], s.e[1], s.e[2], s.e[3], s.e[4], s.e[5], s.e[6],
+                                     s.b[0], s.b[1], s.b[2], s.b[3], s.b[4], s.b[5], s.b[6]);
                 } else {
                     s.pos = s.x0; s.vel = s.v0; s.acc = s.a0;
                     if (dec == 2) {
-                        double er[7], br[7];
-                        for (int j = 0; j < 7; j++) { er[j] = ABC_W7(W.er, j, c); br[j] = ABC_W7(W.br, j, c); }
-                        abc_predict_next(s, sm.ratio(l), er, br);
+                        abc_predict_next(s, sm.ratio(l),
+                                         ABC_W7(W.er, 0, c), ABC_W7(W.er, 1, c), ABC_W7(W.er, 2, c), ABC_W7(W.er, 3, c),
+                                         ABC_W7(W.er, 4, c), ABC_W7(W.er, 5, c), ABC_W7(W.er, 6, c),
+                                         ABC_W7(W.br, 0, c), ABC_W7(W.br, 1, c), ABC_W7(W.br, 2, c), ABC_W7(W.br, 3, c),
+                                         ABC_W7(W.br, 4, c), ABC_W7(W.br, 5, c), ABC_W7(W.br, 6, c));
                     }
                 }
                 abc_comp_store(W, ws, c, s);
@@ -431,10 +489,7 @@ __device__ __forceinline__ void abc_worker_tasks(const AbEphem& E, const AbForce
                                                  int widx, int node, int which_flag, int l) {
     if (!sm.flag(which_flag, l)) return;
     const AbcWorkerPlan& wp = A.plan.w[widx];
-    if (wp.nbody) {
-        if (wp.planets) abc_task_group<true>(E, F, sm, sm.tab(node, l), wp, l);
-        else abc_task_group<false>(E, F, sm, sm.tab(node, l), wp, l);
-    }
+    if (wp.nbody) abc_task_group(E, F, sm, sm.tab(node, l), wp, l);
     if (wp.scalar[0] != ABC_T_NONE) abc_run_task(E, F, sm, node, l, wp.scalar[0]);
     if (wp.scalar[1] != ABC_T_NONE) abc_run_task(E, F, sm, node, l, wp.scalar[1]);
 }
@@ -443,7 +498,7 @@ __device__ void abc_worker_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& 
     const int widx = warp - ABC_FIRST_WORKER;
     for (;;) {
         if (!ABC_SYNC_OR(0)) return;                                             /* B1 */
-        abc_fill_warp(E, F, sm, A.plan, warp);
+        abc_fill_warp(ABC_CTXPASS A.plan.ast_split, A.plan.cap_p, A.plan.cap_a, warp);
         ABC_SYNC();                                                              /* B2 */
         ABC_LANES(l) { abc_fill_shift(E, sm, warp, l); }
         ABC_SYNC();                                                              /* B3 */

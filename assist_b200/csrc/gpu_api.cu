@@ -1012,10 +1012,39 @@ static void build_coop_plan(const struct assist_ephem* e, const AbEphem& E, cons
     if (cap_p + cap_a > 194) { cap_p = bank_friendly(Rp_need); }
     if (cap_p + cap_a > 194) { cap_a = bank_friendly(maxRa); }
     if (cap_p + cap_a > 194) { cap_p = 90; cap_a = 102; }      /* oversized records are read straight from the image */
+    if (getenv("ASSIST_B200_FILL_CAP")) { cap_p = atoi(getenv("ASSIST_B200_FILL_CAP")); cap_a = cap_p; }      /* experiments: 0 = no staging */
+    if (getenv("ASSIST_B200_FILL_CAP_P")) cap_p = atoi(getenv("ASSIST_B200_FILL_CAP_P"));
+    if (getenv("ASSIST_B200_FILL_CAP_A")) cap_a = atoi(getenv("ASSIST_B200_FILL_CAP_A"));
     if (cap_p > 8 * 2 * ABC_FILL_PRE_HOST) cap_p = 8 * 2 * ABC_FILL_PRE_HOST - 6;
     if (cap_a > 8 * 2 * ABC_FILL_PRE_HOST) cap_a = 8 * 2 * ABC_FILL_PRE_HOST - 6;
     plan->cap_p = cap_p; plan->cap_a = cap_a;
     plan->attempt_budget = budget;
+}
+
+/* host copy of the asteroid descriptors (masses refreshed by build_ephem) for the kernel's constant memory */
+static const AbSpkTarget* coop_ast_tg(const struct assist_ephem* e) {
+    if (!e || !e->spk_asteroids || !e->spk_asteroids->b200_host_desc) return nullptr;
+    return ((const AbSpkDesc*)e->spk_asteroids->b200_host_desc)->tg.data();
+}
+
+/* ASSIST_B200_COOP_TIMING=1: 16 device counters of the kernel's phases, printed to stderr after every launch */
+static unsigned long long* g_coop_timing = nullptr;
+static unsigned long long* coop_timing(assist_gpu_batch* b) {
+    (void)b;
+    if (!getenv("ASSIST_B200_COOP_TIMING")) return nullptr;
+    if (!g_coop_timing) { if (cudaMalloc((void**)&g_coop_timing, 16 * sizeof(unsigned long long)) != cudaSuccess) return nullptr; }
+    cudaMemsetAsync(g_coop_timing, 0, 16 * sizeof(unsigned long long), 0);
+    return g_coop_timing;
+}
+static void coop_timing_report(assist_gpu_batch* b) {
+    if (!g_coop_timing || !getenv("ASSIST_B200_COOP_TIMING")) return;
+    unsigned long long t[16];
+    if (cudaMemcpy(t, g_coop_timing, sizeof(t), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    static const char* nm[10] = {"bookkeeping", "fill", "shift", "fill-check", "-", "workers", "components", "convergence", "dt-control", "advance+store"};
+    double tot = 0; for (int q = 0; q < 10; q++) tot += (double)t[q];
+    fprintf(stderr, "[assist-b200 coop timing] grid %d, attempts/CTA %.0f, evals/CTA %.0f, cycles/CTA %.3e\n", b->coop_grid,
+            (double)t[10] / b->coop_grid, (double)t[11] / b->coop_grid, tot / b->coop_grid);
+    for (int q = 0; q < 10; q++) if (q != 4) fprintf(stderr, "    %-14s %5.1f %%   %9.0f cycles per attempt\n", nm[q], 100.0 * t[q] / tot, (double)t[q] / (double)(t[10] ? t[10] : 1));
 }
 
 static int ensure_coop_batch(assist_gpu_batch* b, bool fast) {
@@ -1092,9 +1121,11 @@ extern "C" int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int 
             build_coop_plan(b->ephem, E, F, b->attempt_budget, &plan);
             CU(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), 0));
             CU(cudaEventRecord(b->ev0, 0));
-            e = fast ? ab_launch_pp_coop_fast(E, F, b->d, b->wc, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, &plan, b->coop_grid, 0)
-                     : ab_launch_pp_coop_strict(E, F, b->d, b->wc, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, &plan, b->coop_grid, 0);
-            return finish_launch(b, e, "pp_coop");
+            e = fast ? ab_launch_pp_coop_fast(E, F, b->d, b->wc, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, &plan, coop_ast_tg(b->ephem), coop_timing(b), b->coop_grid, 0)
+                     : ab_launch_pp_coop_strict(E, F, b->d, b->wc, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, &plan, coop_ast_tg(b->ephem), coop_timing(b), b->coop_grid, 0);
+            rc = finish_launch(b, e, "pp_coop");
+            coop_timing_report(b);
+            return rc;
         }
         if (b->sched_queue) {
             /* work-queue scheduling: a resident grid of threads pulls systems until the queue is empty */
@@ -1201,8 +1232,8 @@ extern "C" int assist_gpu_batch_integrate_or_interpolate(assist_gpu_batch* b, co
         build_coop_plan(b->ephem, E, F, b->attempt_budget, &plan);
         CU(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), 0));
         CU(cudaEventRecord(b->ev0, 0));
-        e = fastm ? ab_launch_pp_coop_fast(E, F, b->d, b->wc, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, &plan, b->coop_grid, 0)
-                  : ab_launch_pp_coop_strict(E, F, b->d, b->wc, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, &plan, b->coop_grid, 0);
+        e = fastm ? ab_launch_pp_coop_fast(E, F, b->d, b->wc, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, &plan, coop_ast_tg(b->ephem), coop_timing(b), b->coop_grid, 0)
+                  : ab_launch_pp_coop_strict(E, F, b->d, b->wc, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, &plan, coop_ast_tg(b->ephem), coop_timing(b), b->coop_grid, 0);
     } else if (b->sched_queue) {
         rc = ensure_working_batch(b);
         if (rc) return rc;

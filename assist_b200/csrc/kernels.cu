@@ -764,7 +764,6 @@ __global__ void sh_interpolate_kernel(const __grid_constant__ AbBatch Bt, double
 /* ------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(ABC_THREADS, 1)
 pp_coop_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F, const __grid_constant__ AbcArgs A) {
-    extern __shared__ double abc_shared[];
     AbcSmem sm;
     sm.d = abc_shared;
     sm.i = reinterpret_cast<int*>(abc_shared + ABC_SM_DOUBLES);
@@ -905,12 +904,20 @@ cudaError_t AB_CAT2(ab_pp_coop_max_grid, AB_SFX)(int* max_grid) {
 
 cudaError_t AB_CAT2(ab_launch_pp_coop, AB_SFX)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const AbBatch& W, double tmax, int exact,
                                                unsigned long long* queue_head, const AbSlices& SL, const double* times, int n_times, double* out,
-                                               const void* plan, int grid, cudaStream_t st) {
+                                               const void* plan, const AbSpkTarget* host_ast_tg, unsigned long long* timing, int grid, cudaStream_t st) {
     if (grid < 1) return cudaSuccess;
+    {   /* launch-time constants of the fill routine (see coop_device.cuh) */
+        cudaError_t ec;
+        if ((ec = cudaMemcpyToSymbolAsync(c_abcE, &E, sizeof(AbEphem), 0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return ec;
+        if ((ec = cudaMemcpyToSymbolAsync(c_abcF, &F, sizeof(AbForceOpts), 0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return ec;
+        if (host_ast_tg && E.n_ast > 0 &&
+            (ec = cudaMemcpyToSymbolAsync(c_abc_ast, host_ast_tg, sizeof(AbSpkTarget) * E.n_ast, 0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return ec;
+    }
     AbcArgs A;
     A.Bt = Bt; A.W = W; A.tmax = tmax; A.exact_finish_time = exact; A.queue_head = queue_head; A.SL = SL;
     A.times = times; A.n_times = n_times; A.out = out;
     A.plan = *reinterpret_cast<const AbcPlan*>(plan);
+    A.timing = timing;
     cudaError_t e = cudaFuncSetAttribute(pp_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ABC_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     pp_coop_kernel<<<grid, ABC_THREADS, ABC_SMEM_BYTES, st>>>(E, F, A);

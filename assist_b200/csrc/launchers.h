@@ -14,7 +14,8 @@
     cudaError_t ab_pp_coop_max_grid_##sfx(int* max_grid);                                                           \
     cudaError_t ab_launch_pp_coop_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const AbBatch& W, \
                                         double tmax, int exact, unsigned long long* queue_head, const AbSlices& SL,  \
-                                        const double* times, int n_times, double* out, const void* plan, int grid,    \
+                                        const double* times, int n_times, double* out, const void* plan,              \
+                                        const AbSpkTarget* host_ast_tg, unsigned long long* timing, int grid,      \
                                         cudaStream_t st);                                                             \
     cudaError_t ab_launch_ephem_eval_##sfx(const AbEphem& E, const double* t, int n_t, double* out, int* status,   \
                                            cudaStream_t st);                                                        \

@@ -40,7 +40,9 @@ struct AbcEmulShared {
     pthread_barrier_t bar;
     int or_flag[2];
 };
+namespace ab_emul { struct AbcSmem; }
 struct AbcEmulCtx {
+    const ab_emul::AbcSmem* sm;
     int block;
     int warp;
     int phase;
@@ -168,6 +170,8 @@ extern "C" int abc_emul_run(void* h, const void* E_, const void* F_, const void*
     for (int k = 0; k < 28; k++) c_rri[k] = 1.0 / AB_RR[k];
     memcpy(c_c, AB_C, sizeof(AB_C));
     memcpy(c_d, AB_D, sizeof(AB_D));
+    c_abcE = E; c_abcF = F;
+    for (int m = 0; m < E.n_ast && m < AB_MAX_AST; m++) c_abc_ast[m] = E.a_tgt[m];
 
     AbcArgs A;
     hb->w.epsilon = hb->d.epsilon; hb->w.min_dt = hb->d.min_dt; hb->w.has_params = hb->d.has_params;
@@ -180,6 +184,7 @@ extern "C" int abc_emul_run(void* h, const void* E_, const void* F_, const void*
     A.SL.origin = 0.0; A.SL.wlen = 1.0; A.SL.n_win = 1; A.SL.done = done.data(); A.SL.epoch = epoch.data();
     A.times = times; A.n_times = n_times; A.out = out;
     A.plan = *(const AbcPlan*)plan_;
+    A.timing = nullptr;
     if (A.W.n < n_blocks * ABC_SLOTS) return -1;
 
     std::vector<AbcEmulShared> shared((size_t)n_blocks);
@@ -196,6 +201,7 @@ extern "C" int abc_emul_run(void* h, const void* E_, const void* F_, const void*
             j.E = &E; j.F = &F; j.A = &A;
             j.sm.d = smem[b].data();
             j.sm.i = (int*)(smem[b].data() + ABC_SM_DOUBLES);
+            j.ctx.sm = &j.sm;
         }
     }
     for (size_t k = 0; k < jobs.size(); k++) pthread_create(&th[k], NULL, warp_main, &jobs[k]);
