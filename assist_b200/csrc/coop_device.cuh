@@ -41,13 +41,11 @@
 #include "forces_device.cuh"
 #include "ias15_device.cuh"
 
-/* node table: entries of one (node, slot) */
-#define ABC_TAB_E 88
-#define ABC_NODE_STRIDE (ABC_TAB_E * ABC_SLOTS + 4)    /* +4: the 8 nodes of a slot fall into different banks (fill stores) */
+/* node table in shared memory: the planets' positions of one (node, slot).  What a single task reads (asteroid
+ * positions, the Sun's velocity, the particle-independent EIH sums) lives in the CTA's global table, device_types.h. */
+#define ABC_TAB_E 33
+#define ABC_NODE_STRIDE (ABC_TAB_E * ABC_SLOTS + 2)    /* +2: the (slot, node) lanes of a half-warp of the fill fall into 16 different banks */
 #define ABC_E_POS(i, c) ((i) * 3 + (c))
-#define ABC_E_SVEL(c) (81 + (c))
-#define ABC_E_TERM1 84
-#define ABC_E_AR(c) (85 + (c))
 
 /* contribution slots */
 #define ABC_C_NG 0
@@ -60,22 +58,18 @@
 #define ABC_C_GRSIMPLE 24
 #define ABC_NCON 27
 
-/* shared-memory carve-up (doubles first, then ints).  XV .. EXTRA are free while the node tables are being filled
- * and double as the staging area of the coefficient records (ABC_SM_STAGE); the total is the 227 KB a CTA can have. */
+/* shared-memory carve-up (doubles first, then ints): 102 KB, so that two CTAs fit an SM */
 #define ABC_SM_TAB 0
 #define ABC_SM_XV (ABC_SM_TAB + 8 * ABC_NODE_STRIDE)
 #define ABC_SM_PROD (ABC_SM_XV + 6 * ABC_SLOTS)
 #define ABC_SM_Q (ABC_SM_PROD + 81 * ABC_SLOTS)
 #define ABC_SM_CON (ABC_SM_Q + 11 * ABC_SLOTS)
 #define ABC_SM_MON (ABC_SM_CON + ABC_NCON * ABC_SLOTS)       /* |a| x3, |db6| x3, |b6| x3 */
-#define ABC_SM_EXTRA (ABC_SM_MON + 9 * ABC_SLOTS)            /* staging only */
-#define ABC_SM_PRM (ABC_SM_EXTRA + 1920)
+#define ABC_SM_PRM (ABC_SM_MON + 9 * ABC_SLOTS)
 #define ABC_SM_T0 (ABC_SM_PRM + 3 * ABC_SLOTS)               /* start time of the attempt */
 #define ABC_SM_DT (ABC_SM_T0 + ABC_SLOTS)                    /* step of the attempt */
 #define ABC_SM_RATIO (ABC_SM_DT + ABC_SLOTS)                 /* predict_next ratio */
 #define ABC_SM_DOUBLES (ABC_SM_RATIO + ABC_SLOTS)
-#define ABC_SM_STAGE ABC_SM_XV
-#define ABC_STAGE_DOUBLES (ABC_SM_PRM - ABC_SM_XV)           /* 6208: 32 slots x (cap_p + cap_a), cap_p + cap_a <= 194 */
 #define ABC_SMI_ACTIVE 0      /* slot takes part in this attempt */
 #define ABC_SMI_NEEDA0 1      /* slot needs the force evaluation at the start of the step */
 #define ABC_SMI_SW 2          /* slot is still sweeping */
@@ -83,7 +77,8 @@
 #define ABC_SMI_NGON 4        /* Marsden term active for this slot */
 #define ABC_SMI_ERR 5         /* ephemeris status of the fill */
 #define ABC_SM_INTS (6 * ABC_SLOTS)
-#define ABC_SMEM_BYTES ((size_t)ABC_SM_DOUBLES * 8 + (size_t)ABC_SM_INTS * 4)
+#define ABC_SMEM_GROUP_BYTES ((size_t)ABC_SM_DOUBLES * 8 + (size_t)ABC_SM_INTS * 4)
+#define ABC_SMEM_BYTES (ABC_GROUPS * ABC_SMEM_GROUP_BYTES)
 
 #ifdef AB_HOST_EMUL
 #define ABC_NL 32
@@ -99,13 +94,23 @@
 #define ABC_LANES(l) for (int l = (int)(threadIdx.x & 31), once_ = 1; once_; once_ = 0)
 #define ABC_LI(l) 0
 #define ABC_SYNC() __syncthreads()
-#define ABC_SYNC_OR(p) (__syncthreads_or(p) != 0)
+#define ABC_SYNC_OR(p) abc_sync_or(p)
 #define ABC_CTXARG
 #define ABC_CTXPASS
-#define ABC_BLOCK ((int)blockIdx.x)
+#define ABC_BLOCK ((int)blockIdx.x * ABC_GROUPS + (int)(threadIdx.x / (32 * ABC_GWARPS)))     /* index of the group */
 #endif
 
 namespace AB_NS {
+
+#ifndef AB_HOST_EMUL
+/* __syncthreads_or whose result passes through a volatile local: ptxas (12.9) otherwise REMATERIALISES the predicate
+ * where it is live across a region of high register pressure -- by executing the barrier a second time (seen in the
+ * SASS of the component warps: BAR.RED.OR twice, first result dropped), which desynchronises the CTA. */
+__device__ __forceinline__ bool abc_sync_or(int p) {
+    volatile int keep = __syncthreads_or(p);
+    return keep != 0;
+}
+#endif
 
 /* Launch-time copies in CONSTANT memory for the out-of-line fill routine: a kernel parameter reached through a
  * reference is read with generic loads (hundreds of cycles each, one after the other in the record look-up); these
@@ -113,6 +118,7 @@ namespace AB_NS {
 static __constant__ AbEphem c_abcE;
 static __constant__ AbForceOpts c_abcF;
 static __constant__ AbSpkTarget c_abc_ast[AB_MAX_AST];
+static __constant__ AbcPlan c_abcP;
 #ifndef AB_HOST_EMUL
 extern __shared__ double abc_shared[];
 #endif
@@ -127,21 +133,23 @@ struct AbcRows {
     int stride;       /* doubles between consecutive rows */
     __device__ __forceinline__ AbcRow operator[](int i) const { return AbcRow{base + i * stride}; }
 };
-struct AbcScalars {
-    const double* base;
-    __device__ __forceinline__ double operator[](int) const { return *base; }
+/* the Sun's velocity of one (node, slot): in the CTA's global table, read where a term needs it (Marsden, simple GR) */
+struct AbcVelG {
+    const double* g;
+    __device__ __forceinline__ double operator[](int c) const { return __ldcg(g + c * ABC_SLOTS); }
+};
+struct AbcVelRows {
+    AbcVelG s;
+    __device__ __forceinline__ AbcVelG operator[](int) const { return s; }
 };
 struct AbcTabView {
     const double* gm;
-    AbcRows pos, vel, eih_ar, eih_av;
-    AbcScalars eih_term1;
+    AbcRows pos;
+    AbcVelRows vel;
     double earth_acc[3];
-    __device__ __forceinline__ AbcTabView(const double* gm_, const double* node_slot) : gm(gm_) {
+    __device__ __forceinline__ AbcTabView(const double* gm_, const double* node_slot, const double* gt_node_slot) : gm(gm_) {
         pos.base = node_slot; pos.stride = 3 * ABC_SLOTS;
-        vel.base = node_slot + ABC_E_SVEL(0) * ABC_SLOTS; vel.stride = 0;
-        eih_ar.base = node_slot + ABC_E_AR(0) * ABC_SLOTS; eih_ar.stride = 0;
-        eih_av = eih_ar;
-        eih_term1.base = node_slot + ABC_E_TERM1 * ABC_SLOTS;
+        vel.s.g = gt_node_slot + ABC_GT_SVEL(0) * ABC_SLOTS;
         earth_acc[0] = earth_acc[1] = earth_acc[2] = 0.0;
     }
 };
@@ -173,6 +181,7 @@ struct AbcArgs {
     int n_times;
     double* out;
     AbcPlan plan;
+    double* gtab;                    /* [grid][ABC_GT_DOUBLES]: the CTAs' global tables */
     unsigned long long* timing;      /* optional: 16 cycle counters of the phases (coop_roles.cuh, ABC_TICK) */
 };
 
@@ -204,17 +213,17 @@ __device__ int abc_coverage(const AbEphem& E, double t_first, double t_last) {
     return AB_OK;
 }
 
-/* ---- the fill: thread = (slot, node); warps 0-7 take the planets, a few asteroids (plan.ast_split) and then the
- * particle-independent EIH sums of their node, warps 8-15 the other asteroids of the same slots.
- * Lane = 8 * (slot within the warp's four) + node.
+/* ---- the fill: thread = (slot, node), lane = 8 * (slot within the warp's four) + node.  A thread evaluates the Sun
+ * (with its velocity), then the EMB, the planets and the asteroids, then the particle-independent EIH sums of its
+ * node: everything one (slot, node) needs comes from one thread, so the fill has no barrier inside.
  *
- * The kernel is bound by the latency of each warp's own dependent chain (16 warps per SM, FP64 results 8 cycles
- * apart), so a lane evaluates FOUR series side by side: four record look-ups, four MID loads and four Chebyshev
- * recurrences in flight at once, 16-byte coefficient loads from the packed image (the eight node-lanes of a slot
- * read the same one or two records: the loads of a warp touch a handful of lines).  Arithmetic per (series, time) is
- * that of ephem_device.cuh: same sums, same order.
- * (A variant that copied the records of a slot cooperatively into shared memory first measured slower: the copy and
- * its bookkeeping cost more instructions than the gather it avoided.) */
+ * The coefficient records are read straight from the packed image with 16-byte loads (the eight node-lanes of a slot
+ * read the same one or two records: a warp's load touches a handful of lines).  With two CTAs' tables in shared memory
+ * the L1 is a few KB, i.e. every record comes from L2: a thread runs ABC_FILL_NS series side by side and loads the
+ * coefficients of the next pair of terms while it works on the current one.  Arithmetic per (series, time) is that of
+ * ephem_device.cuh: same sums, same order. */
+#define ABC_FILL_NS 2
+
 struct AbcSeriesRef {
     const double* img;
     const AbSpkTarget* tg;
@@ -222,30 +231,32 @@ struct AbcSeriesRef {
     int idx;
 };
 
-/* series s of a warp's list: EMB, Mercury .. Pluto (the Sun is evaluated on its own, with velocity), then asteroids */
-__device__ __forceinline__ AbcSeriesRef abc_series_ref(int ast_split, bool planets_half, int s, int s_end) {
+/* series s of the list: EMB, Mercury .. Pluto (the Sun is evaluated on its own, with velocity), then the asteroids */
+__device__ __forceinline__ AbcSeriesRef abc_series_ref(int s, int s_end) {
     const AbEphem& E = c_abcE;
     AbcSeriesRef r;
     if (s >= s_end) { r.img = E.spka_img; r.tg = &c_abc_ast[0]; r.kind = -1; r.idx = 0; return r; }
-    if (planets_half && s < AB_NPLANETS) {
+    if (s < AB_NPLANETS) {
         r.img = E.spkp_img;
         if (s == 0) { r.kind = 0; r.idx = -1; r.tg = &E.p_tgt[E.emb_index]; }
         else { r.idx = s; r.kind = 2; r.tg = &E.p_tgt[E.p_index[s]]; }
     } else {
-        const int m = planets_half ? (s - AB_NPLANETS) : (ast_split + s);
+        const int m = s - AB_NPLANETS;
         r.img = E.spka_img; r.kind = 3; r.idx = m; r.tg = &c_abc_ast[m];
     }
     return r;
 }
 
-/* Position sums (file units) of four series at time t, the four recurrences side by side. */
-__device__ __forceinline__ void abc_quad_eval(const AbcSeriesRef* R, double jd_ref, double t, double (*u)[3]) {
-    const double2* q[4];
-    int P[4];
-    double z[4], T1[4], T2[4], a0[4], a1[4], a2[4];
+/* Position sums (file units) of NS series at time t, the recurrences side by side, coefficients one pair of terms ahead. */
+template <int NS>
+__device__ __forceinline__ void abc_multi_eval(const AbcSeriesRef* R, double jd_ref, double t, double (*u)[3]) {
+    const double2* q[NS];
+    int P[NS];
+    double z[NS], T1[NS], T2[NS], a0[NS], a1[NS], a2[NS];
+    double2 cA[NS], cB[NS], cC[NS];
     int Pmax = 0;
 #pragma unroll
-    for (int s = 0; s < 4; s++) {
+    for (int s = 0; s < NS; s++) {
         if (R[s].kind < 0) { P[s] = 0; z[s] = 0.0; q[s] = nullptr; continue; }      /* past the end of the list */
         const AbSpkTarget& tg = *R[s].tg;
         const AbSpkSeg& sg = tg.seg[ab_spk_segment(tg, jd_ref, t)];
@@ -256,11 +267,16 @@ __device__ __forceinline__ void abc_quad_eval(const AbcSeriesRef* R, double jd_r
         if (P[s] > Pmax) Pmax = P[s];
     }
 #pragma unroll
-    for (int s = 0; s < 4; s++) {
+    for (int s = 0; s < NS; s++) {
         /* p = 0 (T = 1) and p = 1 (T = z) */
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        cA[s] = cB[s] = cC[s] = double2{0.0, 0.0};
         if (P[s] > 0) {
             const double2 A = __ldg(q[s]), B = __ldg(q[s] + 1), C = __ldg(q[s] + 2);      /* x0 y0 | z0 x1 | y1 z1 */
+            if (P[s] > 2) {
+                cA[s] = __ldg(q[s] + 3); cB[s] = __ldg(q[s] + 4);
+                if (P[s] > 3) cC[s] = __ldg(q[s] + 5);
+            }
             s0 += A.x * 1.0; s1 += A.y * 1.0; s2 += B.x * 1.0;
             s0 += B.y * z[s]; s1 += C.x * z[s]; s2 += C.y * z[s];
         }
@@ -269,37 +285,48 @@ __device__ __forceinline__ void abc_quad_eval(const AbcSeriesRef* R, double jd_r
     }
 #pragma unroll 1
     for (int p = 2; p < Pmax; p += 2) {
+        double2 nA[NS], nB[NS], nC[NS];
 #pragma unroll
-        for (int s = 0; s < 4; s++) {
+        for (int s = 0; s < NS; s++) {
+            nA[s] = nB[s] = nC[s] = double2{0.0, 0.0};
+            if (p + 2 < P[s]) {
+                const double2* qq = q[s] + 3 * ((p + 2) >> 1);
+                nA[s] = __ldg(qq); nB[s] = __ldg(qq + 1);                                /* xp yp | zp xp+1 */
+                if (p + 3 < P[s]) nC[s] = __ldg(qq + 2);                                  /* yp+1 zp+1 */
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
             if (p < P[s]) {
-                const double2* qq = q[s] + 3 * (p >> 1);
-                const double2 A = __ldg(qq), B = __ldg(qq + 1);                          /* xp yp | zp xp+1 */
+                const double2 A = cA[s], B = cB[s];
                 const double Ta = 2.0 * z[s] * T1[s] - T2[s];
                 a0[s] += A.x * Ta; a1[s] += A.y * Ta; a2[s] += B.x * Ta;
                 if (p + 1 < P[s]) {      /* an odd number of terms: the second half of the last pair is padding */
-                    const double2 C = __ldg(qq + 2);                                      /* yp+1 zp+1 */
+                    const double2 C = cC[s];
                     const double Tb = 2.0 * z[s] * Ta - T1[s];
                     a0[s] += B.y * Tb; a1[s] += C.x * Tb; a2[s] += C.y * Tb;
                     T2[s] = Ta; T1[s] = Tb;
                 }
             }
+            cA[s] = nA[s]; cB[s] = nB[s]; cC[s] = nC[s];
         }
     }
 #pragma unroll
-    for (int s = 0; s < 4; s++) { u[s][0] = a0[s]; u[s][1] = a1[s]; u[s][2] = a2[s]; }
+    for (int s = 0; s < NS; s++) { u[s][0] = a0[s]; u[s][1] = a1[s]; u[s][2] = a2[s]; }
 }
 
-/* what becomes of the sums of one series: EMB kept, planets and asteroids into the table */
-__device__ __forceinline__ void abc_fill_store(const AbcSeriesRef& R, double* u, double* emb, double* tb) {
+/* what becomes of the sums of one series: EMB kept, planets into shared memory, asteroids (heliocentric / 149597870.7,
+ * reference src/spk.c:470, + Sun, reference src/forces.c:213-219) into the global table */
+__device__ __forceinline__ void abc_fill_store(const AbcSeriesRef& R, double* u, double* emb, double* tb, double* g,
+                                               double sx, double sy, double sz) {
     const AbEphem& E = c_abcE;
     if (R.kind == 0) {
         emb[0] = u[0]; emb[1] = u[1]; emb[2] = u[2];
     } else if (R.kind == 3) {
-        /* heliocentric position / 149597870.7 (reference src/spk.c:470); the Sun is added after the barrier */
-        const int b = AB_NPLANETS + R.idx;
-        tb[ABC_E_POS(b, 0) * ABC_SLOTS] = AB_DIVK(u[0], 149597870.7);
-        tb[ABC_E_POS(b, 1) * ABC_SLOTS] = AB_DIVK(u[1], 149597870.7);
-        tb[ABC_E_POS(b, 2) * ABC_SLOTS] = AB_DIVK(u[2], 149597870.7);
+        const int m = R.idx;
+        g[ABC_GT_AST(m, 0) * ABC_SLOTS] = AB_DIVK(u[0], 149597870.7) + sx;
+        g[ABC_GT_AST(m, 1) * ABC_SLOTS] = AB_DIVK(u[1], 149597870.7) + sy;
+        g[ABC_GT_AST(m, 2) * ABC_SLOTS] = AB_DIVK(u[2], 149597870.7) + sz;
     } else if (R.kind == 2) {
         const int b = R.idx;
         if (b == 3 || b == 4) { u[0] += emb[0]; u[1] += emb[1]; u[2] += emb[2]; }    /* relative to the EMB (reference src/spk.c:572-587) */
@@ -312,130 +339,100 @@ __device__ __forceinline__ void abc_fill_store(const AbcSeriesRef& R, double* u,
 #ifdef AB_HOST_EMUL
 #define ABC_SM_HERE(sm) const AbcSmem& sm = *ctx->sm
 #else
-#define ABC_SM_HERE(sm) AbcSmem sm; sm.d = abc_shared; sm.i = reinterpret_cast<int*>(abc_shared + ABC_SM_DOUBLES)
+#define ABC_SM_HERE(sm) AbcSmem sm; sm.d = abc_shared + (threadIdx.x / (32 * ABC_GWARPS)) * (ABC_SMEM_GROUP_BYTES / 8); sm.i = reinterpret_cast<int*>(sm.d + ABC_SM_DOUBLES)
 #endif
 
-struct AbcFillLane {
-    double t;
-    int active;
-    double emb[3];
-};
-
-__device__ __noinline__ void abc_fill_warp(ABC_CTXARG int ast_split, int cap_p, int cap_a, int warp) {
+__device__ __noinline__ void abc_fill_warp(ABC_CTXARG double* gt, int warp) {
     const AbEphem& E = c_abcE;
     const AbForceOpts& F = c_abcF;
     ABC_SM_HERE(sm);
-    (void)cap_p; (void)cap_a;
-    AbcFillLane L[ABC_NL];
     const double jd_ref = E.jd_ref;
-    const bool planets_half = (warp < 8);
-    ABC_LANES(l) {
-        AbcFillLane& q = L[ABC_LI(l)];
-        const int slot = 4 * (warp & 7) + (l >> 3);
-        const int node = l & 7;
-        q.active = sm.flag(ABC_SMI_ACTIVE, slot);
-        const double t0 = sm.t0(slot);
-        q.t = (node == 0) ? t0 : (t0 + sm.dt(slot) * c_h[node]);
-        q.emb[0] = q.emb[1] = q.emb[2] = 0.0;
-    }
     /* usual SPK layout: every body and the EMB have a target */
     bool spk_regular = (E.planets_source != AB_SRC_ASCII) && E.emb_index >= 0;
     for (int b = 0; b < AB_NPLANETS && spk_regular; b++) if (E.p_index[b] < 0) spk_regular = false;
-    int s_first = 0;
-    if (planets_half) {
-        ABC_LANES(l) {
-            AbcFillLane& q = L[ABC_LI(l)];
-            if (q.active) {
-                const int slot = 4 * (warp & 7) + (l >> 3);
-                double* tb = sm.tab(l & 7, slot);
-                int err = AB_OK;
-                /* the Sun with its velocity; every planet when the layout is unusual (DE-binary planets, a kernel
-                 * without Earth or EMB target): the one-time routines */
-                for (int b = 0; b < (spk_regular ? 1 : AB_NPLANETS); b++) {
-                    double GM, x[3], v[3], a[3];
-                    int flag;
-                    if (b == 0) {
-                        flag = ab_planet<1>(E, 0, q.t, &GM, x, v, a);
-                        tb[ABC_E_SVEL(0) * ABC_SLOTS] = v[0]; tb[ABC_E_SVEL(1) * ABC_SLOTS] = v[1]; tb[ABC_E_SVEL(2) * ABC_SLOTS] = v[2];
-                    } else {
-                        flag = ab_planet<0>(E, b, q.t, &GM, x, v, a);
-                    }
-                    if (flag != AB_OK && err == AB_OK) err = flag;
-                    tb[ABC_E_POS(b, 0) * ABC_SLOTS] = x[0]; tb[ABC_E_POS(b, 1) * ABC_SLOTS] = x[1]; tb[ABC_E_POS(b, 2) * ABC_SLOTS] = x[2];
+    const int s_end = AB_NPLANETS + E.n_ast;
+    ABC_LANES(l) {
+        const int slot = 4 * warp + (l >> 3);
+        const int node = l & 7;
+        if (!sm.flag(ABC_SMI_ACTIVE, slot)) continue;
+        const double t0 = sm.t0(slot);
+        const double t = (node == 0) ? t0 : (t0 + sm.dt(slot) * c_h[node]);
+        double* tb = sm.tab(node, slot);
+        double* g = gt + node * ABC_GT_NODE + slot;
+        int err = AB_OK;
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        /* the Sun with its velocity; every planet when the layout is unusual (DE-binary planets, a kernel
+         * without Earth or EMB target): the one-time routines */
+        for (int b = 0; b < (spk_regular ? 1 : AB_NPLANETS); b++) {
+            double GM, x[3], v[3], a[3];
+            int flag;
+            if (b == 0) {
+                flag = ab_planet<1>(E, 0, t, &GM, x, v, a);
+                g[ABC_GT_SVEL(0) * ABC_SLOTS] = v[0]; g[ABC_GT_SVEL(1) * ABC_SLOTS] = v[1]; g[ABC_GT_SVEL(2) * ABC_SLOTS] = v[2];
+                sx = x[0]; sy = x[1]; sz = x[2];
+            } else {
+                flag = ab_planet<0>(E, b, t, &GM, x, v, a);
+            }
+            if (flag != AB_OK && err == AB_OK) err = flag;
+            tb[ABC_E_POS(b, 0) * ABC_SLOTS] = x[0]; tb[ABC_E_POS(b, 1) * ABC_SLOTS] = x[1]; tb[ABC_E_POS(b, 2) * ABC_SLOTS] = x[2];
+        }
+        if (err != AB_OK) sm.flag(ABC_SMI_ERR, slot) = err;      /* the lanes of a slot may race: every value written is a valid code */
+        double emb[3] = {0.0, 0.0, 0.0};
+#pragma unroll 1
+        for (int s = spk_regular ? 0 : AB_NPLANETS; s < s_end; s += ABC_FILL_NS) {
+            AbcSeriesRef R[ABC_FILL_NS];
+#pragma unroll
+            for (int j = 0; j < ABC_FILL_NS; j++) R[j] = abc_series_ref(s + j, s_end);
+            double u[ABC_FILL_NS][3];
+            abc_multi_eval<ABC_FILL_NS>(R, jd_ref, t, u);
+#pragma unroll
+            for (int j = 0; j < ABC_FILL_NS; j++) abc_fill_store(R[j], u[j], emb, tb, g, sx, sy, sz);
+        }
+        /* particle-independent EIH sums of the Sun at this node (ab_fill_nodes, same operations): the lane reads back
+         * the eleven positions it has just written */
+        if (F.forces & 0x40) {
+            double term1 = 0.0, arx = 0.0, ary = 0.0, arz = 0.0;
+#pragma unroll 1
+            for (int k0 = 1; k0 < AB_NPLANETS; k0 += 5) {
+                /* five terms at a time: the square roots and divisions of a group are independent and overlap,
+                 * then the group is added in order */
+                double t1[5], fx[5], fy[5], fz[5], GMk[5], dxjk[5], dyjk[5], dzjk[5], rjk2[5], _rjk[5], den[5];
+                bool ok = true;
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    const int k = k0 + j;
+                    GMk[j] = E.gm[k];
+                    dxjk[j] = sx - tb[ABC_E_POS(k, 0) * ABC_SLOTS];
+                    dyjk[j] = sy - tb[ABC_E_POS(k, 1) * ABC_SLOTS];
+                    dzjk[j] = sz - tb[ABC_E_POS(k, 2) * ABC_SLOTS];
+                    rjk2[j] = dxjk[j] * dxjk[j] + dyjk[j] * dyjk[j] + dzjk[j] * dzjk[j];
+                    ok = ok && ab_nb_ok(rjk2[j]) && ab_nb_ok(GMk[j]);
                 }
-                if (err != AB_OK) sm.flag(ABC_SMI_ERR, slot) = err;      /* the lanes of a slot may race: every value written is a valid code */
-            }
-        }
-        if (!spk_regular) s_first = AB_NPLANETS;
-    }
-    const int s_end = planets_half ? (AB_NPLANETS + ast_split) : (E.n_ast - ast_split);
-#pragma unroll 1
-    for (int s = s_first; s < s_end; s += 4) {
-        AbcSeriesRef R[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) R[j] = abc_series_ref(ast_split, planets_half, s + j, s_end);
-        ABC_LANES(l) {
-            AbcFillLane& q = L[ABC_LI(l)];
-            if (q.active) {
-                double u[4][3];
-                abc_quad_eval(R, jd_ref, q.t, u);
-                double* tb = sm.tab(l & 7, 4 * (warp & 7) + (l >> 3));
+                for (int j = 0; j < 5; j++) _rjk[j] = ab_sqrt_nb(rjk2[j]);
 #pragma unroll
-                for (int j = 0; j < 4; j++) abc_fill_store(R[j], u[j], q.emb, tb);
-            }
-        }
-    }
-    /* particle-independent EIH sums of the Sun at this node (ab_fill_nodes, same operations): the lane reads back
-     * the eleven positions it has just written */
-    if (planets_half && (F.forces & 0x40)) {
-        ABC_LANES(l) {
-            const AbcFillLane& q = L[ABC_LI(l)];
-            if (q.active) {
-                double* tb = sm.tab(l & 7, 4 * (warp & 7) + (l >> 3));
-                const double sx = tb[ABC_E_POS(0, 0) * ABC_SLOTS], sy = tb[ABC_E_POS(0, 1) * ABC_SLOTS], sz = tb[ABC_E_POS(0, 2) * ABC_SLOTS];
-                double term1 = 0.0, arx = 0.0, ary = 0.0, arz = 0.0;
-#pragma unroll 1
-                for (int k0 = 1; k0 < AB_NPLANETS; k0 += 5) {
-                    /* five terms at a time: the square roots and divisions of a group are independent and overlap,
-                     * then the group is added in order */
-                    double t1[5], fx[5], fy[5], fz[5];
+                for (int j = 0; j < 5; j++) { den[j] = rjk2[j] * _rjk[j]; ok = ok && ab_nb_ok(den[j]); }
+#pragma unroll
+                for (int j = 0; j < 5; j++) { t1[j] = ab_div_nb(GMk[j], _rjk[j]); fx[j] = ab_div_nb(GMk[j], den[j]); }
+                if (!ok) {
 #pragma unroll
                     for (int j = 0; j < 5; j++) {
-                        const int k = k0 + j;
-                        const double GMk = E.gm[k];
-                        const double dxjk = sx - tb[ABC_E_POS(k, 0) * ABC_SLOTS];
-                        const double dyjk = sy - tb[ABC_E_POS(k, 1) * ABC_SLOTS];
-                        const double dzjk = sz - tb[ABC_E_POS(k, 2) * ABC_SLOTS];
-                        const double rjk2 = dxjk * dxjk + dyjk * dyjk + dzjk * dzjk;
-                        const double _rjk = sqrt(rjk2);
-                        t1[j] = GMk / _rjk;
-                        const double fac = GMk / (rjk2 * _rjk);
-                        fx[j] = fac * dxjk; fy[j] = fac * dyjk; fz[j] = fac * dzjk;
+                        _rjk[j] = sqrt(rjk2[j]);
+                        t1[j] = GMk[j] / _rjk[j];
+                        fx[j] = GMk[j] / (rjk2[j] * _rjk[j]);
                     }
-#pragma unroll
-                    for (int j = 0; j < 5; j++) { term1 += t1[j]; arx -= fx[j]; ary -= fy[j]; arz -= fz[j]; }
                 }
-                tb[ABC_E_TERM1 * ABC_SLOTS] = term1;
-                tb[ABC_E_AR(0) * ABC_SLOTS] = arx; tb[ABC_E_AR(1) * ABC_SLOTS] = ary; tb[ABC_E_AR(2) * ABC_SLOTS] = arz;
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    const double fac = fx[j];
+                    fx[j] = fac * dxjk[j]; fy[j] = fac * dyjk[j]; fz[j] = fac * dzjk[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 5; j++) { term1 += t1[j]; arx -= fx[j]; ary -= fy[j]; arz -= fz[j]; }
             }
+            g[ABC_GT_TERM1 * ABC_SLOTS] = term1;
+            g[ABC_GT_AR(0) * ABC_SLOTS] = arx; g[ABC_GT_AR(1) * ABC_SLOTS] = ary; g[ABC_GT_AR(2) * ABC_SLOTS] = arz;
         }
-    }
-}
-
-/* after the barrier: asteroids heliocentric -> barycentric (reference src/forces.c:213-219); thread = (slot, node, half) */
-__device__ void abc_fill_shift(const AbEphem& E, const AbcSmem& sm, int warp, int lane) {
-    const int slot = 4 * (warp & 7) + (lane >> 3);
-    const int node = lane & 7;
-    if (!sm.flag(ABC_SMI_ACTIVE, slot)) return;
-    double* tb = sm.tab(node, slot);
-    const double sx = tb[ABC_E_POS(0, 0) * ABC_SLOTS], sy = tb[ABC_E_POS(0, 1) * ABC_SLOTS], sz = tb[ABC_E_POS(0, 2) * ABC_SLOTS];
-    const int half = (E.n_ast + 1) / 2;
-    const int m0 = (warp < 8) ? 0 : half, m1 = (warp < 8) ? half : E.n_ast;
-    for (int m = m0; m < m1; m++) {
-        const int b = AB_NPLANETS + m;
-        tb[ABC_E_POS(b, 0) * ABC_SLOTS] = tb[ABC_E_POS(b, 0) * ABC_SLOTS] + sx;
-        tb[ABC_E_POS(b, 1) * ABC_SLOTS] = tb[ABC_E_POS(b, 1) * ABC_SLOTS] + sy;
-        tb[ABC_E_POS(b, 2) * ABC_SLOTS] = tb[ABC_E_POS(b, 2) * ABC_SLOTS] + sz;
     }
 }
 
@@ -451,48 +448,100 @@ __device__ __forceinline__ bool abc_body_on(int i, int fmask) {
 
 /* N bodies of the direct term (reference src/forces.c:325-344) and, for planets, their terms of the EIH potential
  * sum (src/forces.c:1400-1416: same separation, same square root).  The bodies are independent until the component
- * warps add them up, so their chains (difference, square root, division) are laid side by side. */
-template <int N, bool PLANETS>
-__device__ __forceinline__ void abc_task_bodies(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, const double* tb,
-                                                const unsigned char* ids, int slot) {
-    const double px = sm.xv(0, slot), py = sm.xv(1, slot), pz = sm.xv(2, slot);
+ * warps add them up, so their chains (difference, square root, division) are laid side by side.  ids[n] = 255: no body. */
+template <int N>
+__device__ __forceinline__ void abc_bodies(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, const int* ids,
+                                           const double (*c)[3], double px, double py, double pz, int slot) {
     const double xo = 0.0, yo = 0.0, zo = 0.0;
-    double dx[N], dy[N], dz[N], _r[N], GM[N];
+    double dx[N], dy[N], dz[N], r2[N], _r[N], r3[N], GM[N], prefac[N], q[N];
+    bool ok = true;
 #pragma unroll
     for (int n = 0; n < N; n++) {
-        const int i = ids[n];
-        const double cx = tb[ABC_E_POS(i, 0) * ABC_SLOTS], cy = tb[ABC_E_POS(i, 1) * ABC_SLOTS], cz = tb[ABC_E_POS(i, 2) * ABC_SLOTS];
+        const int i = (ids[n] == 255) ? 0 : ids[n];
         GM[n] = E.gm[i];
-        dx[n] = px + (xo - cx);
-        dy[n] = py + (yo - cy);
-        dz[n] = pz + (zo - cz);
-        const double r2 = dx[n] * dx[n] + dy[n] * dy[n] + dz[n] * dz[n];
-        _r[n] = sqrt(r2);
+        dx[n] = px + (xo - c[n][0]);
+        dy[n] = py + (yo - c[n][1]);
+        dz[n] = pz + (zo - c[n][2]);
+        r2[n] = dx[n] * dx[n] + dy[n] * dy[n] + dz[n] * dz[n];
+        ok = ok && ab_nb_ok(r2[n]) && ab_nb_ok(GM[n]);
     }
-    const bool eih = PLANETS && (F.forces & 0x40);
+    /* square roots and quotients of the group side by side (fp_device.cuh); operands outside the branch-free range
+     * (a particle inside a body, a zero mass) take the built-in operators */
+#pragma unroll
+    for (int n = 0; n < N; n++) _r[n] = ab_sqrt_nb(r2[n]);
+#pragma unroll
+    for (int n = 0; n < N; n++) { r3[n] = _r[n] * _r[n] * _r[n]; ok = ok && ab_nb_ok(r3[n]); }
+#pragma unroll
+    for (int n = 0; n < N; n++) { prefac[n] = ab_div_nb(GM[n], r3[n]); q[n] = ab_div_nb(GM[n], _r[n]); }
+    if (!ok) {
+#pragma unroll
+        for (int n = 0; n < N; n++) {
+            _r[n] = sqrt(r2[n]);
+            prefac[n] = GM[n] / (_r[n] * _r[n] * _r[n]);
+            q[n] = GM[n] / _r[n];
+        }
+    }
+    const bool eih = (F.forces & 0x40) != 0;
 #pragma unroll
     for (int n = 0; n < N; n++) {
         const int i = ids[n];
-        const double prefac = GM[n] / (_r[n] * _r[n] * _r[n]);
-        const double p0 = prefac * dx[n], p1 = prefac * dy[n], p2 = prefac * dz[n];
+        if (i == 255) continue;
+        const double p0 = prefac[n] * dx[n], p1 = prefac[n] * dy[n], p2 = prefac[n] * dz[n];
         if (abc_body_on(i, F.forces)) { sm.prod(i, 0, slot) = p0; sm.prod(i, 1, slot) = p1; sm.prod(i, 2, slot) = p2; }
-        if (PLANETS && i < AB_NPLANETS && eih) sm.q(i, slot) = GM[n] / _r[n];
+        if (i < AB_NPLANETS && eih) sm.q(i, slot) = q[n];
     }
 }
 
-/* The group of a worker warp, one body after the other through the same few hundred bytes of code: nine warps walk
- * through it at the same time, so it is fetched once per SM and not once per warp (the kernel's hot code has to fit
- * the instruction cache: unrolled per-warp variants of this loop made the force phase twice as long). */
-__device__ __forceinline__ void abc_task_group(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, const double* tb,
-                                            const AbcWorkerPlan& wp, int slot) {
+#ifndef ABC_BN
+#define ABC_BN 2      /* bodies side by side */
+#endif
+__device__ __forceinline__ void abc_ast_fetch(const AbcWorkerPlan& wp, const double* g, int k0, double (*c)[3]) {
+#pragma unroll
+    for (int j = 0; j < ABC_BN; j++) {
+        const int m = (k0 + j < wp.nast) ? wp.ast[k0 + j] : wp.ast[0];
+#pragma unroll
+        for (int q = 0; q < 3; q++) c[j][q] = (k0 + j < wp.nast) ? __ldcg(g + ABC_GT_AST(m, q) * ABC_SLOTS) : 0.0;
+    }
+}
+
+/* planets first, then asteroids, through ONE copy of abc_bodies<ABC_BN>: the hot code of a node round has to stay
+ * inside the instruction cache */
+__device__ __forceinline__ void abc_task_all_bodies(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, const double* tb,
+                                                    const double* g, const AbcWorkerPlan& wp, int slot, double (*first)[3]) {
+    const double px = sm.xv(0, slot), py = sm.xv(1, slot), pz = sm.xv(2, slot);
+    double nxt[ABC_BN][3];
+#pragma unroll
+    for (int j = 0; j < ABC_BN; j++) { nxt[j][0] = first[j][0]; nxt[j][1] = first[j][1]; nxt[j][2] = first[j][2]; }
+    const int np = (wp.nbody + ABC_BN - 1) / ABC_BN * ABC_BN;           /* planets in groups of ABC_BN, then asteroids */
+    const int total = np + wp.nast;
 #pragma unroll 1
-    for (int n = 0; n < wp.nbody; n++) abc_task_bodies<1, true>(E, F, sm, tb, wp.body + n, slot);
+    for (int n = 0; n < total; n += ABC_BN) {
+        int ids[ABC_BN];
+        double c[ABC_BN][3];
+        if (n < np) {
+#pragma unroll
+            for (int j = 0; j < ABC_BN; j++) {
+                ids[j] = (n + j < wp.nbody) ? wp.body[n + j] : 255;
+                const int i = (ids[j] == 255) ? 0 : ids[j];
+                c[j][0] = tb[ABC_E_POS(i, 0) * ABC_SLOTS]; c[j][1] = tb[ABC_E_POS(i, 1) * ABC_SLOTS]; c[j][2] = tb[ABC_E_POS(i, 2) * ABC_SLOTS];
+            }
+        } else {
+            const int k0 = n - np;
+#pragma unroll
+            for (int j = 0; j < ABC_BN; j++) {
+                ids[j] = (k0 + j < wp.nast) ? AB_NPLANETS + wp.ast[k0 + j] : 255;
+                c[j][0] = nxt[j][0]; c[j][1] = nxt[j][1]; c[j][2] = nxt[j][2];
+            }
+            if (k0 + ABC_BN < wp.nast) abc_ast_fetch(wp, g, k0 + ABC_BN, nxt);
+        }
+        abc_bodies<ABC_BN>(E, F, sm, ids, c, px, py, pz, slot);
+    }
 }
 
 /* EIH source block of the Sun for the real particle (reference src/forces.c:1319-1501 with j = 0), everything
  * except the potential sum over the planets, which the component warps add in order.  Same expressions as
  * ab_force_eih. */
-__device__ void abc_task_eih_source(const AbEphem& E, const AbcSmem& sm, const double* tb, int slot) {
+__device__ void abc_task_eih_source(const AbEphem& E, const AbcSmem& sm, const double* tb, const double* ev, int slot) {
     const double over_C2 = E.over_c_squared;
     const double beta = 1.0;
     const double gamma = 1.0;
@@ -504,7 +553,7 @@ __device__ void abc_task_eih_source(const AbEphem& E, const AbcSmem& sm, const d
     {
         const double GMj = E.gm[0];
         const double xj = tb[ABC_E_POS(0, 0) * ABC_SLOTS], yj = tb[ABC_E_POS(0, 1) * ABC_SLOTS], zj = tb[ABC_E_POS(0, 2) * ABC_SLOTS];
-        const double vxj = tb[ABC_E_SVEL(0) * ABC_SLOTS], vyj = tb[ABC_E_SVEL(1) * ABC_SLOTS], vzj = tb[ABC_E_SVEL(2) * ABC_SLOTS];
+        const double vxj = ev[0], vyj = ev[1], vzj = ev[2];         /* Sun's velocity, EIH sums: fetched from the global table by the caller */
 
         const double dxij = pix + (xo - xj);
         const double dyij = piy + (yo - yj);
@@ -532,8 +581,8 @@ __device__ void abc_task_eih_source(const AbEphem& E, const AbcSmem& sm, const d
         term7y_sum += prefacij_f * (pivy - (vyj - vyo));
         term7z_sum += prefacij_f * (pivz - (vzj - vzo));
 
-        double term1 = tb[ABC_E_TERM1 * ABC_SLOTS];
-        const double axj = tb[ABC_E_AR(0) * ABC_SLOTS], ayj = tb[ABC_E_AR(1) * ABC_SLOTS], azj = tb[ABC_E_AR(2) * ABC_SLOTS];
+        double term1 = ev[3];
+        const double axj = ev[4], ayj = ev[5], azj = ev[6];
         term1 *= -(2 * beta - 1) * over_C2;
 
         const double rijdotaj = dxij * (axj - axo) + dyij * (ayj - ayo) + dzij * (azj - azo);
@@ -571,12 +620,12 @@ __device__ __forceinline__ void abc_sys_from_slot(const AbcSmem& sm, int slot, A
     }
 }
 
-__device__ void abc_run_task(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, int node, int slot, int kind) {
-    const double* tb = sm.tab(node, slot);
-    if (kind == ABC_T_EIHSRC) { abc_task_eih_source(E, sm, tb, slot); return; }
+__device__ void abc_run_task(const AbEphem& E, const AbForceOpts& F, const AbcSmem& sm, const double* tb, const double* g,
+                             const double* ev, int slot, int kind) {
+    if (kind == ABC_T_EIHSRC) { abc_task_eih_source(E, sm, tb, ev, slot); return; }
     AbSysT<1> S;
     abc_sys_from_slot(sm, slot, S);
-    const AbcTabView B(E.gm, tb);
+    const AbcTabView B(E.gm, tb, g);
     int dst;
     switch (kind) {
         case ABC_T_EARTHJ: ab_force_earth_harmonics<1, AbcTabView>(E, F, B, S, 0.0, 0.0, 0.0); dst = ABC_C_EARTH; break;

@@ -6,11 +6,9 @@
  *   -------  -------------  ----------------------------------------------------------------------
  *            control        bookkeeping per slot (queue, integrate() entry / exit, output epochs, windows)
  *   B1 (or)  all            anything left to do?  no -> the CTA retires
- *            all 16 warps   fill: Chebyshev sums of the 8 node times (warps 0-7 planets + EIH pair sums of the Sun,
- *                           warps 8-15 asteroids), records staged through shared memory
+ *            all 8 warps    fill: thread = (slot, node): Chebyshev sums of every body at the 8 node times + the EIH pair
+ *                           sums of the Sun; planets into shared memory, the rest into the CTA's global table
  *   B2
- *            all 16 warps   asteroids to barycentric
- *   B3
  *            control        ephemeris errors of the fill, sweep state of the attempt
  *   B4 (or)  all            does any slot need the force evaluation at the start of its step?
  *            components     state from the working batch into registers
@@ -39,7 +37,18 @@ namespace AB_NS {
 #ifdef AB_HOST_EMUL
 #define ABC_TICK(slot_) do { } while (0)
 #else
-#define ABC_TICK(slot_) do { if (A.timing && (threadIdx.x & 31) == 0) { const long long now_ = clock64(); tacc[slot_] += (unsigned long long)(now_ - tlast); tlast = now_; } } while (0)
+#define ABC_TICK(slot_) do { if (A.timing && threadIdx.x == 32 * ABC_CTRL_WARP) { const long long now_ = clock64(); tacc[slot_] += (unsigned long long)(now_ - tlast); tlast = now_; } } while (0)
+#endif
+
+/* probes of one warp's own time (component warp x of the CTA's first group): BEGIN..MID = busy, MID..END = waiting */
+#ifdef AB_HOST_EMUL
+#define ABC_PROBE_BEGIN() do { } while (0)
+#define ABC_PROBE_MID(slot_) do { } while (0)
+#define ABC_PROBE_END(slot_) do { } while (0)
+#else
+#define ABC_PROBE_BEGIN() do { if (A.timing && threadIdx.x == 0) pr_t = clock64(); } while (0)
+#define ABC_PROBE_MID(slot_) do { if (A.timing && threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(A.timing + slot_, (unsigned long long)(now_ - pr_t)); pr_t = now_; } } while (0)
+#define ABC_PROBE_END(slot_) do { if (A.timing && threadIdx.x == 0 && pr_t) { const long long now_ = clock64(); atomicAdd(A.timing + slot_, (unsigned long long)(now_ - pr_t)); pr_t = 0; } } while (0)
 #endif
 
 #define ABC_ERR_BUDGET 7      /* index into assist_error_messages: step budget exhausted / dt == 0 */
@@ -215,17 +224,14 @@ __device__ void abc_control_main(ABC_CTXARG const AbEphem& E, const AbForceOpts&
         }
         if (!ABC_SYNC_OR(alive)) {                                               /* B1 */
 #ifndef AB_HOST_EMUL
-            if (A.timing && (threadIdx.x & 31) == 0) for (int q = 0; q < 16; q++) atomicAdd(A.timing + q, tacc[q]);
+            if (A.timing && threadIdx.x == 32 * ABC_CTRL_WARP) for (int q = 0; q < 16; q++) atomicAdd(A.timing + q, tacc[q]);
 #endif
             return;
         }
         ABC_TICK(0);
-        abc_fill_warp(ABC_CTXPASS A.plan.ast_split, A.plan.cap_p, A.plan.cap_a, ABC_CTRL_WARP);
+        abc_fill_warp(ABC_CTXPASS A.gtab + (long long)ABC_BLOCK * ABC_GT_DOUBLES, ABC_CTRL_WARP);
         ABC_SYNC();                                                              /* B2 */
         ABC_TICK(1);
-        ABC_LANES(l) { abc_fill_shift(E, sm, ABC_CTRL_WARP, l); }
-        ABC_SYNC();                                                              /* B3 */
-        ABC_TICK(2);
         int anya0 = 0;
         ABC_LANES(l) {
             AbcCtl& C = ctl[ABC_LI(l)];
@@ -368,12 +374,13 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
     AbcComp st[ABC_NL];
     const AbBatch& W = A.W;
     const long long wn = W.n;
+#ifndef AB_HOST_EMUL
+    long long pr_t = 0;
+#endif
     for (;;) {
         if (!ABC_SYNC_OR(0)) return;                                             /* B1 */
-        abc_fill_warp(ABC_CTXPASS A.plan.ast_split, A.plan.cap_p, A.plan.cap_a, c);
+        abc_fill_warp(ABC_CTXPASS A.gtab + (long long)ABC_BLOCK * ABC_GT_DOUBLES, c);
         ABC_SYNC();                                                              /* B2 */
-        ABC_LANES(l) { abc_fill_shift(E, sm, c, l); }
-        ABC_SYNC();                                                              /* B3 */
         const bool a0_round = ABC_SYNC_OR(0);                                    /* B4 */
         ABC_LANES(l) {
             /* every lane loads (an idle slot reads its stale working copy and never uses it): the registers carry
@@ -410,6 +417,7 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
         for (;;) {
             for (int nn = 1; nn < 8; nn++) {
                 ABC_SYNC();                                                      /* B7 */
+                ABC_PROBE_END(13);
                 if (nn < 6) {
                     /* while the workers evaluate node nn: the part of the prediction for node nn + 1 that the
                      * coming update cannot change (it touches b_0 .. b_{nn-1}) */
@@ -422,6 +430,7 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
                     }
                 }
                 ABC_SYNC();                                                      /* B8 */
+                ABC_PROBE_BEGIN();
                 ABC_LANES(l) {
                     if (sm.flag(ABC_SMI_SW, l)) {
                         AbcComp& s = st[ABC_LI(l)];
@@ -442,6 +451,7 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
                         }
                     }
                 }
+                ABC_PROBE_MID(12);
             }
             ABC_SYNC();                                                          /* B9 */
             if (!ABC_SYNC_OR(0)) break;                                          /* B10 */
@@ -485,33 +495,49 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
 
 /* ---- worker warps --------------------------------------------------------------------------------- */
 
-__device__ __forceinline__ void abc_worker_tasks(const AbEphem& E, const AbForceOpts& F, const AbcArgs& A, const AbcSmem& sm,
-                                                 int widx, int node, int which_flag, int l) {
-    if (!sm.flag(which_flag, l)) return;
-    const AbcWorkerPlan& wp = A.plan.w[widx];
-    if (wp.nbody) abc_task_group(E, F, sm, sm.tab(node, l), wp, l);
-    if (wp.scalar[0] != ABC_T_NONE) abc_run_task(E, F, sm, node, l, wp.scalar[0]);
-    if (wp.scalar[1] != ABC_T_NONE) abc_run_task(E, F, sm, node, l, wp.scalar[1]);
+/* One copy in the kernel (the a0 round and the node rounds call it): see abc_task_all_bodies. */
+__device__ __noinline__ void abc_worker_tasks(ABC_CTXARG const double* gt, int widx, int node, int which_flag) {
+    const AbEphem& E = c_abcE;
+    const AbForceOpts& F = c_abcF;
+    ABC_SM_HERE(sm);
+    ABC_LANES(l) {
+        if (sm.flag(which_flag, l)) {
+            const AbcWorkerPlan& wp = c_abcP.w[widx];
+            const double* tb = sm.tab(node, l);
+            const double* g = gt + node * ABC_GT_NODE + l;
+            /* requests to the global table first: they travel while the planets are worked on */
+            double ac[ABC_BN][3];
+            if (wp.nast) abc_ast_fetch(wp, g, 0, ac);
+            double ev[7];
+            const bool eihsrc = (wp.scalar[0] == ABC_T_EIHSRC || wp.scalar[1] == ABC_T_EIHSRC);
+            if (eihsrc) {
+#pragma unroll
+                for (int q = 0; q < 7; q++) ev[q] = __ldcg(g + (ABC_GT_SVEL(0) + q) * ABC_SLOTS);
+            }
+            if (wp.scalar[0] != ABC_T_NONE) abc_run_task(E, F, sm, tb, g, ev, l, wp.scalar[0]);
+            if (wp.scalar[1] != ABC_T_NONE) abc_run_task(E, F, sm, tb, g, ev, l, wp.scalar[1]);
+            if (wp.nbody + wp.nast) abc_task_all_bodies(E, F, sm, tb, g, wp, l, ac);
+        }
+    }
 }
 
 __device__ void abc_worker_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F, const AbcArgs& A, const AbcSmem& sm, int warp) {
     const int widx = warp - ABC_FIRST_WORKER;
+    double* gt = A.gtab + (long long)ABC_BLOCK * ABC_GT_DOUBLES;
     for (;;) {
         if (!ABC_SYNC_OR(0)) return;                                             /* B1 */
-        abc_fill_warp(ABC_CTXPASS A.plan.ast_split, A.plan.cap_p, A.plan.cap_a, warp);
+        abc_fill_warp(ABC_CTXPASS gt, warp);
         ABC_SYNC();                                                              /* B2 */
-        ABC_LANES(l) { abc_fill_shift(E, sm, warp, l); }
-        ABC_SYNC();                                                              /* B3 */
         const bool a0_round = ABC_SYNC_OR(0);                                    /* B4 */
         if (a0_round) {
             ABC_SYNC();                                                          /* B5 */
-            ABC_LANES(l) { abc_worker_tasks(E, F, A, sm, widx, 0, ABC_SMI_NEEDA0, l); }
+            abc_worker_tasks(ABC_CTXPASS gt, widx, 0, ABC_SMI_NEEDA0);
             ABC_SYNC();                                                          /* B6 */
         }
         for (;;) {
             for (int nn = 1; nn < 8; nn++) {
                 ABC_SYNC();                                                      /* B7 */
-                ABC_LANES(l) { abc_worker_tasks(E, F, A, sm, widx, nn, ABC_SMI_SW, l); }
+                abc_worker_tasks(ABC_CTXPASS gt, widx, nn, ABC_SMI_SW);
                 ABC_SYNC();                                                      /* B8 */
             }
             ABC_SYNC();                                                          /* B9 */

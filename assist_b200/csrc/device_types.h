@@ -159,12 +159,29 @@ struct AbShared {
 };
 
 /* ---- pp_coop_kernel (coop_device.cuh): CTA geometry and the launch-time plan of its worker warps ---- */
+/* A CTA holds ABC_GROUPS independent groups of ABC_SLOTS systems; a group has its own ABC_GWARPS warps (3 component
+ * warps, 1 control warp, 4 workers), its own shared-memory block and global table.  The groups walk through the
+ * phases of a step attempt TOGETHER (CTA-wide barriers): twice the systems under every latency-bound phase, and all
+ * warps of the SM execute the same code at the same time (the hot code is larger than the instruction cache). */
 #define ABC_SLOTS 32
-#define ABC_WARPS 16
+#define ABC_GROUPS 2
+#define ABC_GWARPS 8
+#define ABC_WARPS (ABC_GROUPS * ABC_GWARPS)
 #define ABC_THREADS (ABC_WARPS * 32)
-#define ABC_CTRL_WARP 3
+#define ABC_CTAS_PER_SM 1
+#define ABC_CTRL_WARP 3          /* roles by warp index inside the group */
 #define ABC_FIRST_WORKER 4
-#define ABC_NWORK (ABC_WARPS - ABC_FIRST_WORKER)
+#define ABC_NWORK (ABC_GWARPS - ABC_FIRST_WORKER)
+
+/* per-group table in GLOBAL memory (L2 resident): what only one task reads at a node -- the asteroid positions and the
+ * Sun's velocity / particle-independent EIH sums -- as [node][entry][slot] */
+#define ABC_GT_AST(m, c) ((m) * 3 + (c))
+#define ABC_GT_SVEL(c) (3 * AB_MAX_AST + (c))
+#define ABC_GT_TERM1 (3 * AB_MAX_AST + 3)
+#define ABC_GT_AR(c) (3 * AB_MAX_AST + 4 + (c))
+#define ABC_GT_E (3 * AB_MAX_AST + 7)
+#define ABC_GT_NODE (ABC_GT_E * ABC_SLOTS)
+#define ABC_GT_DOUBLES (8 * ABC_GT_NODE)
 
 /* task kinds of the workers */
 #define ABC_T_BODY0 0            /* 0..26: body index */
@@ -176,19 +193,18 @@ struct AbShared {
 #define ABC_T_EIHSRC 32          /* EIH source block of the Sun (everything but the potential sum over the planets) */
 #define ABC_T_NONE 255
 
-/* launch-time plan of the worker warps: a group of bodies of the direct term evaluated side by side (their square
- * roots and divisions are independent and overlap) plus up to two of the single-body terms */
-#define ABC_MAX_GROUP 6
+/* launch-time plan of the worker warps: up to two of the single-body terms, a list of planets (positions in shared
+ * memory) and a list of asteroids (positions in the global table, fetched four at a time ahead of their use) */
+#define ABC_MAX_GROUP 16
 struct AbcWorkerPlan {
     unsigned char scalar[2];          /* ABC_T_EARTHJ ..., ABC_T_NONE */
-    unsigned char nbody;              /* bodies in the group */
-    unsigned char planets;            /* the group holds planets: also their terms of the EIH potential sum */
+    unsigned char nbody;              /* planets (and the Sun) in body[] */
+    unsigned char nast;               /* asteroids in ast[] (index m of the small-body kernel) */
     unsigned char body[ABC_MAX_GROUP];
+    unsigned char ast[ABC_MAX_GROUP];
 };
 struct AbcPlan {
     AbcWorkerPlan w[ABC_NWORK];
-    int ast_split;            /* fill: asteroids [0, ast_split) are evaluated by the warps that take the planets */
-    int cap_p, cap_a;         /* fill: doubles of staging area per slot for the two halves (cap_p + cap_a <= 194, both even) */
     long long attempt_budget; /* step attempts per system and call before it is retired with an error; <= 0: none */
 };
 

@@ -83,6 +83,22 @@ extern "C" int assist_gpu_set_device(int device) {
     return 0;
 }
 
+extern "C" int assist_gpu_selftest_fp(unsigned long long seed, long long n_pairs, unsigned long long mismatches[2]) {
+    int dev = 0;
+    int rc = ensure_device(&dev);
+    if (rc) return rc;
+    if (!mismatches || n_pairs < 1) return set_err(ASSIST_GPU_ERR_ARG, "bad argument");
+    unsigned long long* d_bad = nullptr;
+    CU(cudaMalloc((void**)&d_bad, 2 * sizeof(unsigned long long)));
+    CU(cudaMemset(d_bad, 0, 2 * sizeof(unsigned long long)));
+    const int blocks = 1184, iters = (int)((n_pairs + (long long)blocks * 256 - 1) / ((long long)blocks * 256));
+    cudaError_t e = ab_launch_fp_selftest_strict(seed, blocks, iters, d_bad, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(mismatches, d_bad, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d_bad);
+    if (e != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "fp self-test failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" void assist_gpu_default_options(struct assist_gpu_options* opt) {
     /* defaults of assist_init, reference src/assist.c:415-438, and REBOUND's IAS15 defaults */
     opt->forces = ASSIST_FORCE_SUN | ASSIST_FORCE_PLANETS | ASSIST_FORCE_ASTEROIDS | ASSIST_FORCE_NON_GRAVITATIONAL |
@@ -565,6 +581,7 @@ struct assist_gpu_batch {
     int sched_coop;         /* 1 (default): pp_coop_kernel wherever it applies (no variational particles, one EIH source, barycentric) */
     AbBatch wc;             /* working slots of pp_coop_kernel: 32 per CTA */
     char* wcblock;
+    double* d_gtab;             /* pp_coop_kernel: the CTAs' global tables (ABC_GT_DOUBLES each) */
     int coop_grid;
     long long attempt_budget; /* step attempts per system and call (pp_coop_kernel); <= 0: unlimited */
     int* d_active[2];       /* ping-pong lists of systems still integrating */
@@ -706,6 +723,7 @@ extern "C" void assist_gpu_batch_free(assist_gpu_batch* b) {
     cudaFree(b->block); cudaFree(b->snapshot); cudaFree(b->d_stage); cudaFree(b->d_stage_prm); cudaFree(b->d_out);
     cudaFree(b->d_active[0]); cudaFree(b->d_active[1]); cudaFree(b->d_count);
     cudaFree(b->wcblock);
+    cudaFree(b->d_gtab);
     cudaFree(b->wblock); cudaFree(b->d_queue); cudaFree(b->d_slice_done); cudaFree(b->d_slice_epoch); cudaFree(b->d_trange);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -916,108 +934,48 @@ static bool coop_applies(const assist_gpu_batch* b, const AbForceOpts& F) {
     return b->sched_coop && b->mode == ASSIST_GPU_PER_PARTICLE && b->K == 1 && F.gr_eih_sources == 1 && !F.geocentric;
 }
 
-/* Spread the force terms over the worker warps: longest task first onto the least loaded warp.  The weights
- * are rough FP64 instruction counts of the strict build. */
-#define ABC_FILL_PRE_HOST 7      /* coop_device.cuh: ABC_FILL_PRE */
+/* Spread the force terms over the worker warps: longest task first onto the least loaded warp.  The weights are
+ * rough lengths (cycles) of the dependent chains in the strict build: a phase ends with its slowest warp.  Planets run
+ * two side by side, asteroids four (coop_device.cuh).  ASSIST_B200_COOP_COSTS="earth,eih,sunj2,planet,asteroid"
+ * overrides the weights (tuning aid). */
 static void build_coop_plan(const struct assist_ephem* e, const AbEphem& E, const AbForceOpts& F, long long budget, AbcPlan* plan) {
-    /* rough latencies (cycles) of the chains: the phase ends with its slowest warp */
-    struct Scalar { int kind; int cost; };
-    std::vector<Scalar> sc;
-    const int nb = AB_NPLANETS + E.n_ast;
+    (void)e;
+    int c_earth = 1000, c_eih = 800, c_sunj2 = 700, c_planet = 250, c_ast = 130;
+    if (const char* cs = getenv("ASSIST_B200_COOP_COSTS")) sscanf(cs, "%d,%d,%d,%d,%d", &c_earth, &c_eih, &c_sunj2, &c_planet, &c_ast);
+    struct Task { int kind; int cost; };      /* kind: ABC_T_* or body index 0..26 */
+    std::vector<Task> tasks;
+    if ((F.forces & 0x08) && F.has_params) tasks.push_back({ABC_T_NG, 3000});
+    if (F.forces & 0x10) tasks.push_back({ABC_T_EARTHJ, c_earth});
+    if (F.forces & 0x40) tasks.push_back({ABC_T_EIHSRC, c_eih});
+    if (F.forces & 0x20) tasks.push_back({ABC_T_SUNJ2, c_sunj2});
+    if (F.forces & 0x80) tasks.push_back({ABC_T_GRSIMPLE, 600});
+    if (F.forces & 0x100) tasks.push_back({ABC_T_GRPOT, 500});
+    /* a body is evaluated when its direct term is on, or (planets) when the EIH potential sum needs its separation */
     const bool eih = (F.forces & 0x40) != 0;
-    if ((F.forces & 0x08) && F.has_params) sc.push_back({ABC_T_NG, 3000});
-    if (F.forces & 0x10) sc.push_back({ABC_T_EARTHJ, 1000});
-    if (eih) sc.push_back({ABC_T_EIHSRC, 800});
-    if (F.forces & 0x20) sc.push_back({ABC_T_SUNJ2, 700});
-    if (F.forces & 0x80) sc.push_back({ABC_T_GRSIMPLE, 600});
-    if (F.forces & 0x100) sc.push_back({ABC_T_GRPOT, 500});
-    memset(plan->w, 0, sizeof(plan->w));
+    for (int i = 0; i < AB_NPLANETS; i++) {
+        const bool on = (i == 0) ? (F.forces & 0x01) != 0 : (F.forces & 0x02) != 0;
+        if (on || eih) tasks.push_back({i, c_planet});
+    }
+    if (F.forces & 0x04) for (int m = 0; m < E.n_ast; m++) tasks.push_back({AB_NPLANETS + m, c_ast});
+    std::stable_sort(tasks.begin(), tasks.end(), [](const Task& a, const Task& b) { return a.cost > b.cost; });
+    memset(plan, 0, sizeof(*plan));
     int load[ABC_NWORK] = {0};
     for (int w = 0; w < ABC_NWORK; w++) { plan->w[w].scalar[0] = ABC_T_NONE; plan->w[w].scalar[1] = ABC_T_NONE; }
-    /* the single-body terms: one warp each, at most half of the warps (the others pair up on the lightest ones) */
-    const int scalar_warps = (int)sc.size() < ABC_NWORK / 2 ? (int)sc.size() : ABC_NWORK / 2;
-    for (size_t k = 0; k < sc.size(); k++) {
-        int best = 0;
-        for (int w = 1; w < scalar_warps; w++) if (load[w] < load[best]) best = w;
-        if ((int)k < scalar_warps) best = (int)k;
-        AbcWorkerPlan& wp = plan->w[best];
-        if (wp.scalar[0] == ABC_T_NONE) wp.scalar[0] = (unsigned char)sc[k].kind; else wp.scalar[1] = (unsigned char)sc[k].kind;
-        load[best] += sc[k].cost;
-    }
-    /* the bodies of the direct term: homogeneous groups (planets / asteroids) over the remaining warps */
-    const int group_warps = ABC_NWORK - scalar_warps;
-    int gp = (int)((double)group_warps * (AB_NPLANETS * 1.3) / (AB_NPLANETS * 1.3 + E.n_ast) + 0.5);
-    if (gp < 1) gp = 1;
-    if (E.n_ast > 0 && gp > group_warps - 1) gp = group_warps - 1;
-    if (E.n_ast == 0) gp = group_warps;
-    while ((AB_NPLANETS + gp - 1) / gp > ABC_MAX_GROUP) gp++;       /* never more than ABC_MAX_GROUP bodies in a group */
-    int ga = group_warps - gp;
-    int w = scalar_warps;
-    for (int g = 0; g < gp; g++, w++) {
-        AbcWorkerPlan& wp = plan->w[w];
-        wp.planets = 1;
-        for (int i = g; i < AB_NPLANETS; i += gp) wp.body[wp.nbody++] = (unsigned char)i;
-    }
-    /* asteroid groups; what does not fit goes to the lightest scalar warp as an extra group */
-    std::vector<int> ast;
-    for (int i = AB_NPLANETS; i < nb; i++) ast.push_back(i);
-    size_t next = 0;
-    for (int g = 0; g < ga && next < ast.size(); g++, w++) {
-        AbcWorkerPlan& wp = plan->w[w];
-        wp.planets = 0;
-        const size_t take = (ast.size() - next + (size_t)(ga - g) - 1) / (size_t)(ga - g);
-        for (size_t q = 0; q < take && q < ABC_MAX_GROUP; q++) wp.body[wp.nbody++] = (unsigned char)ast[next++];
-    }
-    while (next < ast.size()) {          /* leftovers: scalar warps that have no group yet, lightest first */
+    for (const Task& t : tasks) {
         int best = -1;
-        for (int q = 0; q < scalar_warps; q++) if (plan->w[q].nbody < ABC_MAX_GROUP && !plan->w[q].planets && (best < 0 || load[q] < load[best])) best = q;
-        if (best < 0) break;
-        plan->w[best].body[plan->w[best].nbody++] = (unsigned char)ast[next++];
-        load[best] += 100;
-    }
-    /* fill: warps 0-7 take the planets, the first ast_split asteroids and the EIH sums of the Sun, warps 8-15 the other
-     * asteroids; the split balances rough instruction counts (60 per series + 9 per Chebyshev term, 900 for the sums).
-     * Staging areas: two records of the largest record size of each half when that fits the 194 doubles a slot can
-     * have for both, sizes = 6 or 10 mod 16 so that the four slots of a warp start in different banks. */
-    int maxRp = 0, maxRa = 0, pa = 0;
-    double cost_p = (F.forces & 0x40) ? 900.0 : 0.0;
-    if (!e->ascii_planets && e->spk_planets && e->spk_planets->b200_host_desc) {
-        const AbSpkDesc* pd = (const AbSpkDesc*)e->spk_planets->b200_host_desc;
-        for (int k = -1; k < AB_NPLANETS; k++) {
-            const int idx = (k < 0) ? E.emb_index : E.p_index[k];
-            if (idx < 0) continue;
-            int P = 0;
-            for (int q = 0; q < pd->tg[idx].nseg; q++) { if (pd->tg[idx].seg[q].R > maxRp) maxRp = pd->tg[idx].seg[q].R; if (pd->tg[idx].seg[q].P > P) P = pd->tg[idx].seg[q].P; }
-            cost_p += 60.0 + 9.0 * P * (k == 0 ? 1.6 : 1.0);
+        for (int w = 0; w < ABC_NWORK; w++) {
+            const AbcWorkerPlan& wp = plan->w[w];
+            const bool fits = (t.kind >= ABC_T_EARTHJ) ? (wp.scalar[1] == ABC_T_NONE)
+                              : (t.kind < AB_NPLANETS ? wp.nbody < ABC_MAX_GROUP : wp.nast < ABC_MAX_GROUP);
+            if (fits && (best < 0 || load[w] < load[best])) best = w;
         }
-    } else {
-        cost_p += 12 * 200.0;       /* DE-binary planets: the one-time routines */
+        if (best < 0) continue;      /* cannot happen: 6 single-body terms, 11 + 16 bodies, 4 x (2 + 16 + 16) places */
+        AbcWorkerPlan& wp = plan->w[best];
+        if (t.kind >= ABC_T_EARTHJ) { if (wp.scalar[0] == ABC_T_NONE) wp.scalar[0] = (unsigned char)t.kind; else wp.scalar[1] = (unsigned char)t.kind; }
+        else if (t.kind < AB_NPLANETS) wp.body[wp.nbody++] = (unsigned char)t.kind;
+        else wp.ast[wp.nast++] = (unsigned char)(t.kind - AB_NPLANETS);
+        load[best] += t.cost;
     }
-    if (e->spk_asteroids && e->spk_asteroids->b200_host_desc) {
-        const AbSpkDesc* ad = (const AbSpkDesc*)e->spk_asteroids->b200_host_desc;
-        for (int m = 0; m < E.n_ast; m++)
-            for (int q = 0; q < ad->tg[m].nseg; q++) { if (ad->tg[m].seg[q].R > maxRa) maxRa = ad->tg[m].seg[q].R; if (ad->tg[m].seg[q].P > pa) pa = ad->tg[m].seg[q].P; }
-    }
-    const double cost_a = 60.0 + 9.0 * pa;
-    int split = 0;
-    while (split < E.n_ast && cost_p + (split + 1) * cost_a <= (E.n_ast - split - 1) * cost_a) split++;
-    const char* sp = getenv("ASSIST_B200_AST_SPLIT");
-    if (sp) split = atoi(sp);
-    if (split < 0) split = 0;
-    if (split > E.n_ast) split = E.n_ast;
-    plan->ast_split = split;
-    auto bank_friendly = [](int want) { int c = want < 2 ? 2 : want; while (!((c % 16) == 6 || (c % 16) == 10)) c++; return c; };
-    const int Rp_need = (split > 0 && maxRa > maxRp) ? maxRa : maxRp;
-    int cap_p = bank_friendly(2 * Rp_need), cap_a = bank_friendly(2 * maxRa);
-    if (cap_p + cap_a > 194) { cap_p = bank_friendly(Rp_need); }
-    if (cap_p + cap_a > 194) { cap_a = bank_friendly(maxRa); }
-    if (cap_p + cap_a > 194) { cap_p = 90; cap_a = 102; }      /* oversized records are read straight from the image */
-    if (getenv("ASSIST_B200_FILL_CAP")) { cap_p = atoi(getenv("ASSIST_B200_FILL_CAP")); cap_a = cap_p; }      /* experiments: 0 = no staging */
-    if (getenv("ASSIST_B200_FILL_CAP_P")) cap_p = atoi(getenv("ASSIST_B200_FILL_CAP_P"));
-    if (getenv("ASSIST_B200_FILL_CAP_A")) cap_a = atoi(getenv("ASSIST_B200_FILL_CAP_A"));
-    if (cap_p > 8 * 2 * ABC_FILL_PRE_HOST) cap_p = 8 * 2 * ABC_FILL_PRE_HOST - 6;
-    if (cap_a > 8 * 2 * ABC_FILL_PRE_HOST) cap_a = 8 * 2 * ABC_FILL_PRE_HOST - 6;
-    plan->cap_p = cap_p; plan->cap_a = cap_a;
     plan->attempt_budget = budget;
 }
 
@@ -1045,6 +1003,8 @@ static void coop_timing_report(assist_gpu_batch* b) {
     fprintf(stderr, "[assist-b200 coop timing] grid %d, attempts/CTA %.0f, evals/CTA %.0f, cycles/CTA %.3e\n", b->coop_grid,
             (double)t[10] / b->coop_grid, (double)t[11] / b->coop_grid, tot / b->coop_grid);
     for (int q = 0; q < 10; q++) if (q != 4) fprintf(stderr, "    %-14s %5.1f %%   %9.0f cycles per attempt\n", nm[q], 100.0 * t[q] / tot, (double)t[q] / (double)(t[10] ? t[10] : 1));
+    fprintf(stderr, "    component warp x of every CTA's first group: busy %.0f, waiting %.0f cycles per node round\n",
+            (double)t[12] / (double)(t[11] ? t[11] : 1), (double)t[13] / (double)(t[11] ? t[11] : 1));
 }
 
 static int ensure_coop_batch(assist_gpu_batch* b, bool fast) {
@@ -1055,14 +1015,16 @@ static int ensure_coop_batch(assist_gpu_batch* b, bool fast) {
         eo = ab_pp_coop_max_grid_fast(&g2);
         if (eo != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "pp_coop occupancy query failed: %s", cudaGetErrorString(eo));
         int grid = g1 < g2 ? g1 : g2;
-        const int need = (b->n + ABC_SLOTS - 1) / ABC_SLOTS;
+        const int need = (b->n + ABC_GROUPS * ABC_SLOTS - 1) / (ABC_GROUPS * ABC_SLOTS);
         if (grid > need) grid = need;
         if (grid < 1) grid = 1;
         b->coop_grid = grid;
-        const size_t slots = (size_t)grid * ABC_SLOTS;
+        const size_t slots = (size_t)grid * ABC_GROUPS * ABC_SLOTS;
         CU(cudaMalloc((void**)&b->wcblock, batch_bytes(slots, b->C)));
         CU(cudaMemset(b->wcblock, 0, batch_bytes(slots, b->C)));
         layout_batch(b->wc, b->wcblock, slots, b->K, b->mode);
+        CU(cudaMalloc((void**)&b->d_gtab, sizeof(double) * (size_t)grid * ABC_GROUPS * ABC_GT_DOUBLES));
+        CU(cudaMemset(b->d_gtab, 0, sizeof(double) * (size_t)grid * ABC_GROUPS * ABC_GT_DOUBLES));
         if (!b->d_queue) CU(cudaMalloc((void**)&b->d_queue, sizeof(unsigned long long)));
         if (!b->d_slice_done) CU(cudaMalloc((void**)&b->d_slice_done, sizeof(int) * (size_t)b->n));
         if (!b->d_slice_epoch) CU(cudaMalloc((void**)&b->d_slice_epoch, sizeof(int) * (size_t)b->n));
@@ -1121,8 +1083,8 @@ extern "C" int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int 
             build_coop_plan(b->ephem, E, F, b->attempt_budget, &plan);
             CU(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), 0));
             CU(cudaEventRecord(b->ev0, 0));
-            e = fast ? ab_launch_pp_coop_fast(E, F, b->d, b->wc, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, &plan, coop_ast_tg(b->ephem), coop_timing(b), b->coop_grid, 0)
-                     : ab_launch_pp_coop_strict(E, F, b->d, b->wc, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, &plan, coop_ast_tg(b->ephem), coop_timing(b), b->coop_grid, 0);
+            e = fast ? ab_launch_pp_coop_fast(E, F, b->d, b->wc, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, &plan, coop_ast_tg(b->ephem), b->d_gtab, coop_timing(b), b->coop_grid, 0)
+                     : ab_launch_pp_coop_strict(E, F, b->d, b->wc, t_end, exact_finish_time, b->d_queue, SL, NULL, 0, NULL, &plan, coop_ast_tg(b->ephem), b->d_gtab, coop_timing(b), b->coop_grid, 0);
             rc = finish_launch(b, e, "pp_coop");
             coop_timing_report(b);
             return rc;
@@ -1232,8 +1194,8 @@ extern "C" int assist_gpu_batch_integrate_or_interpolate(assist_gpu_batch* b, co
         build_coop_plan(b->ephem, E, F, b->attempt_budget, &plan);
         CU(cudaMemsetAsync(b->d_queue, 0, sizeof(unsigned long long), 0));
         CU(cudaEventRecord(b->ev0, 0));
-        e = fastm ? ab_launch_pp_coop_fast(E, F, b->d, b->wc, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, &plan, coop_ast_tg(b->ephem), coop_timing(b), b->coop_grid, 0)
-                  : ab_launch_pp_coop_strict(E, F, b->d, b->wc, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, &plan, coop_ast_tg(b->ephem), coop_timing(b), b->coop_grid, 0);
+        e = fastm ? ab_launch_pp_coop_fast(E, F, b->d, b->wc, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, &plan, coop_ast_tg(b->ephem), b->d_gtab, coop_timing(b), b->coop_grid, 0)
+                  : ab_launch_pp_coop_strict(E, F, b->d, b->wc, 0.0, 0, b->d_queue, SL, d_times, n_times, b->d_out, &plan, coop_ast_tg(b->ephem), b->d_gtab, coop_timing(b), b->coop_grid, 0);
     } else if (b->sched_queue) {
         rc = ensure_working_batch(b);
         if (rc) return rc;

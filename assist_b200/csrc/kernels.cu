@@ -762,15 +762,45 @@ __global__ void sh_interpolate_kernel(const __grid_constant__ AbBatch Bt, double
 /* ------------------------------------------------------------------------ */
 /* per-particle IAS15, one CTA per 32 systems (coop_device.cuh, coop_roles.cuh) */
 /* ------------------------------------------------------------------------ */
-__global__ void __launch_bounds__(ABC_THREADS, 1)
+__global__ void __launch_bounds__(ABC_THREADS, ABC_CTAS_PER_SM)
 pp_coop_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F, const __grid_constant__ AbcArgs A) {
-    AbcSmem sm;
-    sm.d = abc_shared;
-    sm.i = reinterpret_cast<int*>(abc_shared + ABC_SM_DOUBLES);
-    const int warp = (int)(threadIdx.x >> 5);
+    ABC_SM_HERE(sm);
+    const int warp = (int)(threadIdx.x >> 5) % ABC_GWARPS;       /* role inside the group */
     if (warp < 3) abc_comp_main(E, F, A, sm, warp);
     else if (warp == ABC_CTRL_WARP) abc_control_main(E, F, A, sm);
     else abc_worker_main(E, F, A, sm, warp);
+}
+
+/* self-test of fp_device.cuh: branch-free division / square root against the built-in operators, bit for bit */
+__global__ void fp_selftest_kernel(unsigned long long seed, int iters, unsigned long long* bad) {
+    unsigned long long s = seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x + 1);
+    unsigned long long nd = 0, ns = 0;
+    for (int it = 0; it < iters; it++) {
+        double v[2];
+        for (int k = 0; k < 2; k++) {
+            s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
+            const unsigned long long r = s * 0x2545F4914F6CDD1DULL;
+            unsigned long long mant = r & 0xFFFFFFFFFFFFFULL;
+            const int pat = (int)((r >> 52) & 7);
+            if (pat == 0) mant = 0; else if (pat == 1) mant = 0xFFFFFFFFFFFFFULL; else if (pat == 2) mant &= 0xFFFFF00000000ULL;
+            else if (pat == 3) mant |= 0xFFFFFFFF00000ULL;
+            s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
+            const unsigned long long r2 = s * 0x2545F4914F6CDD1DULL;
+            const unsigned long long ex = 0x280ULL + (r2 % 0x300ULL);
+            const unsigned long long sign = (k == 1) ? ((r2 >> 40) & 1ULL) : 0ULL;
+            v[k] = __longlong_as_double((long long)((sign << 63) | (ex << 52) | mant));
+        }
+        if (ab_nb_ok(v[0]) && ab_nb_ok(v[1])) {
+            const double q = ab_div_nb(v[1], v[0]), q0 = v[1] / v[0];
+            if (__double_as_longlong(q) != __double_as_longlong(q0)) nd++;
+            const double r = ab_sqrt_nb(v[0]), r0 = sqrt(v[0]);
+            if (__double_as_longlong(r) != __double_as_longlong(r0)) ns++;
+        } else {
+            nd++; ns++;      /* the generator stays inside the range by construction */
+        }
+    }
+    if (nd) atomicAdd(bad, nd);
+    if (ns) atomicAdd(bad + 1, ns);
 }
 #endif  /* AB_TU == 4 */
 
@@ -890,6 +920,11 @@ cudaError_t AB_CAT2(ab_launch_sh_interpolate, AB_SFX)(const AbBatch& Bt, double 
 #endif
 
 #if AB_TU == 4
+cudaError_t AB_CAT2(ab_launch_fp_selftest, AB_SFX)(unsigned long long seed, int blocks, int iters, unsigned long long* d_bad, cudaStream_t st) {
+    fp_selftest_kernel<<<blocks, 256, 0, st>>>(seed, iters, d_bad);
+    return cudaGetLastError();
+}
+
 cudaError_t AB_CAT2(ab_pp_coop_max_grid, AB_SFX)(int* max_grid) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaError_t e;
@@ -904,12 +939,13 @@ cudaError_t AB_CAT2(ab_pp_coop_max_grid, AB_SFX)(int* max_grid) {
 
 cudaError_t AB_CAT2(ab_launch_pp_coop, AB_SFX)(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const AbBatch& W, double tmax, int exact,
                                                unsigned long long* queue_head, const AbSlices& SL, const double* times, int n_times, double* out,
-                                               const void* plan, const AbSpkTarget* host_ast_tg, unsigned long long* timing, int grid, cudaStream_t st) {
+                                               const void* plan, const AbSpkTarget* host_ast_tg, double* gtab, unsigned long long* timing, int grid, cudaStream_t st) {
     if (grid < 1) return cudaSuccess;
     {   /* launch-time constants of the fill routine (see coop_device.cuh) */
         cudaError_t ec;
         if ((ec = cudaMemcpyToSymbolAsync(c_abcE, &E, sizeof(AbEphem), 0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return ec;
         if ((ec = cudaMemcpyToSymbolAsync(c_abcF, &F, sizeof(AbForceOpts), 0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return ec;
+        if ((ec = cudaMemcpyToSymbolAsync(c_abcP, plan, sizeof(AbcPlan), 0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return ec;
         if (host_ast_tg && E.n_ast > 0 &&
             (ec = cudaMemcpyToSymbolAsync(c_abc_ast, host_ast_tg, sizeof(AbSpkTarget) * E.n_ast, 0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return ec;
     }
@@ -918,6 +954,7 @@ cudaError_t AB_CAT2(ab_launch_pp_coop, AB_SFX)(const AbEphem& E, const AbForceOp
     A.times = times; A.n_times = n_times; A.out = out;
     A.plan = *reinterpret_cast<const AbcPlan*>(plan);
     A.timing = timing;
+    A.gtab = gtab;
     cudaError_t e = cudaFuncSetAttribute(pp_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ABC_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     pp_coop_kernel<<<grid, ABC_THREADS, ABC_SMEM_BYTES, st>>>(E, F, A);

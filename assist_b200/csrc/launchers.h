@@ -12,10 +12,11 @@
     cudaError_t ab_upload_constants_##sfx##_tu3();                                                                  \
     cudaError_t ab_upload_constants_##sfx##_tu4();                                                                  \
     cudaError_t ab_pp_coop_max_grid_##sfx(int* max_grid);                                                           \
+    cudaError_t ab_launch_fp_selftest_##sfx(unsigned long long seed, int blocks, int iters, unsigned long long* d_bad, cudaStream_t st); \
     cudaError_t ab_launch_pp_coop_##sfx(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, const AbBatch& W, \
                                         double tmax, int exact, unsigned long long* queue_head, const AbSlices& SL,  \
                                         const double* times, int n_times, double* out, const void* plan,              \
-                                        const AbSpkTarget* host_ast_tg, unsigned long long* timing, int grid,      \
+                                        const AbSpkTarget* host_ast_tg, double* gtab, unsigned long long* timing, int grid, \
                                         cudaStream_t st);                                                             \
     cudaError_t ab_launch_ephem_eval_##sfx(const AbEphem& E, const double* t, int n_t, double* out, int* status,   \
                                            cudaStream_t st);                                                        \

@@ -83,6 +83,10 @@ int assist_gpu_device_count(void);
 int assist_gpu_set_device(int device);
 const char* assist_gpu_last_error(void);
 void assist_gpu_default_options(struct assist_gpu_options* opt);
+/* Self-test of the kernels' branch-free IEEE division / square root against the built-in operators on n_pairs
+ * pseudo-random operand pairs (seeded); mismatches[0] = quotients, mismatches[1] = roots that differ in any bit.
+ * New with the GPU build: the reference divides on the host (src/forces.c:331-333 and every other quotient). */
+int assist_gpu_selftest_fp(unsigned long long seed, long long n_pairs, unsigned long long mismatches[2]);
 
 /* ---- ephemeris ------------------------------------------------------------ */
 /* Upload (once per device) the coefficient tables of an initialised ephemeris. */

@@ -64,3 +64,39 @@ def shared_var_case():
 
 def comet_case(n=6):
     return populations.comets(n, seed=19)
+
+
+# ---- north_star sizes (tests/golden/make_golden_large.py, tests/test_gpu_large.py) ----------------------------
+# fixed subsamples of the populations bench.py runs (same generators, same seeds)
+C5_EPOCHS = T0 - 10.0 * np.arange(1, 1828)          # 1827 epochs, every 10 d, 50 yr backward
+C5_SPARSE = np.arange(0, 1827, 29)
+
+
+def c3_subsample():
+    """1000 of the 10^6 NEO+MBA particles of BASELINE config 3: every 1000th (200 NEOs, 800 main-belt)."""
+    return populations.neo_mba_mix(1000000, seed=20261703)[::1000].copy()
+
+
+def c4_subsample():
+    """256 of the 10^5 systems of BASELINE config 4 (real particle + 6 variational)."""
+    return populations.with_variations(populations.main_belt(100000, seed=20261704)[::390][:256], 6)
+
+
+def c5_subsample():
+    st, prm = populations.comets(100000, seed=20261705)
+    return st[::390][:256].copy(), prm[::390][:256].copy()
+
+
+def c2_population():
+    return populations.main_belt(10000, seed=20261702)
+
+
+def eih11_case():
+    return populations.neo_mba_mix(64, seed=31)
+
+
+def geocentric_case(earth_state):
+    """12 near-Earth particles as GEOCENTRIC states: barycentric state minus Earth's at T0
+    (earth_state(t) -> [x y z vx vy vz] of ASSIST body 3)."""
+    st = populations.neo(12, seed=37)
+    return st - np.asarray(earth_state(T0))[None, :]

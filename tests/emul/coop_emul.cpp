@@ -43,8 +43,8 @@ struct AbcEmulShared {
 namespace ab_emul { struct AbcSmem; }
 struct AbcEmulCtx {
     const ab_emul::AbcSmem* sm;
-    int block;
-    int warp;
+    int block;      /* index of the group (ABC_BLOCK) */
+    int warp;       /* warp index inside the CTA */
     int phase;
     AbcEmulShared* sh;
 };
@@ -74,7 +74,7 @@ struct WarpJob {
 
 static void* warp_main(void* arg) {
     WarpJob* j = (WarpJob*)arg;
-    const int w = j->ctx.warp;
+    const int w = j->ctx.warp % ABC_GWARPS;
     if (w < 3) abc_comp_main(&j->ctx, *j->E, *j->F, *j->A, j->sm, w);
     else if (w == ABC_CTRL_WARP) abc_control_main(&j->ctx, *j->E, *j->F, *j->A, j->sm);
     else abc_worker_main(&j->ctx, *j->E, *j->F, *j->A, j->sm, w);
@@ -123,7 +123,7 @@ extern "C" void* abc_emul_create(int n, int max_blocks) {
     EmulBatch* b = new EmulBatch();
     b->n = n;
     layout(b->d, b->mem, b->cnt, b->ints, (size_t)n);
-    b->w_slots = max_blocks * ABC_SLOTS;
+    b->w_slots = max_blocks * ABC_GROUPS * ABC_SLOTS;
     layout(b->w, b->wmem, b->wcnt, b->wints, (size_t)b->w_slots);
     return b;
 }
@@ -170,7 +170,7 @@ extern "C" int abc_emul_run(void* h, const void* E_, const void* F_, const void*
     for (int k = 0; k < 28; k++) c_rri[k] = 1.0 / AB_RR[k];
     memcpy(c_c, AB_C, sizeof(AB_C));
     memcpy(c_d, AB_D, sizeof(AB_D));
-    c_abcE = E; c_abcF = F;
+    c_abcE = E; c_abcF = F; c_abcP = *(const AbcPlan*)plan_;
     for (int m = 0; m < E.n_ast && m < AB_MAX_AST; m++) c_abc_ast[m] = E.a_tgt[m];
 
     AbcArgs A;
@@ -185,22 +185,25 @@ extern "C" int abc_emul_run(void* h, const void* E_, const void* F_, const void*
     A.times = times; A.n_times = n_times; A.out = out;
     A.plan = *(const AbcPlan*)plan_;
     A.timing = nullptr;
-    if (A.W.n < n_blocks * ABC_SLOTS) return -1;
+    std::vector<double> gtab((size_t)n_blocks * ABC_GROUPS * ABC_GT_DOUBLES, 0.0);
+    A.gtab = gtab.data();
+    if (A.W.n < n_blocks * ABC_GROUPS * ABC_SLOTS) return -1;
 
     std::vector<AbcEmulShared> shared((size_t)n_blocks);
-    std::vector<std::vector<double>> smem((size_t)n_blocks);
+    std::vector<std::vector<double>> smem((size_t)n_blocks * ABC_GROUPS);
     std::vector<WarpJob> jobs((size_t)n_blocks * ABC_WARPS);
     std::vector<pthread_t> th((size_t)n_blocks * ABC_WARPS);
     for (int b = 0; b < n_blocks; b++) {
         pthread_barrier_init(&shared[b].bar, NULL, ABC_WARPS);
         shared[b].or_flag[0] = shared[b].or_flag[1] = 0;
-        smem[b].assign(ABC_SMEM_BYTES / 8 + 1, 0.0);
+        for (int g = 0; g < ABC_GROUPS; g++) smem[(size_t)b * ABC_GROUPS + g].assign(ABC_SMEM_GROUP_BYTES / 8 + 1, 0.0);
         for (int w = 0; w < ABC_WARPS; w++) {
             WarpJob& j = jobs[(size_t)b * ABC_WARPS + w];
-            j.ctx.block = b; j.ctx.warp = w; j.ctx.phase = 0; j.ctx.sh = &shared[b];
+            const size_t unit = (size_t)b * ABC_GROUPS + w / ABC_GWARPS;
+            j.ctx.block = (int)unit; j.ctx.warp = w; j.ctx.phase = 0; j.ctx.sh = &shared[b];
             j.E = &E; j.F = &F; j.A = &A;
-            j.sm.d = smem[b].data();
-            j.sm.i = (int*)(smem[b].data() + ABC_SM_DOUBLES);
+            j.sm.d = smem[unit].data();
+            j.sm.i = (int*)(smem[unit].data() + ABC_SM_DOUBLES);
             j.ctx.sm = &j.sm;
         }
     }

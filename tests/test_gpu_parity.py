@@ -446,3 +446,14 @@ def test_kepler_orbit_analytic(tmp_path, paths, lib):
     assert abs(energy(st) / energy(x0[0]) - 1.0) < 1e-14
     dt_res = (t0 + 170 * period) - t0 - 170 * period
     assert np.linalg.norm(st[:3] - np.array([x0[0, 0], x0[0, 4] * dt_res, 0.0])) < 1e-11
+
+
+def test_branch_free_division_and_sqrt(lib):
+    """fp_device.cuh: the branch-free quotient / square root used for groups of bodies equal the built-in IEEE
+    operators bit for bit on 2^28 seeded operand pairs (random and structured mantissas, exponents over the whole
+    range the callers' guard lets through)."""
+    bad = (ctypes.c_ulonglong * 2)(7, 7)
+    lib.assist_gpu_selftest_fp.argtypes = [ctypes.c_ulonglong, ctypes.c_longlong, ctypes.POINTER(ctypes.c_ulonglong)]
+    rc = lib.assist_gpu_selftest_fp(20261017, 1 << 28, bad)
+    assert rc == 0, lib.assist_gpu_last_error()
+    assert (bad[0], bad[1]) == (0, 0)
