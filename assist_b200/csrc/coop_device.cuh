@@ -222,7 +222,9 @@ __device__ int abc_coverage(const AbEphem& E, double t_first, double t_last) {
  * the L1 is a few KB, i.e. every record comes from L2: a thread runs ABC_FILL_NS series side by side and loads the
  * coefficients of the next pair of terms while it works on the current one.  Arithmetic per (series, time) is that of
  * ephem_device.cuh: same sums, same order. */
+#ifndef ABC_FILL_NS
 #define ABC_FILL_NS 2
+#endif
 
 struct AbcSeriesRef {
     const double* img;

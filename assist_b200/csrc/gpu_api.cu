@@ -940,7 +940,7 @@ static bool coop_applies(const assist_gpu_batch* b, const AbForceOpts& F) {
  * overrides the weights (tuning aid). */
 static void build_coop_plan(const struct assist_ephem* e, const AbEphem& E, const AbForceOpts& F, long long budget, AbcPlan* plan) {
     (void)e;
-    int c_earth = 1000, c_eih = 800, c_sunj2 = 700, c_planet = 250, c_ast = 130;
+    int c_earth = 500, c_eih = 400, c_sunj2 = 300, c_planet = 250, c_ast = 200;
     if (const char* cs = getenv("ASSIST_B200_COOP_COSTS")) sscanf(cs, "%d,%d,%d,%d,%d", &c_earth, &c_eih, &c_sunj2, &c_planet, &c_ast);
     struct Task { int kind; int cost; };      /* kind: ABC_T_* or body index 0..26 */
     std::vector<Task> tasks;
