@@ -84,6 +84,7 @@ __device__ bool abc_bookkeeping(const AbcArgs& A, AbcCtl& C, long long slot) {
                 if (q >= n_items) { C.exhausted = true; break; }
                 C.win = (int)(q / (unsigned long long)Bt.n);
                 C.sys = (long long)(q % (unsigned long long)Bt.n);
+                if (SL.order) C.sys = SL.order[C.sys];
                 C.pending = true;
             }
             if (C.win > 0 && *((volatile int*)(SL.done + C.sys)) < C.win) break;       /* try again after the next trip */

@@ -119,6 +119,7 @@ struct AbSlices {
     int n_win;
     int* done;                /* [n] windows completed per system */
     int* epoch;               /* [n] next output epoch per system (epoch runs) */
+    const int* order;         /* [n] or NULL: the queue hands out system order[k] as its k-th item of a window (longest expected first) */
 };
 
 #define AB_NODE_DOUBLES 94   /* doubles of an AbNode after the gm pointer */

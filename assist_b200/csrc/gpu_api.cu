@@ -581,6 +581,7 @@ struct assist_gpu_batch {
     int sched_coop;         /* 1 (default): pp_coop_kernel wherever it applies (no variational particles, one EIH source, barycentric) */
     AbBatch wc;             /* working slots of pp_coop_kernel: 32 per CTA */
     char* wcblock;
+    int* d_order;               /* work queue: systems in the order of their expected step counts, longest first (or NULL) */
     double* d_gtab;             /* pp_coop_kernel: the CTAs' global tables (ABC_GT_DOUBLES each) */
     int coop_grid;
     long long attempt_budget; /* step attempts per system and call (pp_coop_kernel); <= 0: unlimited */
@@ -724,6 +725,7 @@ extern "C" void assist_gpu_batch_free(assist_gpu_batch* b) {
     cudaFree(b->d_active[0]); cudaFree(b->d_active[1]); cudaFree(b->d_count);
     cudaFree(b->wcblock);
     cudaFree(b->d_gtab);
+    cudaFree(b->d_order);
     cudaFree(b->wblock); cudaFree(b->d_queue); cudaFree(b->d_slice_done); cudaFree(b->d_slice_epoch); cudaFree(b->d_trange);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -747,6 +749,52 @@ static int upload_particles(assist_gpu_batch* b, const double* state) {
     return 0;
 }
 
+/* Queue order of a per-particle batch: a system is a serial chain of steps, so a launch ends with its longest
+ * system; handing the long ones out FIRST keeps the tail of the launch short (strong scaling: VERDICT r1 item 5).
+ * Expected step count ~ a^-3/2 (1 - e)^-1 from the osculating elements of the (nearly heliocentric) barycentric
+ * state -- log-correlation 0.98 with the measured counts of the C3 population.  A counting sort into 1024 buckets,
+ * O(n) on the host.  Results do not depend on the order (tests/test_gpu_parity.py::test_properties_at_scale). */
+static int build_queue_order(assist_gpu_batch* b, const double* state) {
+    const size_t n = b->n;
+    if (b->mode != ASSIST_GPU_PER_PARTICLE || n < 2 || (getenv("ASSIST_B200_QUEUE_ORDER") && atoi(getenv("ASSIST_B200_QUEUE_ORDER")) == 0)) {
+        if (b->d_order) { cudaFree(b->d_order); b->d_order = nullptr; }
+        return 0;
+    }
+    const double gms = 2.959122082855911e-4;        /* GM of the Sun, AU^3 / day^2: only the ORDER of the costs matters */
+    const int NB = 1024;
+    std::vector<unsigned short> key(n);
+    std::vector<int> count(NB + 1, 0);
+    const size_t stride = (size_t)b->K * 6;
+    for (size_t i = 0; i < n; i++) {
+        const double* s = state + i * stride;
+        const double r = sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+        const double v2 = s[3] * s[3] + s[4] * s[4] + s[5] * s[5];
+        const double inv_a = 2.0 / r - v2 / gms;                 /* 1 / a */
+        double cost = 1e30;                                      /* unbound or degenerate: first */
+        if (inv_a > 0.0 && r > 0.0) {
+            const double hx = s[1] * s[5] - s[2] * s[4], hy = s[2] * s[3] - s[0] * s[5], hz = s[0] * s[4] - s[1] * s[3];
+            double e2 = 1.0 - (hx * hx + hy * hy + hz * hz) * inv_a / gms;
+            if (e2 < 0.0) e2 = 0.0;
+            const double ome = 1.0 - sqrt(e2);
+            if (ome > 1e-6) cost = inv_a * sqrt(inv_a) / ome;
+        }
+        /* log2 scale: 2^-12 .. 2^20 over the buckets, longest expected = bucket 0 */
+        double lg = log2(cost);
+        if (!(lg == lg)) lg = 20.0;
+        int k = (int)((20.0 - lg) * (NB / 32.0));
+        if (k < 0) k = 0;
+        if (k >= NB) k = NB - 1;
+        key[i] = (unsigned short)k;
+        count[k + 1]++;
+    }
+    for (int k = 0; k < NB; k++) count[k + 1] += count[k];
+    std::vector<int> order(n);
+    for (size_t i = 0; i < n; i++) order[(size_t)count[key[i]]++] = (int)i;
+    if (!b->d_order) CU(cudaMalloc((void**)&b->d_order, sizeof(int) * n));
+    CU(cudaMemcpy(b->d_order, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
 extern "C" int assist_gpu_batch_set_state(assist_gpu_batch* b, double t0, double dt0, const double* state,
                                           const double* params, const int* nvar_per_system) {
     if (!b || !state) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
@@ -755,6 +803,8 @@ extern "C" int assist_gpu_batch_set_state(assist_gpu_batch* b, double t0, double
     /* fresh IAS15 history: everything zero (REBOUND zeroes b, e, csx, csv ... on allocation) */
     CU(cudaMemset(b->block, 0, b->block_bytes));
     int rc = upload_particles(b, state);
+    if (rc) return rc;
+    rc = build_queue_order(b, state);
     if (rc) return rc;
     if (params) {
         CU(cudaMemcpy(b->d_stage_prm, params, sizeof(double) * 3 * n * b->K, cudaMemcpyHostToDevice));
@@ -875,7 +925,7 @@ static double unkey(unsigned long long k) {
  * earliest system towards t_end.  One slice when slicing is off or the systems lie on both sides of t_end. */
 static int build_slices(assist_gpu_batch* b, const AbEphem& E, double t_end, AbSlices* SL) {
     SL->origin = 0.0; SL->wlen = 1.0; SL->n_win = 1;
-    SL->done = b->d_slice_done; SL->epoch = b->d_slice_epoch;
+    SL->done = b->d_slice_done; SL->epoch = b->d_slice_epoch; SL->order = b->d_order;
     if (b->slice_days > 0.0 && t_end == t_end) {
         unsigned long long init[2] = {~0ULL, 0ULL}, got[2];
         CU(cudaMemcpy(b->d_trange, init, sizeof(init), cudaMemcpyHostToDevice));

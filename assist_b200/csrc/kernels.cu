@@ -429,6 +429,7 @@ pp_queue_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbFor
                 if (q >= n_items) { exhausted = true; break; }
                 win = (int)(q / (unsigned long long)Bt.n);
                 sys = (long long)(q % (unsigned long long)Bt.n);
+                if (SL.order) sys = SL.order[sys];
                 pending = true;
             }
             /* the previous window of this system must have been stored (it was handed out earlier, so it is running or done) */

@@ -9,8 +9,11 @@ synthetic NEO+MBA population, per-particle adaptive dt, all default forces (mask
 gr_eih_sources 1), 10 yr forward, synthetic DE440-layout planets .bsp + 16-asteroid .bsp.
 The other configs of BASELINE.json are available with --workload c2|c4|c5.
 One bench "step" = one full pass of the hot path over the batch (every particle integrated over
-the whole span).  Weak scaling: every GPU integrates its own --n-per-gpu particles; no collective
-on the data path (torch.distributed only carries the barrier and a max/sum of scalars).
+the whole span).  Scaling: C3 is the configuration BASELINE.json states as "10^6 ... sharded 1/2/4/8", so its
+default is STRONG scaling -- one population of --n particles in total, dealt out round-robin over the GPUs; at
+N > 1 the line also carries a `weak` block (that many particles on EVERY GPU, fewer passes).  The other workloads
+default to weak scaling.  No collective on the data path (torch.distributed only carries the barrier, a max/sum
+of scalars and a gather of per-rank timings).
 
 `value`   accepted IAS15 particle-steps per second, whole job, inputs resident in HBM
           (device snapshot -> integrate), timed between barriers, max over ranks.
@@ -213,8 +216,10 @@ def main():
     ap.add_argument("--n-per-gpu", type=int, default=0, help="particles per GPU (0 = the workload's own size)")
     ap.add_argument("--math", default="strict", choices=["strict", "fast"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the CPU baseline sample (0 = sized for ~10-30 s)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: --n-per-gpu particles on every GPU; strong: that many in total, sliced")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="weak: --n-per-gpu particles on every GPU; strong: that many in total, dealt out round-robin "
+                         "(default: strong for c3, weak for the others)")
+    ap.add_argument("--no-weak-leg", action="store_true", help="skip the extra weak-scaling measurement of a strong run at N > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -225,16 +230,19 @@ def main():
     from assist_b200 import sharding
     from assist_b200.synth import ephem_writer, populations
     wl = workloads()[args.workload]
+    if args.scaling is None:
+        args.scaling = "strong" if args.workload == "c3" else "weak"
     n_req = args.n_per_gpu or wl["n"]
     T0 = populations.T0
     T_END = T0 + wl["span"]
     data_dir = os.path.join(ROOT, "data")
 
-    def population(world_, rank_):
-        st_ = sharding.local_population(lambda n, seed: wl["gen"](n, seed), n_req, wl["seed"], world_, rank_, args.scaling)
+    def population(world_, rank_, scaling_=None):
+        scaling_ = scaling_ or args.scaling
+        st_ = sharding.local_population(lambda n, seed: wl["gen"](n, seed), n_req, wl["seed"], world_, rank_, scaling_)
         pr_ = None
         if wl["prm"]:
-            pr_ = np.ascontiguousarray(sharding.local_population(lambda n, seed: wl["prm"](n, seed), n_req, wl["seed"], world_, rank_, args.scaling))
+            pr_ = np.ascontiguousarray(sharding.local_population(lambda n, seed: wl["prm"](n, seed), n_req, wl["seed"], world_, rank_, scaling_))
         return np.ascontiguousarray(st_), pr_
 
     # ------------------------------------------------------------------ reference arm
@@ -382,7 +390,51 @@ def main():
     if times is not None and not np.isfinite(out_arr).all():
         raise SystemExit("bench.py: dense output holds non-finite values")
 
-    # reduce over ranks: max time, sum steps
+    # what bounds a rank's pass: its longest single system (a serial chain of steps) against the kernel time
+    longest = None
+    if not shared:
+        cnt = b.counters()
+        per_sys = (cnt["steps"] + cnt["rejected"]).astype(np.int64)
+        longest = int(per_sys.max())
+    my_kernel_ms = kernel_ms / args.steps
+
+    # extra leg of a strong-scaled run: the same number of particles on EVERY GPU (weak scaling), fewer passes
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_weak_leg:
+        b.close()
+        st_w, prm_w = population(world, rank, "weak")
+        bw = ab.Batch(eph, st_w.shape[0], wl["nvar"], ab.SHARED_STEP if shared else ab.PER_PARTICLE, forces=wl["forces"],
+                      gr_eih_sources=1, min_dt=wl["min_dt"], math=math_mode)
+        bw.set_state(T0, st_w, params=prm_w)
+        bw.snapshot()
+        passes = min(2, args.steps)
+        w_kernel = 0.0
+
+        def weak_pass():
+            bw.restore()
+            if times is None:
+                bw.integrate(T_END)
+            else:
+                bw.integrate_or_interpolate(times)
+        weak_pass()
+        barrier()
+        t_start = time.perf_counter()
+        for _ in range(passes):
+            weak_pass()
+            w_kernel += bw.stats()["last_kernel_ms"]
+        barrier()
+        t_w = time.perf_counter() - t_start
+        sw = bw.stats()
+        (t_w, w_kernel), (w_steps, w_n) = sharding.reduce_max_sum(
+            dist, [t_w, w_kernel], [float(sw["steps"] * (st_w.shape[0] if shared else 1)), float(st_w.shape[0])], device="cuda")
+        weak = {"value": w_steps * passes / t_w, "unit": UNIT, "n_total": int(w_n), "steps": passes, "warmup": 1,
+                "ms_per_step": 1e3 * t_w / passes, "kernel_ms_per_step_max": w_kernel / passes,
+                "what": "the same workload with %d particles on EVERY GPU (population seeded per rank)" % st_w.shape[0]}
+        bw.close()
+
+    # reduce over ranks: max time, sum steps; per-rank table
+    per_rank = sharding.gather_rows(dist, [my_kernel_ms, float(longest or 0), float(n), float(steps_per_pass)],
+                                    device="cuda" if dist is not None else None)
     (t_dev, t_e2e, kernel_ms), (tot_steps, tot_n) = sharding.reduce_max_sum(
         dist, [t_dev, t_e2e, kernel_ms], [float(steps_per_pass), float(n)], device="cuda" if dist is not None else None)
     if rank != 0:
@@ -407,13 +459,16 @@ def main():
     # same reuse, so the algorithmic ephemeris work is 8 tables per step.  In a shared-step batch all particles share them.
     eph_flops = 8.0 * f_eph * (sk["steps"] if shared else steps_per_pass)
     achieved_eph = (flops + eph_flops) / kernel_s / 1e12
-    # DRAM bytes of one launch of this kernel, from the committed ncu capture of the same configuration (profiles/README.md)
-    traffic = None
+    # DRAM bytes and FP64-pipe activity of one launch of this kernel: NOT measured in this run -- read from the committed
+    # ncu capture of the same workload / size / math (profiles/captures.json names the capture file of each entry); null
+    # when no capture of this exact configuration is committed
+    capture = None
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get("%s:%d:%s" % (args.workload, n, args.math))
+        with open(os.path.join(ROOT, "profiles", "captures.json")) as fh:
+            capture = json.load(fh).get("%s:%d:%s" % (args.workload, n, args.math))
     except OSError:
         pass
+    traffic = capture["dram_bytes_per_launch"] if capture else None
     # the same launch against the HBM roof (MEASURED_PEAKS.json, driver-written): the kernel is far from both
     hbm = None
     if traffic:
@@ -424,13 +479,19 @@ def main():
             hbm_peak, hbm_src = 6650.0, "of fallback (B200_PROFILING.md)"
         hbm = {"achieved_gbs": traffic / kernel_s / 1e9, "peak_gbs": hbm_peak, "frac": traffic / kernel_s / 1e9 / hbm_peak,
                "peak_source": hbm_src}
+    coop = (not shared) and wl["nvar"] == 0
+    kname = ("sh_integrate_kernel" if shared else
+             ("pp_coop_kernel" if coop else "pp_queue_kernel") + (", epoch output" if times is not None else ""))
     roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "hbm": hbm,
-                "kernel": "fused ephemeris + forces + IAS15 integrate kernel (%s), %d launch(es) per pass"
-                          % ("sh_integrate_kernel" if shared else "pp_queue_kernel, epoch output" if times is not None else "pp_queue_kernel", launches // S),
+                "traffic": traffic, "traffic_source": (capture or {}).get("source"),
+                "fp64_pipe_active_pct": (capture or {}).get("fp64_pipe_active_pct"), "hbm": hbm,
+                "kernel": "fused ephemeris + forces + IAS15 integrate kernel (%s), %d launch(es) per pass" % (kname, launches // S),
                 "flops_per_force_eval": f_force, "achieved_incl_ephemeris": achieved_eph, "frac_incl_ephemeris": achieved_eph / peak,
                 "ephemeris_flops_per_table": f_eph, "ephemeris_tables_per_step": 8, "force_evals_per_s": evals_per_pass / kernel_s,
                 "pc_iterations_per_step": iters_per_step,
+                "ceiling": "strict math forbids FMA contraction (reference operation order): an add or a multiply fills a DFMA "
+                           "slot with one flop, so `frac` cannot exceed 0.5 by construction; IEEE division and square root "
+                           "expand to ~10 FP64 instructions each and count as one flop",
                 "peak_source": "register-resident DFMA loop measured in this run (MEASURED_PEAKS.json has no FP64 entry)"}
 
     cpu_baseline = None
@@ -450,8 +511,16 @@ def main():
                        "cache": ("per-GPU batch state %.2f GB >> 126 MB L2, so every pass streams from HBM" % state_gb) if state_gb > 0.5 else
                                 ("per-GPU batch state %.3f GB; every pass restarts from a device snapshot and rewrites the whole "
                                  "state, nothing is reused between passes" % state_gb),
-                       "particle_steps_per_pass": tot_steps, "parity": "strict math is bit-identical to the reference C build (tests/)"},
+                       "particle_steps_per_pass": tot_steps,
+                       "parity": "strict math: ephemeris, every force term and the integrated states are bit-identical to the reference's "
+                                 "src/*.c driven by this repo's restatement of REBOUND's IAS15 (tests/); the IAS15 stepper itself is "
+                                 "UNPINNED against a REBOUND binary (REBOUND is absent offline), see DESIGN.md section 2"},
             "kernel_ms_per_step": kernel_ms / S,
+            "per_rank": [{"rank": r, "kernel_ms_per_step": row[0], "longest_system_attempts": int(row[1]), "particles": int(row[2]),
+                          "particle_steps_per_pass": int(row[3]),
+                          "ms_per_attempt_if_longest_system_bounds_the_pass": (row[0] / row[1]) if row[1] else None}
+                         for r, row in enumerate(per_rank)],
+            "weak": weak,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes + prm_bytes), "d2h_bytes_per_step": int(out_bytes)},
             "gpu_launches": int(all_launches), "integrate_kernel_launches": int(launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}

@@ -25,7 +25,8 @@ def test_shard_bounds_cover_and_are_disjoint():
 def test_strong_slices_reassemble_the_population():
     full = populations.neo_mba_mix(999, seed=7)
     parts = [sharding.local_population(populations.neo_mba_mix, 999, 7, 4, r, "strong") for r in range(4)]
-    assert np.array_equal(np.concatenate(parts, axis=0), full)
+    assert np.array_equal(sharding.interleave(parts), full)
+    assert np.array_equal(parts[1], full[1::4])
     a = sharding.local_population(populations.neo_mba_mix, 100, 7, 2, 0, "weak")
     b = sharding.local_population(populations.neo_mba_mix, 100, 7, 2, 1, "weak")
     assert a.shape == b.shape == (100, 6) and not np.array_equal(a, b)
@@ -43,9 +44,10 @@ def _worker(rank, world, port, q):
     # stand-in for the per-rank integration: a deterministic function of the local slice
     result = local * 2.0
     maxima, sums = sh.reduce_max_sum(dist, [1.0 + rank, 5.0 - rank], [float(local.shape[0]), 3.0])
-    gathered = sh.gather_states(dist, result, world, rank)
+    gathered = sh.gather_states(dist, result, world, rank, "strong")
+    rows = sh.gather_rows(dist, [float(rank), float(local.shape[0])])
     if rank == 0:
-        q.put((maxima, sums, gathered))
+        q.put((maxima, sums, gathered, rows))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -60,9 +62,10 @@ def test_two_rank_gloo_reduce_and_gather():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    maxima, sums, gathered = q.get(timeout=180)
+    maxima, sums, gathered, rows = q.get(timeout=180)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert maxima == [2.0, 5.0] and sums == [101.0, 6.0]
     assert np.array_equal(gathered, populations.main_belt(101, seed=11) * 2.0)
+    assert rows == [[0.0, 51.0], [1.0, 50.0]]
