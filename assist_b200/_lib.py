@@ -86,5 +86,20 @@ def load():
     lib.assist_gpu_host_alloc.argtypes = [ctypes.c_size_t]
     lib.assist_gpu_host_free.restype = None
     lib.assist_gpu_host_free.argtypes = [c_void_p]
+    lib.assist_gpu_selftest_fp.argtypes = [c_ulonglong, ctypes.c_longlong, P(c_ulonglong)]
+    # one population over several GPUs
+    lib.assist_gpu_multi_create.restype = c_void_p
+    lib.assist_gpu_multi_create.argtypes = [P(Ephem), c_int, c_int, P(c_int), c_int]
+    lib.assist_gpu_multi_free.restype = None
+    lib.assist_gpu_multi_free.argtypes = [c_void_p]
+    lib.assist_gpu_multi_device_count.argtypes = [c_void_p]
+    lib.assist_gpu_multi_last_error.restype = c_char_p
+    lib.assist_gpu_multi_set_options.argtypes = [c_void_p, P(GpuOptions)]
+    lib.assist_gpu_multi_set_state.argtypes = [c_void_p, c_double, c_double, P(c_double), P(c_double)]
+    lib.assist_gpu_multi_integrate.argtypes = [c_void_p, c_double, c_int]
+    lib.assist_gpu_multi_integrate_or_interpolate.argtypes = [c_void_p, P(c_double), c_int, P(c_double)]
+    lib.assist_gpu_multi_get_state.argtypes = [c_void_p, P(c_double), P(c_double), P(c_double), P(c_double), P(c_int)]
+    lib.assist_gpu_multi_get_counters.argtypes = [c_void_p, P(c_ulonglong), P(c_ulonglong), P(c_ulonglong), P(c_ulonglong)]
+    lib.assist_gpu_multi_get_stats.argtypes = [c_void_p, P(GpuStats), P(c_double)]
     _lib = lib
     return lib

@@ -203,3 +203,73 @@ class Batch:
             self.close()
         except Exception:
             pass
+
+
+class MultiBatch:
+    """One per-particle population over several GPUs of a box (include/assist_gpu.h: assist_gpu_multi_*): one
+    sub-batch and one host thread per device, no collective, a host gather of outputs.  devices=None: every visible
+    device.  Results are those of a single-device Batch, bit for bit."""
+
+    def __init__(self, ephem, n_sys, n_var=0, devices=None, **opts):
+        self.lib = ephem.lib
+        self.ephem = ephem
+        self.n, self.n_var, self.K = int(n_sys), int(n_var), 1 + int(n_var)
+        dev = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        self.ptr = self.lib.assist_gpu_multi_create(ephem.ptr, self.n, self.n_var,
+                                                    dev.ctypes.data_as(POINTER(c_int)) if dev is not None else None,
+                                                    0 if dev is None else dev.size)
+        if not self.ptr:
+            raise RuntimeError("assist_gpu_multi_create: " + self.lib.assist_gpu_multi_last_error().decode())
+        self.n_devices = self.lib.assist_gpu_multi_device_count(self.ptr)
+        self.opt = make_options(self.lib, **opts)
+        self._check(self.lib.assist_gpu_multi_set_options(self.ptr, byref(self.opt)), "set_options")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("%s failed (%d): %s" % (what, rc, self.lib.assist_gpu_multi_last_error().decode()))
+
+    def set_state(self, t0, state, params=None, dt0=0.001):
+        state = np.ascontiguousarray(state, dtype=np.float64).reshape(self.n, self.K, 6)
+        prm = None if params is None else np.ascontiguousarray(params, dtype=np.float64).reshape(self.n, self.K, 3)
+        self._check(self.lib.assist_gpu_multi_set_state(self.ptr, float(t0), float(dt0), _dp(state),
+                                                        _dp(prm) if prm is not None else None), "set_state")
+
+    def integrate(self, t_end, exact_finish_time=1):
+        self._check(self.lib.assist_gpu_multi_integrate(self.ptr, float(t_end), int(exact_finish_time)), "integrate")
+
+    def integrate_or_interpolate(self, times):
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        out = np.empty((times.size, self.n, self.K, 6), dtype=np.float64)
+        self._check(self.lib.assist_gpu_multi_integrate_or_interpolate(self.ptr, _dp(times), times.size, _dp(out)), "integrate_or_interpolate")
+        return out
+
+    def get_state(self):
+        state = np.empty((self.n, self.K, 6)); t = np.empty(self.n); dt = np.empty(self.n); dtl = np.empty(self.n)
+        st = np.empty(self.n, dtype=np.int32)
+        self._check(self.lib.assist_gpu_multi_get_state(self.ptr, _dp(state), _dp(t), _dp(dt), _dp(dtl),
+                                                        st.ctypes.data_as(POINTER(c_int))), "get_state")
+        return dict(state=state, t=t, dt=dt, dt_last_done=dtl, status=st)
+
+    def counters(self):
+        out = {k: np.zeros(self.n, dtype=np.uint64) for k in ("steps", "rejected", "iters", "evals")}
+        u64 = POINTER(ctypes.c_ulonglong)
+        self._check(self.lib.assist_gpu_multi_get_counters(self.ptr, *[out[k].ctypes.data_as(u64) for k in ("steps", "rejected", "iters", "evals")]), "get_counters")
+        return out
+
+    def stats(self):
+        s = GpuStats()
+        per_dev = np.zeros(self.n_devices)
+        self._check(self.lib.assist_gpu_multi_get_stats(self.ptr, byref(s), _dp(per_dev)), "get_stats")
+        return dict(steps=s.steps, steps_rejected=s.steps_rejected, pc_iterations=s.pc_iterations, force_evals=s.force_evals,
+                    kernel_launches=s.kernel_launches, last_kernel_ms=s.last_kernel_ms, kernel_ms_per_device=per_dev)
+
+    def close(self):
+        if self.ptr:
+            self.lib.assist_gpu_multi_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -754,17 +754,13 @@ static int upload_particles(assist_gpu_batch* b, const double* state) {
  * Expected step count ~ a^-3/2 (1 - e)^-1 from the osculating elements of the (nearly heliocentric) barycentric
  * state -- log-correlation 0.98 with the measured counts of the C3 population.  A counting sort into 1024 buckets,
  * O(n) on the host.  Results do not depend on the order (tests/test_gpu_parity.py::test_properties_at_scale). */
-static int build_queue_order(assist_gpu_batch* b, const double* state) {
-    const size_t n = b->n;
-    if (b->mode != ASSIST_GPU_PER_PARTICLE || n < 2 || (getenv("ASSIST_B200_QUEUE_ORDER") && atoi(getenv("ASSIST_B200_QUEUE_ORDER")) == 0)) {
-        if (b->d_order) { cudaFree(b->d_order); b->d_order = nullptr; }
-        return 0;
-    }
+extern "C" void ab_gpu_cost_order_host(const double* state, int n_, int K, int* order) {
+    const size_t n = (size_t)n_;
     const double gms = 2.959122082855911e-4;        /* GM of the Sun, AU^3 / day^2: only the ORDER of the costs matters */
     const int NB = 1024;
     std::vector<unsigned short> key(n);
     std::vector<int> count(NB + 1, 0);
-    const size_t stride = (size_t)b->K * 6;
+    const size_t stride = (size_t)K * 6;
     for (size_t i = 0; i < n; i++) {
         const double* s = state + i * stride;
         const double r = sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
@@ -788,8 +784,17 @@ static int build_queue_order(assist_gpu_batch* b, const double* state) {
         count[k + 1]++;
     }
     for (int k = 0; k < NB; k++) count[k + 1] += count[k];
-    std::vector<int> order(n);
     for (size_t i = 0; i < n; i++) order[(size_t)count[key[i]]++] = (int)i;
+}
+
+static int build_queue_order(assist_gpu_batch* b, const double* state) {
+    const size_t n = b->n;
+    if (b->mode != ASSIST_GPU_PER_PARTICLE || n < 2 || (getenv("ASSIST_B200_QUEUE_ORDER") && atoi(getenv("ASSIST_B200_QUEUE_ORDER")) == 0)) {
+        if (b->d_order) { cudaFree(b->d_order); b->d_order = nullptr; }
+        return 0;
+    }
+    std::vector<int> order(n);
+    ab_gpu_cost_order_host(state, (int)n, b->K, order.data());
     if (!b->d_order) CU(cudaMalloc((void**)&b->d_order, sizeof(int) * n));
     CU(cudaMemcpy(b->d_order, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     return 0;

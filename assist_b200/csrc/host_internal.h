@@ -28,6 +28,9 @@ struct spk_s;
 int ab_gpu_spk_target_eval(struct spk_s* file, int target_index, int emb_index, double jd_ref, double jd_rel,
                            int mode, const double* ud, double* out);
 int ab_gpu_ascii_work(const double* P, int ncm, int ncf, int niv, double t0, double t1, double* out);
+/* order[k] = the system with the k-th largest expected step count (a^-3/2 (1 - e)^-1 of the osculating orbit);
+ * state[n][K][6], the real particle first.  Host only. */
+void ab_gpu_cost_order_host(const double* state, int n, int K, int* order);
 /* frees the cached descriptor block of an SPK file (struct spk_s::b200_host_desc) */
 void ab_spk_desc_free(void* desc);
 

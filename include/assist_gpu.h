@@ -139,6 +139,26 @@ int assist_gpu_batch_get_stats(assist_gpu_batch* b, struct assist_gpu_stats* sta
 /* Per-system counters of a per-particle batch (each array n_sys long; any may be NULL). */
 int assist_gpu_batch_get_counters(assist_gpu_batch* b, unsigned long long* steps, unsigned long long* rejected,
                                   unsigned long long* iters, unsigned long long* evals);
+/* ---- one population over several GPUs of one box (north star (4)) -------------------------------------------
+ * New with the GPU build (the reference runs one simulation per process).  Per-particle semantics
+ * only.  One sub-batch per device, one host thread per device for every call that launches work; state, outputs and
+ * counters are scattered / gathered in the order of the caller's population.  devices == NULL: every visible device.
+ * The systems are dealt out in the order of their expected step counts, so every device gets the same mix. */
+typedef struct assist_gpu_multi assist_gpu_multi;
+assist_gpu_multi* assist_gpu_multi_create(const struct assist_ephem* ephem, int n_sys, int n_var, const int* devices, int n_devices);
+void assist_gpu_multi_free(assist_gpu_multi* m);
+int assist_gpu_multi_device_count(const assist_gpu_multi* m);
+const char* assist_gpu_multi_last_error(void);
+int assist_gpu_multi_set_options(assist_gpu_multi* m, const struct assist_gpu_options* opt);
+int assist_gpu_multi_set_state(assist_gpu_multi* m, double t0, double dt0, const double* state, const double* params);
+int assist_gpu_multi_integrate(assist_gpu_multi* m, double t_end, int exact_finish_time);
+int assist_gpu_multi_integrate_or_interpolate(assist_gpu_multi* m, const double* times, int n_times, double* out);
+int assist_gpu_multi_get_state(assist_gpu_multi* m, double* state, double* t, double* dt, double* dt_last_done, int* status);
+int assist_gpu_multi_get_counters(assist_gpu_multi* m, unsigned long long* steps, unsigned long long* rejected,
+                                  unsigned long long* iters, unsigned long long* evals);
+/* sums over the devices; last_kernel_ms = the slowest device; kernel_ms_per_device (may be NULL): n_devices entries */
+int assist_gpu_multi_get_stats(assist_gpu_multi* m, struct assist_gpu_stats* stats, double* kernel_ms_per_device);
+
 /* Page-locked host memory for state / output buffers (cudaHostAlloc). */
 void* assist_gpu_host_alloc(size_t bytes);
 void assist_gpu_host_free(void* p);

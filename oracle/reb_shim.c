@@ -43,6 +43,22 @@
 
 static const double safety_factor = 0.25;
 
+/* ---- variants of the two places where this restatement could differ from a REBOUND 4.x binary at round-off or
+ * worse ("What's weak" 1).  Defaults = what every golden vector was generated with.  The spread between
+ * the variants bounds what the real REBOUND could change (tests/test_cpu_oracle.py::test_ias15_variant_spread,
+ * DESIGN.md section 2).
+ *   predictor_form 0: nested Horner form (the form of REBOUND's integrator_ias15.c as remembered)
+ *                  1: precomputed s[0..8] / sv[0..7] coefficients, the form the reference's own copy of the same
+ *                     polynomial uses (reference src/assist.c:562-596) -- same value, different rounding
+ *   reject_restores_acc 1: a rejected step restores accelerations together with positions and velocities
+ *                       0: positions and velocities only */
+static int shim_predictor_form = 0;
+static int shim_reject_restores_acc = 1;
+void reb_shim_set_variant(int predictor_form, int reject_restores_acc){
+    shim_predictor_form = predictor_form;
+    shim_reject_restores_acc = reject_restores_acc;
+}
+
 /* ------------------------------------------------------------------------ */
 /* simulation life cycle                                                    */
 /* ------------------------------------------------------------------------ */
@@ -417,6 +433,41 @@ static int ias15_step(struct reb_simulation* r){
         for (int n = 1; n < 8; n++){
             r->t = t_beginning + r->dt * hh[n];
 
+            if (shim_predictor_form == 1){
+                /* s[] form: x = x0 + (s8 b6 + ... + s2 b0 + s1 a0 + s0 v0), compensated sums subtracted first */
+                const double h = hh[n];
+                double s[9], sv[8];
+                s[0] = r->dt * h;
+                s[1] = s[0] * s[0] / 2.;
+                s[2] = s[1] * h / 3.;
+                s[3] = s[2] * h / 2.;
+                s[4] = 3. * s[3] * h / 5.;
+                s[5] = 2. * s[4] * h / 3.;
+                s[6] = 5. * s[5] * h / 7.;
+                s[7] = 3. * s[6] * h / 4.;
+                s[8] = 7. * s[7] * h / 9.;
+                sv[0] = r->dt * h;
+                sv[1] = sv[0] * h / 2.;
+                sv[2] = 2. * sv[1] * h / 3.;
+                sv[3] = 3. * sv[2] * h / 4.;
+                sv[4] = 4. * sv[3] * h / 5.;
+                sv[5] = 5. * sv[4] * h / 6.;
+                sv[6] = 6. * sv[5] * h / 7.;
+                sv[7] = 7. * sv[6] * h / 8.;
+                for (int i = 0; i < N; i++){
+                    double* const px[3] = {&particles[i].x, &particles[i].y, &particles[i].z};
+                    double* const pv[3] = {&particles[i].vx, &particles[i].vy, &particles[i].vz};
+                    for (int c = 0; c < 3; c++){
+                        const int k = 3*i+c;
+                        const double xk = -csx[k] + (s[8]*b.p6[k] + s[7]*b.p5[k] + s[6]*b.p4[k] + s[5]*b.p3[k] + s[4]*b.p2[k] + s[3]*b.p1[k] + s[2]*b.p0[k] + s[1]*a0[k] + s[0]*v0[k]);
+                        *px[c] = xk + x0[k];
+                        if (r->additional_forces && r->force_is_velocity_dependent){
+                            const double vk = -csv[k] + (sv[7]*b.p6[k] + sv[6]*b.p5[k] + sv[5]*b.p4[k] + sv[4]*b.p3[k] + sv[3]*b.p2[k] + sv[2]*b.p1[k] + sv[1]*b.p0[k] + sv[0]*a0[k]);
+                            *pv[c] = vk + v0[k];
+                        }
+                    }
+                }
+            } else {
             for (int i = 0; i < N; i++){
                 const int k0 = 3*i+0, k1 = 3*i+1, k2 = 3*i+2;
                 double xk0 = -csx[k0] + ((((((((b.p6[k0]*7.*hh[n]/9. + b.p5[k0])*3.*hh[n]/4. + b.p4[k0])*5.*hh[n]/7. + b.p3[k0])*2.*hh[n]/3. + b.p2[k0])*3.*hh[n]/5. + b.p1[k0])*hh[n]/2. + b.p0[k0])*hh[n]/3. + a0[k0])*r->dt*hh[n]/2. + v0[k0])*r->dt*hh[n];
@@ -438,6 +489,7 @@ static int ias15_step(struct reb_simulation* r){
                 }
             }
 
+            }
             reb_simulation_update_acceleration(r);
 
             for (int k = 0; k < N; ++k){
@@ -602,7 +654,7 @@ static int ias15_step(struct reb_simulation* r){
                 particles[k].x = x0[3*k+0]; particles[k].y = x0[3*k+1]; particles[k].z = x0[3*k+2];
                 particles[k].vx = v0[3*k+0]; particles[k].vy = v0[3*k+1]; particles[k].vz = v0[3*k+2];
                 /* the retry starts from the accelerations at the beginning of the step */
-                particles[k].ax = a0[3*k+0]; particles[k].ay = a0[3*k+1]; particles[k].az = a0[3*k+2];
+                if (shim_reject_restores_acc){ particles[k].ax = a0[3*k+0]; particles[k].ay = a0[3*k+1]; particles[k].az = a0[3*k+2]; }
             }
             r->dt = dt_new;
             if (r->dt_last_done != 0.){

@@ -453,7 +453,34 @@ def test_branch_free_division_and_sqrt(lib):
     operators bit for bit on 2^28 seeded operand pairs (random and structured mantissas, exponents over the whole
     range the callers' guard lets through)."""
     bad = (ctypes.c_ulonglong * 2)(7, 7)
-    lib.assist_gpu_selftest_fp.argtypes = [ctypes.c_ulonglong, ctypes.c_longlong, ctypes.POINTER(ctypes.c_ulonglong)]
     rc = lib.assist_gpu_selftest_fp(20261017, 1 << 28, bad)
     assert rc == 0, lib.assist_gpu_last_error()
     assert (bad[0], bad[1]) == (0, 0)
+
+
+def test_one_population_over_several_devices(eph, fmt, lib):
+    """assist_gpu_multi_*: the library deals a population out over the devices, runs them side by side on host threads
+    and gathers the outputs in the caller's order -- the bits of a single-device batch.  On a one-GPU box the two
+    sub-batches share device 0 (the deal, the threads and the gather are the same code)."""
+    n = 3000
+    st = populations.neo_mba_mix(n, seed=77)
+    one = ab.Batch(eph, n, 0, ab.PER_PARTICLE, forces=0x7F, min_dt=1e-3)
+    one.set_state(cases.T0, st[:, None, :])
+    one.integrate(cases.T0 + 500.0)
+    want, wc = one.get_state(), one.counters()
+    devices = [0, 1, 2] if lib.assist_gpu_device_count() >= 3 else ([0, 1] if lib.assist_gpu_device_count() >= 2 else [0, 0])
+    m = ab.MultiBatch(eph, n, 0, devices=devices, forces=0x7F, min_dt=1e-3)
+    assert m.n_devices == len(devices)
+    m.set_state(cases.T0, st[:, None, :])
+    m.integrate(cases.T0 + 500.0)
+    got, gc = m.get_state(), m.counters()
+    for k in ("state", "t", "dt", "dt_last_done", "status"):
+        assert np.array_equal(got[k], want[k]), k
+    for k in ("steps", "rejected", "iters", "evals"):
+        assert np.array_equal(gc[k], wc[k]), k
+    s = m.stats()
+    assert s["steps"] == one.stats()["steps"] and len(s["kernel_ms_per_device"]) == len(devices)
+    # epoch output through the same deal
+    times = cases.T0 + 500.0 + 25.0 * np.arange(1, 9)
+    assert same(m.integrate_or_interpolate(times), one.integrate_or_interpolate(times))
+    m.close(); one.close()
