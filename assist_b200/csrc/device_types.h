@@ -119,6 +119,7 @@ struct AbSlices {
     int n_win;
     int* done;                /* [n] windows completed per system */
     int* epoch;               /* [n] next output epoch per system (epoch runs) */
+    long long attempt_budget; /* step attempts per system and call before it is retired with an error (<= 0: unlimited) */
     const int* order;         /* [n] or NULL: the queue hands out system order[k] as its k-th item of a window (longest expected first) */
 };
 

@@ -162,8 +162,11 @@ template <int LEVEL>
 __device__ __forceinline__ void ab_ascii_work(const double* __restrict__ Pcol, int ncf, int niv, double c,
                                               double t0, double u[3], double v[3], double w[3]) {
     const double tt = t0 * (double)niv;
-    const int b = (int)tt;
-    const double frac = tt - (double)b;            /* == fmod(tt, 1.0) for tt >= 0, exactly */
+    int b = (int)tt;
+    /* t0 == 1 only at the very end of the file's coverage (jd == end): the last sub-interval at z = +1.  The reference
+     * indexes one sub-interval past the column there (src/ascii_ephem.c:37-41) and returns whatever follows. */
+    if (b > niv - 1) b = niv - 1;
+    const double frac = tt - (double)b;            /* == fmod(tt, 1.0) for 0 <= tt < niv, exactly */
     const double z = 2.0 * frac - 1.0;
     ab_cheb3<LEVEL, false>(Pcol + ncf * (b * 3), ncf, z, c, u, v, w);
 }
@@ -406,7 +409,8 @@ __device__ __noinline__ void ab_ascii_pos_multi(const AbEphem& E, int col, const
         const double* rec = E.ascii_img + (blk + 2) * E.a_rec_words;
         const double tr = ab_divc((E.jd_ref - E.a_beg - (double)blk * E.a_inc) + t[k], E.a_inc, E.a_inc_rd);
         const double tt = tr * (double)niv;
-        const int b = (int)tt;
+        int b = (int)tt;
+        if (b > niv - 1) b = niv - 1;              /* jd == end of coverage, see ab_ascii_work */
         z[k] = 2.0 * (tt - (double)b) - 1.0;
         cf[k] = rec + E.a_off[col] + ncf * (b * 3);
     }

@@ -931,6 +931,7 @@ static double unkey(unsigned long long k) {
 static int build_slices(assist_gpu_batch* b, const AbEphem& E, double t_end, AbSlices* SL) {
     SL->origin = 0.0; SL->wlen = 1.0; SL->n_win = 1;
     SL->done = b->d_slice_done; SL->epoch = b->d_slice_epoch; SL->order = b->d_order;
+    SL->attempt_budget = b->attempt_budget;
     if (b->slice_days > 0.0 && t_end == t_end) {
         unsigned long long init[2] = {~0ULL, 0ULL}, got[2];
         CU(cudaMemcpy(b->d_trange, init, sizeof(init), cudaMemcpyHostToDevice));

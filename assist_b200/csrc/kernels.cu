@@ -417,6 +417,7 @@ pp_queue_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbFor
     long long sys = -1;
     int nv = 0, ep = 0, win = 0;
     double target = tmax, wend = 0.0;
+    long long attempts = 0;
     PPState P;
     while (true) {
         /* Phase A, per lane: get to a point where a step is due.  A lane whose system pauses or finishes stores it
@@ -467,6 +468,7 @@ pp_queue_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbFor
             W.status[slot] = 0;
             pp_copy_system<true>(Bt, sys, W, slot, nv);
             have = true;
+            attempts = 0;
         }
         if (!have) break;
         /* bookkeeping until a step is due, the window ends or the system is done */
@@ -488,6 +490,13 @@ pp_queue_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbFor
             }
             if (integrating && !last && wsign * P.t >= wsign * wend) break;      /* end of the window: pause integrate() */
             if (integrating && ab_check_exit(P.t, P.dt, P.dt_last, P.status, target, exact_finish_time, P.last_full_dt) < 0) {
+                /* a step that cannot advance the time, or a system over its budget of attempts, is retired with an
+                 * error instead of holding the resident grid forever (message 7 of assist_error_messages) */
+                if (P.dt == 0.0 || (SL.attempt_budget > 0 && attempts >= SL.attempt_budget)) {
+                    P.status = 1;
+                    W.status[slot] = 1000 + 7;
+                    continue;
+                }
                 step_due = true;
                 break;
             }
@@ -517,6 +526,7 @@ pp_queue_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbFor
         if (!__syncthreads_or((have || pending) ? 1 : 0)) break;
         __syncwarp();
         if (step_due) {
+            attempts++;
             if (F.gr_eih_sources == 1 && !F.geocentric) pp_step_nodes<PP_KM>(E, F, W, slot, P);
             else pp_step<PP_KM>(E, F, W, slot, P);
         }

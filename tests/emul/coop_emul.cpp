@@ -181,7 +181,7 @@ extern "C" int abc_emul_run(void* h, const void* E_, const void* F_, const void*
     unsigned long long queue = 0;
     A.queue_head = &queue;
     std::vector<int> done((size_t)A.Bt.n, 0), epoch((size_t)A.Bt.n, 0);
-    A.SL.origin = 0.0; A.SL.wlen = 1.0; A.SL.n_win = 1; A.SL.done = done.data(); A.SL.epoch = epoch.data(); A.SL.order = nullptr;
+    A.SL.origin = 0.0; A.SL.wlen = 1.0; A.SL.n_win = 1; A.SL.done = done.data(); A.SL.epoch = epoch.data(); A.SL.order = nullptr; A.SL.attempt_budget = 0;
     A.times = times; A.n_times = n_times; A.out = out;
     A.plan = *(const AbcPlan*)plan_;
     A.timing = nullptr;

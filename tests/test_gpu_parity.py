@@ -484,3 +484,32 @@ def test_one_population_over_several_devices(eph, fmt, lib):
     times = cases.T0 + 500.0 + 25.0 * np.arange(1, 9)
     assert same(m.integrate_or_interpolate(times), one.integrate_or_interpolate(times))
     m.close(); one.close()
+
+
+@pytest.mark.parametrize("nvar", [0, 1])
+def test_a_stuck_system_is_retired_not_looped_on(eph, fmt, monkeypatch, nvar):
+    """a zero timestep or an exhausted budget of step attempts ends THAT system with an error status
+    (1000 + message 7) and the launch returns; the other systems finish.  nvar = 0 runs pp_coop_kernel, nvar = 1
+    the work-queue kernel."""
+    st = populations.main_belt(40, seed=9)
+    state = populations.with_variations(st, nvar) if nvar else st[:, None, :]
+    b = ab.Batch(eph, 40, nvar, ab.PER_PARTICLE, forces=0x7F)
+    b.set_state(cases.T0, state, dt0=0.0)
+    b.integrate(cases.T0 + 10.0)
+    assert (b.get_state()["status"] == 1007).all()
+    b.close()
+    monkeypatch.setenv("ASSIST_B200_ATTEMPT_BUDGET", "5")
+    b = ab.Batch(eph, 40, nvar, ab.PER_PARTICLE, forces=0x7F)
+    b.set_state(cases.T0, state)
+    b.integrate(cases.T0 + 1000.0)
+    got = b.get_state()
+    c = b.counters()
+    assert (got["status"] == 1007).all() and (got["t"] < cases.T0 + 1000.0).all()
+    assert (c["steps"] + (c["rejected"] if nvar == 0 else 0) == 5).all()
+    b.close()
+    monkeypatch.delenv("ASSIST_B200_ATTEMPT_BUDGET")
+    b = ab.Batch(eph, 40, nvar, ab.PER_PARTICLE, forces=0x7F)
+    b.set_state(cases.T0, state)
+    b.integrate(cases.T0 + 100.0)
+    assert (b.get_state()["status"] == 0).all()
+    b.close()
