@@ -666,8 +666,11 @@ __device__ __forceinline__ double abc_sum_forces(const AbEphem& E, const AbForce
         const double beta = 1.0;
         const double gamma = 1.0;
         double term0_sum = 0.0;
+        double qk[AB_NPLANETS];
 #pragma unroll
-        for (int k = 0; k < AB_NPLANETS; k++) term0_sum += sm.q(k, slot);
+        for (int k = 0; k < AB_NPLANETS; k++) qk[k] = sm.q(k, slot);
+#pragma unroll
+        for (int k = 0; k < AB_NPLANETS; k++) term0_sum += qk[k];
         double term0 = term0_sum;
         term0 *= -2 * (beta + gamma) * over_C2;
         const double term1 = sm.con(ABC_C_T + 0, slot), term2 = sm.con(ABC_C_T + 1, slot), term3 = sm.con(ABC_C_T + 2, slot);
@@ -679,13 +682,25 @@ __device__ __forceinline__ double abc_sum_forces(const AbEphem& E, const AbForce
     if (F.forces & 0x100) a += sm.con(ABC_C_GRPOT + c, slot);
     if (F.forces & 0x80) a += sm.con(ABC_C_GRSIMPLE + c, slot);
     if (F.forces & (0x01 | 0x02 | 0x04)) {
+        /* the 27 terms of the direct sum in the reference's order; the values are fetched from shared memory EIGHT AT A
+         * TIME before they are subtracted, so that the chain of dependent subtractions does not wait for one load per
+         * term (a missing asteroid is +0.0: a - 0.0 == a exactly, signed zeros included) */
         const int ast_num = E.n_ast;
-        if (F.forces & 0x04)
-            for (int k = 0; k < ast_num; k++) a -= sm.prod(AB_NPLANETS + k, c, slot);
+        if (F.forces & 0x04) {
+#pragma unroll 1
+            for (int k0 = 0; k0 < ast_num; k0 += 8) {
+                double pa[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) pa[j] = (k0 + j < ast_num) ? sm.prod(AB_NPLANETS + k0 + j, c, slot) : 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) a -= pa[j];
+            }
+        }
         if (F.forces & 0x02) {
-            a -= sm.prod(10, c, slot); a -= sm.prod(4, c, slot); a -= sm.prod(5, c, slot); a -= sm.prod(1, c, slot);
-            a -= sm.prod(9, c, slot); a -= sm.prod(8, c, slot); a -= sm.prod(3, c, slot); a -= sm.prod(2, c, slot);
-            a -= sm.prod(7, c, slot); a -= sm.prod(6, c, slot);
+            const double p10 = sm.prod(10, c, slot), p4 = sm.prod(4, c, slot), p5 = sm.prod(5, c, slot), p1 = sm.prod(1, c, slot);
+            const double p9 = sm.prod(9, c, slot), p8 = sm.prod(8, c, slot), p3 = sm.prod(3, c, slot), p2 = sm.prod(2, c, slot);
+            const double p7 = sm.prod(7, c, slot), p6 = sm.prod(6, c, slot);
+            a -= p10; a -= p4; a -= p5; a -= p1; a -= p9; a -= p8; a -= p3; a -= p2; a -= p7; a -= p6;
         }
         if (F.forces & 0x01) a -= sm.prod(0, c, slot);
     }
