@@ -7,7 +7,8 @@
 Default workload (BASELINE.json configs[2], "c3", the configuration the metric is quoted on):
 synthetic NEO+MBA population, per-particle adaptive dt, all default forces (mask 0x7F,
 gr_eih_sources 1), 10 yr forward, synthetic DE440-layout planets .bsp + 16-asteroid .bsp.
-The other configs of BASELINE.json are available with --workload c2|c4|c5.
+The other configs of BASELINE.json are available with --workload c2|c4|c5, the north star's target
+configuration (10^6 particles WITH variational equations, 10 yr) with --workload target.
 One bench "step" = one full pass of the hot path over the batch (every particle integrated over
 the whole span).  Scaling: C3 is the configuration BASELINE.json states as "10^6 ... sharded 1/2/4/8", so its
 default is STRONG scaling -- one population of --n particles in total, dealt out round-robin over the GPUs; at
@@ -77,6 +78,10 @@ def workloads():
                         "per-particle dt, forces 0x7F, 1826.25 d forward",
                    gen=lambda n, seed: pop.with_variations(pop.main_belt(n, seed=seed), 6), prm=None,
                    seed=20261704, n=100000, nvar=6, mode="pp", forces=0x7F, min_dt=0.0, span=1826.25, dense=None, cpu_per_core=600),
+        "target": dict(desc="north-star target: 10^6 main-belt particles, each with 6 first-order variational particles, per-particle dt, "
+                            "forces 0x7F, min_dt 0.001 d, 3652.5 d forward (BASELINE.json north_star, last sentence)",
+                       gen=lambda n, seed: pop.with_variations(pop.main_belt(n, seed=seed), 6), prm=None,
+                       seed=20261706, n=1000000, nvar=6, mode="pp", forces=0x7F, min_dt=1e-3, span=3652.5, dense=None, cpu_per_core=300),
         "c5": dict(desc="C5 comets with Marsden A1/A2/A3, per-particle dt, forces 0x7F, min_dt 0.001 d, 18262.5 d BACKWARD, "
                         "dense output every 10 d (assist_integrate_or_interpolate semantics)",
                    gen=lambda n, seed: pop.comets(n, seed=seed)[0][:, None, :],
@@ -212,7 +217,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c2", "c3", "c4", "c5", "target"])
     ap.add_argument("--n-per-gpu", type=int, default=0, help="particles per GPU (0 = the workload's own size)")
     ap.add_argument("--math", default="strict", choices=["strict", "fast"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the CPU baseline sample (0 = sized for ~10-30 s)")
@@ -231,7 +236,7 @@ def main():
     from assist_b200.synth import ephem_writer, populations
     wl = workloads()[args.workload]
     if args.scaling is None:
-        args.scaling = "strong" if args.workload == "c3" else "weak"
+        args.scaling = "strong" if args.workload in ("c3", "target") else "weak"
     n_req = args.n_per_gpu or wl["n"]
     T0 = populations.T0
     T_END = T0 + wl["span"]
