@@ -560,10 +560,36 @@ struct reb_simulation* assist_create_interpolated_simulation(struct reb_simulati
     return NULL;
 }
 
+/* reference src/tools.c:35-70: a plain REBOUND simulation holding the ephemeris bodies at r->t as active particles
+ * followed by r's own particles.  The body states come from the GPU ephemeris evaluation (assist_get_particle); the
+ * returned simulation is data -- integrating it needs REBOUND's own N-body gravity, which this library does not
+ * replace (reb_simulation_integrate on it fails with a message: no ASSIST extras attached).
+ * As in the reference, all eleven bodies are added whatever merge_moon is (its filter `i != EARTH || i != MOON` is
+ * always true) and merge_moon = 1 appends the Earth-Moon barycentre as a twelfth active particle. */
 struct reb_simulation* assist_simulation_convert_to_rebound(const struct reb_simulation* r, const struct assist_ephem* ephem, int merge_moon) {
-    (void)r; (void)ephem; (void)merge_moon;
-    fprintf(stderr, "(ASSIST) assist_simulation_convert_to_rebound needs REBOUND's N-body gravity, which is outside the scope of assist-b200.\n");
-    return NULL;
+    if (!r || !ephem) return NULL;
+    struct reb_simulation* r2 = reb_simulation_create();
+    if (!r2) return NULL;
+    r2->t = r->t;
+    r2->dt = r->dt;
+    r2->ri_ias15.epsilon = r->ri_ias15.epsilon;
+    r2->ri_ias15.adaptive_mode = r->ri_ias15.adaptive_mode;
+    for (int i = 0; i < 11; i++) {
+        int error = 0;
+        struct reb_particle p = assist_get_particle_with_error(ephem, i, r->t, &error);
+        if (error != ASSIST_SUCCESS) fprintf(stderr, "(ASSIST) An error occured while trying to initialize particle from ephemeris data.\n");
+        else reb_simulation_add(r2, p);
+    }
+    if (merge_moon) {
+        int error = 0;
+        struct reb_particle p1 = assist_get_particle_with_error(ephem, ASSIST_BODY_EARTH, r->t, &error);
+        struct reb_particle p2 = assist_get_particle_with_error(ephem, ASSIST_BODY_MOON, r->t, &error);
+        if (error != ASSIST_SUCCESS) fprintf(stderr, "(ASSIST) An error occured while trying to initialize particle from ephemeris data.\n");
+        else reb_simulation_add(r2, reb_particle_com_of_pair(p1, p2));
+    }
+    r2->N_active = (int)r2->N;
+    for (unsigned int i = 0; i < r->N; i++) reb_simulation_add(r2, r->particles[i]);
+    return r2;
 }
 
 }  // extern "C"

@@ -513,3 +513,33 @@ def test_a_stuck_system_is_retired_not_looped_on(eph, fmt, monkeypatch, nvar):
     b.integrate(cases.T0 + 100.0)
     assert (b.get_state()["status"] == 0).all()
     b.close()
+
+
+@pytest.mark.parametrize("merge_moon", [0, 1])
+def test_convert_to_rebound_matches_the_reference(eph, fmt, ref, paths, lib, merge_moon):
+    """assist_simulation_convert_to_rebound (reference src/tools.c:35-70) on both libraries: the same particles in the
+    same order (eleven ephemeris bodies, the Earth-Moon barycentre when asked for, then the test particles), N_active,
+    t, dt -- the body states coming from the GPU ephemeris evaluation are the reference's bits."""
+    reph = rh.open_ephem(ref, planets_path(paths, fmt), paths["asteroids_bsp"])
+    st = populations.main_belt(3, seed=5)
+    out = []
+    for L, E in ((ref, reph), (lib, eph.ptr)):
+        L.assist_simulation_convert_to_rebound.restype = ctypes.POINTER(type(L.reb_simulation_create().contents))
+        L.assist_simulation_convert_to_rebound.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        r = L.reb_simulation_create()
+        ax = L.assist_attach(r, E)
+        r.contents.t = cases.T0 + 12.5
+        for s in st:
+            L.reb_simulation_add(r, Particle(x=s[0], y=s[1], z=s[2], vx=s[3], vy=s[4], vz=s[5]))
+        r2 = L.assist_simulation_convert_to_rebound(ctypes.cast(r, ctypes.c_void_p), ctypes.cast(E, ctypes.c_void_p), merge_moon)
+        assert bool(r2)
+        c = r2.contents
+        rows = np.array([[c.particles[i].x, c.particles[i].y, c.particles[i].z, c.particles[i].vx, c.particles[i].vy, c.particles[i].vz,
+                          c.particles[i].m] for i in range(c.N)])
+        out.append((int(c.N), int(c.N_active), c.t, c.dt, rows))
+        L.reb_simulation_free(r2)
+        L.assist_free(ax)
+        L.reb_simulation_free(r)
+    assert out[0][0] == out[1][0] == 11 + merge_moon + 3 and out[0][1] == out[1][1] == 11 + merge_moon
+    assert out[0][2] == out[1][2] and out[0][3] == out[1][3]
+    assert np.array_equal(out[0][4], out[1][4])
