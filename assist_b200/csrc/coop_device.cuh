@@ -1,23 +1,29 @@
 /*
- * coop_device.cuh -- per-particle-dt IAS15 with a whole CTA stepping 32 systems together.
+ * coop_device.cuh -- per-particle-dt IAS15 with a CTA stepping 2 x 32 systems together.
  *
  * Why: one thread per system (kernels.cu, pp_queue_kernel) keeps the 8 body tables of a step (6 KB) and the
  * IAS15 tables in thread-local / global memory and walks one dependent chain per system.  Here a system's
- * working set lives ON CHIP -- the body tables of its 8 node times in shared memory, its IAS15 state in the
- * registers of three "component" warps -- and the independent work of a step is spread over the CTA:
+ * working set lives ON CHIP -- the planets at its 8 node times in shared memory, its IAS15 state in the
+ * registers of three "component" warps -- and the independent work of a step is spread over warps:
  *
- *     lane  = system slot (32 systems per CTA, structure-of-arrays in shared memory with stride 32:
- *             every access of a warp is 32 consecutive doubles, conflict free)
- *     warp  = task
+ *     group = 32 systems with 8 warps of their own, a 102 KB block of shared memory and a 110 KB table in global
+ *             memory (L2) for what one task reads once per node (asteroid positions, Sun velocity, EIH pair sums).
+ *             A CTA holds TWO groups that walk through the phases of a step attempt together (CTA-wide barriers):
+ *             every latency-bound phase serves 64 systems, and all 16 warps of the SM run the same code at the
+ *             same time (the hot code of the roles is larger than the instruction cache).
+ *     lane  = system slot (structure-of-arrays in shared memory with stride 32: every access of a warp is
+ *             32 consecutive doubles, conflict free)
+ *     warp  = task (index inside the group)
  *         warps 0-2    component x / y / z of every system: predictor, ordered force sums, g/b update,
  *                      advance, predict_next  (b, g, e, csb, x0, v0, a0, cs* in registers)
  *         warp  3      control: queue, reb_simulation_integrate bookkeeping, output epochs, convergence and
  *                      step-size control (sqrt7)
- *         warps 4-15   workers: one body of the direct term (+ its share of the EIH sums) or one of the
- *                      single-body terms (Earth J2-J4, solar J2, EIH source block, Marsden, GR variants) per task
- *         all 16       the Chebyshev fill of the node tables: thread = (slot, node), so the eight nodes of a
+ *         warps 4-7    workers: their share of the 27 bodies of the direct term (+ the planets' terms of the EIH
+ *                      potential sum) and of the single-body terms (Earth J2-J4, solar J2, EIH source block,
+ *                      Marsden, GR variants), from a launch-time plan (gpu_api.cu: build_coop_plan)
+ *         all 8        the Chebyshev fill of the node tables: thread = (slot, node), so the eight nodes of a
  *                      system read the same one or two coefficient records (broadcast loads instead of 32 lanes
- *                      gathering 32 records)
+ *                      gathering 32 records), and everything one (slot, node) needs comes from one thread
  *
  * Values are those of the one-thread-per-system path, bit for bit in the strict build: every term is formed
  * by the same operations, and the sums that the reference accumulates in a fixed order (27 direct terms,
@@ -31,7 +37,7 @@
  *
  * The code is written as warp-level role functions made of per-lane blocks (ABC_LANES) separated by CTA
  * barriers (ABC_SYNC).  Built with AB_HOST_EMUL the same source runs on the host, one OS thread per warp
- * (tests/emul): that is how the control flow was brought up without a GPU.
+ * (tests/emul): that is how the control flow is checked without a GPU.
  */
 #ifndef AB_COOP_DEVICE_CUH
 #define AB_COOP_DEVICE_CUH

@@ -1,6 +1,7 @@
 /*
  * coop_roles.cuh -- the three warp roles of pp_coop_kernel and the barrier protocol between them
- * (see coop_device.cuh for the mapping).  One trip of the CTA loop is one IAS15 step ATTEMPT of every slot:
+ * (see coop_device.cuh for the mapping).  One trip of the CTA loop is one IAS15 step ATTEMPT of every slot of both
+ * groups; the barriers are CTA-wide, "all" = the 8 warps of each group:
  *
  *   barrier  who            what
  *   -------  -------------  ----------------------------------------------------------------------
@@ -38,17 +39,6 @@ namespace AB_NS {
 #define ABC_TICK(slot_) do { } while (0)
 #else
 #define ABC_TICK(slot_) do { if (A.timing && threadIdx.x == 32 * ABC_CTRL_WARP) { const long long now_ = clock64(); tacc[slot_] += (unsigned long long)(now_ - tlast); tlast = now_; } } while (0)
-#endif
-
-/* probes of one warp's own time (component warp x of the CTA's first group): BEGIN..MID = busy, MID..END = waiting */
-#ifdef AB_HOST_EMUL
-#define ABC_PROBE_BEGIN() do { } while (0)
-#define ABC_PROBE_MID(slot_) do { } while (0)
-#define ABC_PROBE_END(slot_) do { } while (0)
-#else
-#define ABC_PROBE_BEGIN() do { if (A.timing && threadIdx.x == 0) pr_t = clock64(); } while (0)
-#define ABC_PROBE_MID(slot_) do { if (A.timing && threadIdx.x == 0) { const long long now_ = clock64(); atomicAdd(A.timing + slot_, (unsigned long long)(now_ - pr_t)); pr_t = now_; } } while (0)
-#define ABC_PROBE_END(slot_) do { if (A.timing && threadIdx.x == 0 && pr_t) { const long long now_ = clock64(); atomicAdd(A.timing + slot_, (unsigned long long)(now_ - pr_t)); pr_t = 0; } } while (0)
 #endif
 
 #define ABC_ERR_BUDGET 7      /* index into assist_error_messages: step budget exhausted / dt == 0 */
@@ -375,9 +365,6 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
     AbcComp st[ABC_NL];
     const AbBatch& W = A.W;
     const long long wn = W.n;
-#ifndef AB_HOST_EMUL
-    long long pr_t = 0;
-#endif
     for (;;) {
         if (!ABC_SYNC_OR(0)) return;                                             /* B1 */
         abc_fill_warp(ABC_CTXPASS A.gtab + (long long)ABC_BLOCK * ABC_GT_DOUBLES, c);
@@ -418,7 +405,6 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
         for (;;) {
             for (int nn = 1; nn < 8; nn++) {
                 ABC_SYNC();                                                      /* B7 */
-                ABC_PROBE_END(13);
                 if (nn < 6) {
                     /* while the workers evaluate node nn: the part of the prediction for node nn + 1 that the
                      * coming update cannot change (it touches b_0 .. b_{nn-1}) */
@@ -431,7 +417,6 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
                     }
                 }
                 ABC_SYNC();                                                      /* B8 */
-                ABC_PROBE_BEGIN();
                 ABC_LANES(l) {
                     if (sm.flag(ABC_SMI_SW, l)) {
                         AbcComp& s = st[ABC_LI(l)];
@@ -452,7 +437,6 @@ __device__ void abc_comp_main(ABC_CTXARG const AbEphem& E, const AbForceOpts& F,
                         }
                     }
                 }
-                ABC_PROBE_MID(12);
             }
             ABC_SYNC();                                                          /* B9 */
             if (!ABC_SYNC_OR(0)) break;                                          /* B10 */

@@ -1059,8 +1059,6 @@ static void coop_timing_report(assist_gpu_batch* b) {
     fprintf(stderr, "[assist-b200 coop timing] grid %d, attempts/CTA %.0f, evals/CTA %.0f, cycles/CTA %.3e\n", b->coop_grid,
             (double)t[10] / b->coop_grid, (double)t[11] / b->coop_grid, tot / b->coop_grid);
     for (int q = 0; q < 10; q++) if (q != 4) fprintf(stderr, "    %-14s %5.1f %%   %9.0f cycles per attempt\n", nm[q], 100.0 * t[q] / tot, (double)t[q] / (double)(t[10] ? t[10] : 1));
-    fprintf(stderr, "    component warp x of every CTA's first group: busy %.0f, waiting %.0f cycles per node round\n",
-            (double)t[12] / (double)(t[11] ? t[11] : 1), (double)t[13] / (double)(t[11] ? t[11] : 1));
 }
 
 static int ensure_coop_batch(assist_gpu_batch* b, bool fast) {
