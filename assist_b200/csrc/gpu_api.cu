@@ -434,6 +434,28 @@ extern "C" int assist_gpu_ephem_nbodies(const struct assist_ephem* ephem) {
     return AB_NPLANETS + (ephem->spk_asteroids ? ephem->spk_asteroids->num : 0);
 }
 
+/* Device scratch of the synchronous single-call entry points (assist_gpu_ephem_eval, assist_gpu_eval_forces: what
+ * assist_get_particle, reb_simulation_update_acceleration and the REBOUND-driven plug-in path go through): grow-only
+ * buffers per host thread and device instead of four cudaMalloc / cudaFree pairs per call. */
+struct AbScratch { void* p[5]; size_t cap[5]; };
+static thread_local AbScratch g_scratch[ASSIST_B200_MAX_DEVICES];
+static int scratch_get(int slot, size_t bytes, void** out) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= ASSIST_B200_MAX_DEVICES) return set_err(ASSIST_GPU_ERR_ARG, "device index %d out of range", dev);
+    AbScratch& s = g_scratch[dev];
+    if (s.cap[slot] < bytes) {
+        if (s.p[slot]) cudaFree(s.p[slot]);
+        s.p[slot] = nullptr; s.cap[slot] = 0;
+        const size_t want = bytes < 4096 ? 4096 : bytes + bytes / 4;
+        CU(cudaMalloc(&s.p[slot], want));
+        s.cap[slot] = want;
+    }
+    *out = s.p[slot];
+    return 0;
+}
+#define SCRATCH(slot, bytes, ptr) do { int rc_ = scratch_get((slot), (bytes), (void**)&(ptr)); if (rc_) return rc_; } while (0)
+
 extern "C" int assist_gpu_ephem_eval(const struct assist_ephem* ephem, int math, const double* t, int n_t,
                                      double* out, int* status) {
     AbEphem E;
@@ -443,9 +465,9 @@ extern "C" int assist_gpu_ephem_eval(const struct assist_ephem* ephem, int math,
     const int nb = AB_NPLANETS + E.n_ast;
     double *d_t = nullptr, *d_out = nullptr;
     int* d_st = nullptr;
-    CU(cudaMalloc(&d_t, sizeof(double) * n_t));
-    CU(cudaMalloc(&d_out, sizeof(double) * 10 * (size_t)n_t * nb));
-    CU(cudaMalloc(&d_st, sizeof(int) * (size_t)n_t * nb));
+    SCRATCH(0, sizeof(double) * n_t, d_t);
+    SCRATCH(1, sizeof(double) * 10 * (size_t)n_t * nb, d_out);
+    SCRATCH(2, sizeof(int) * (size_t)n_t * nb, d_st);
     CU(cudaMemcpy(d_t, t, sizeof(double) * n_t, cudaMemcpyHostToDevice));
     cudaError_t e = (math == ASSIST_GPU_MATH_FAST) ? ab_launch_ephem_eval_fast(E, d_t, n_t, d_out, d_st, 0)
                                                    : ab_launch_ephem_eval_strict(E, d_t, n_t, d_out, d_st, 0);
@@ -453,7 +475,6 @@ extern "C" int assist_gpu_ephem_eval(const struct assist_ephem* ephem, int math,
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * 10 * (size_t)n_t * nb, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && status) e = cudaMemcpy(status, d_st, sizeof(int) * (size_t)n_t * nb, cudaMemcpyDeviceToHost);
-    cudaFree(d_t); cudaFree(d_out); cudaFree(d_st);
     if (e != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "ephem_eval: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -472,12 +493,12 @@ extern "C" int assist_gpu_eval_forces(const struct assist_ephem* ephem, const st
     const size_t nt = t_per_system ? n_sys : 1;
     double *d_t = nullptr, *d_state = nullptr, *d_prm = nullptr, *d_acc = nullptr;
     int* d_st = nullptr;
-    CU(cudaMalloc(&d_t, sizeof(double) * nt));
-    CU(cudaMalloc(&d_state, sizeof(double) * 6 * (size_t)n_sys * K));
-    CU(cudaMalloc(&d_acc, sizeof(double) * 3 * (size_t)n_sys * K));
-    CU(cudaMalloc(&d_st, sizeof(int) * (size_t)n_sys));
+    SCRATCH(0, sizeof(double) * nt, d_t);
+    SCRATCH(1, sizeof(double) * 6 * (size_t)n_sys * K, d_state);
+    SCRATCH(2, sizeof(double) * 3 * (size_t)n_sys * K, d_acc);
+    SCRATCH(3, sizeof(int) * (size_t)n_sys, d_st);
     if (params) {
-        CU(cudaMalloc(&d_prm, sizeof(double) * 3 * (size_t)n_sys * K));
+        SCRATCH(4, sizeof(double) * 3 * (size_t)n_sys * K, d_prm);
         CU(cudaMemcpy(d_prm, params, sizeof(double) * 3 * (size_t)n_sys * K, cudaMemcpyHostToDevice));
     }
     CU(cudaMemcpy(d_t, t, sizeof(double) * nt, cudaMemcpyHostToDevice));
@@ -498,7 +519,6 @@ extern "C" int assist_gpu_eval_forces(const struct assist_ephem* ephem, const st
         }
         free(hst);
     }
-    cudaFree(d_t); cudaFree(d_state); cudaFree(d_prm); cudaFree(d_acc); cudaFree(d_st);
     if (e != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "eval_forces: %s", cudaGetErrorString(e));
     if (first_err) return set_err(first_err, "%s", assist_error_messages[first_err]);
     return 0;

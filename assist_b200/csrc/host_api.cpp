@@ -256,8 +256,9 @@ int assist_all_ephem(const struct assist_ephem* ephem, struct assist_ephem_cache
         for (int s = 0; s < 7; s++) if (cache->t[7 * i + s] == t) { item = cache->items[7 * i + s]; hit = true; break; }
     }
     if (!hit) {
-        std::vector<double> out;
-        std::vector<int> st;
+        /* per-thread buffers that keep their capacity: a cache miss does not allocate */
+        static thread_local std::vector<double> out;
+        static thread_local std::vector<int> st;
         const int rc = eval_all_bodies(ephem, t, out, st);
         if (rc) return map_gpu_error(rc);
         if (st[i] != ASSIST_SUCCESS) return st[i];
