@@ -130,3 +130,25 @@ def test_emul_errors_retire_a_system(eph, fmt):
     got = b.get_state()
     assert (got["status"] == 1007).all() and (got["counters"][:, 0] + got["counters"][:, 1] == 5).all()
     b.close()
+
+
+def test_emul_c3_subsample_ten_years(eph, fmt):
+    """The kernel's source on the host over the north star's span: every 25th particle of the fixed C3 subsample
+    (8 NEOs, 32 main-belt objects), 3652.5 d, min_dt 1e-3, against the reference's own output in golden_large.npz --
+    states, t, dt and the per-particle step / sweep / evaluation / rejection counts, bit for bit."""
+    import os
+    from conftest import ROOT
+    if fmt != "bsp":
+        pytest.skip("golden_large.npz holds the SPK planets file only")
+    G = np.load(os.path.join(ROOT, "tests", "golden", "golden_large.npz"))
+    pick = np.arange(0, 1000, 25)
+    st = cases.c3_subsample()[pick]
+    b = coop_emul.EmulBatch(eph, st.shape[0], n_blocks=1, forces=0x7F, min_dt=1e-3)
+    b.set_state(cases.T0, st)
+    b.integrate(cases.T0 + 3652.5)
+    got = b.get_state()
+    assert np.array_equal(got["state"], G["c3_final"][pick])
+    assert np.array_equal(got["t"], G["c3_t"][pick]) and np.array_equal(got["dt"], G["c3_dt"][pick])
+    c = got["counters"].astype(np.int64)          # steps, rejected, iters, evals
+    assert np.array_equal(np.stack([c[:, 0], c[:, 2], c[:, 3], c[:, 1]], axis=1), G["c3_counts"][pick])
+    b.close()
