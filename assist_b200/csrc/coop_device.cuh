@@ -46,6 +46,7 @@
 #include "ephem_device.cuh"
 #include "forces_device.cuh"
 #include "ias15_device.cuh"
+#include <string.h>
 
 /* node table in shared memory: the planets' positions of one (node, slot).  What a single task reads (asteroid
  * positions, the Sun's velocity, the particle-independent EIH sums) lives in the CTA's global table, device_types.h. */
@@ -64,18 +65,28 @@
 #define ABC_C_GRSIMPLE 24
 #define ABC_NCON 27
 
-/* shared-memory carve-up (doubles first, then ints): 102 KB, so that two CTAs fit an SM */
+/* shared-memory carve-up of a group (doubles first, then ints): 113.5 KB, two groups fill the 227 KB of an SM.
+ * XV .. MON are scratch of the node rounds and dead while the node tables are filled; together with the extension
+ * behind them they are the STAGING area of the fill (coefficient records copied in by the TMA unit, see below). */
 #define ABC_SM_TAB 0
-#define ABC_SM_XV (ABC_SM_TAB + 8 * ABC_NODE_STRIDE)
+#define ABC_SM_PRM (ABC_SM_TAB + 8 * ABC_NODE_STRIDE)
+#define ABC_SM_T0 (ABC_SM_PRM + 3 * ABC_SLOTS)               /* start time of the attempt */
+#define ABC_SM_DT (ABC_SM_T0 + ABC_SLOTS)                    /* step of the attempt */
+#define ABC_SM_RATIO (ABC_SM_DT + ABC_SLOTS)                 /* predict_next ratio */
+#define ABC_SM_XV (ABC_SM_RATIO + ABC_SLOTS)
 #define ABC_SM_PROD (ABC_SM_XV + 6 * ABC_SLOTS)
 #define ABC_SM_Q (ABC_SM_PROD + 81 * ABC_SLOTS)
 #define ABC_SM_CON (ABC_SM_Q + 11 * ABC_SLOTS)
 #define ABC_SM_MON (ABC_SM_CON + ABC_NCON * ABC_SLOTS)       /* |a| x3, |db6| x3, |b6| x3 */
-#define ABC_SM_PRM (ABC_SM_MON + 9 * ABC_SLOTS)
-#define ABC_SM_T0 (ABC_SM_PRM + 3 * ABC_SLOTS)               /* start time of the attempt */
-#define ABC_SM_DT (ABC_SM_T0 + ABC_SLOTS)                    /* step of the attempt */
-#define ABC_SM_RATIO (ABC_SM_DT + ABC_SLOTS)                 /* predict_next ratio */
-#define ABC_SM_DOUBLES (ABC_SM_RATIO + ABC_SLOTS)
+#define ABC_SM_EXT (ABC_SM_MON + 9 * ABC_SLOTS)
+#define ABC_SM_EXT_DOUBLES 1488
+#define ABC_SM_DOUBLES (ABC_SM_EXT + ABC_SM_EXT_DOUBLES)
+/* staging area: per warp two stage buffers of ABC_ST_BUF doubles; behind them, outside the scratch that the node rounds
+ * overwrite, per warp two mbarriers and one word with their phase bits */
+#define ABC_ST_BASE ABC_SM_XV
+#define ABC_ST_MBAR (ABC_SM_DOUBLES - 3 * ABC_GWARPS)
+#define ABC_ST_WARP (((ABC_ST_MBAR - ABC_ST_BASE) / ABC_GWARPS) & ~1)
+#define ABC_ST_BUF ((ABC_ST_WARP / 2) & ~1)
 #define ABC_SMI_ACTIVE 0      /* slot takes part in this attempt */
 #define ABC_SMI_NEEDA0 1      /* slot needs the force evaluation at the start of the step */
 #define ABC_SMI_SW 2          /* slot is still sweeping */
@@ -85,6 +96,8 @@
 #define ABC_SM_INTS (6 * ABC_SLOTS)
 #define ABC_SMEM_GROUP_BYTES ((size_t)ABC_SM_DOUBLES * 8 + (size_t)ABC_SM_INTS * 4)
 #define ABC_SMEM_BYTES (ABC_GROUPS * ABC_SMEM_GROUP_BYTES)
+static_assert(ABC_SMEM_BYTES <= 232448, "two groups must fit the 227 KB of dynamic shared memory of an SM");
+static_assert((ABC_ST_BASE & 1) == 0 && (ABC_SMEM_GROUP_BYTES % 16) == 0, "stage buffers are 16-byte aligned");
 
 #ifdef AB_HOST_EMUL
 #define ABC_NL 32
@@ -407,6 +420,430 @@ __device__ __forceinline__ void abc_fill_store(const AbcSeriesRef& R, double* u,
 #define ABC_SM_HERE(sm) AbcSmem sm; sm.d = abc_shared + (threadIdx.x / (32 * ABC_GWARPS)) * (ABC_SMEM_GROUP_BYTES / 8); sm.i = reinterpret_cast<int*>(sm.d + ABC_SM_DOUBLES)
 #endif
 
+/* particle-independent EIH sums of the Sun at one (slot, node) (ab_fill_nodes, same operations): the lane reads back
+ * the eleven positions it has just written */
+__device__ __forceinline__ void abc_fill_eih(const double* tb, double* g, double sx, double sy, double sz) {
+    const AbEphem& E = c_abcE;
+    const AbForceOpts& F = c_abcF;
+    if (F.forces & 0x40) {
+        double term1 = 0.0, arx = 0.0, ary = 0.0, arz = 0.0;
+#pragma unroll 1
+        for (int k0 = 1; k0 < AB_NPLANETS; k0 += 5) {
+            /* five terms at a time: the square roots and divisions of a group are independent and overlap,
+             * then the group is added in order */
+            double t1[5], fx[5], fy[5], fz[5], GMk[5], dxjk[5], dyjk[5], dzjk[5], rjk2[5], _rjk[5], den[5];
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                const int k = k0 + j;
+                GMk[j] = E.gm[k];
+                dxjk[j] = sx - tb[ABC_E_POS(k, 0) * ABC_SLOTS];
+                dyjk[j] = sy - tb[ABC_E_POS(k, 1) * ABC_SLOTS];
+                dzjk[j] = sz - tb[ABC_E_POS(k, 2) * ABC_SLOTS];
+                rjk2[j] = dxjk[j] * dxjk[j] + dyjk[j] * dyjk[j] + dzjk[j] * dzjk[j];
+                ok = ok && ab_nb_ok(rjk2[j]) && ab_nb_ok(GMk[j]);
+            }
+#if !AB_STRICT && !defined(AB_HOST_EMUL)
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                const double ir = ab_rsqrt_fast(rjk2[j]);
+                _rjk[j] = rjk2[j] * ir; den[j] = rjk2[j] * _rjk[j];
+                t1[j] = GMk[j] * ir; fx[j] = t1[j] * (ir * ir);
+            }
+#else
+#pragma unroll
+            for (int j = 0; j < 5; j++) _rjk[j] = ab_sqrt_nb(rjk2[j]);
+#pragma unroll
+            for (int j = 0; j < 5; j++) { den[j] = rjk2[j] * _rjk[j]; ok = ok && ab_nb_ok(den[j]); }
+#pragma unroll
+            for (int j = 0; j < 5; j++) { t1[j] = ab_div_nb(GMk[j], _rjk[j]); fx[j] = ab_div_nb(GMk[j], den[j]); }
+#endif
+            if (!ok) {
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    _rjk[j] = sqrt(rjk2[j]);
+                    t1[j] = GMk[j] / _rjk[j];
+                    fx[j] = GMk[j] / (rjk2[j] * _rjk[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                const double fac = fx[j];
+                fx[j] = fac * dxjk[j]; fy[j] = fac * dyjk[j]; fz[j] = fac * dzjk[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 5; j++) { term1 += t1[j]; arx -= fx[j]; ary -= fy[j]; arz -= fz[j]; }
+        }
+        g[ABC_GT_TERM1 * ABC_SLOTS] = term1;
+        g[ABC_GT_AR(0) * ABC_SLOTS] = arx; g[ABC_GT_AR(1) * ABC_SLOTS] = ary; g[ABC_GT_AR(2) * ABC_SLOTS] = arz;
+    }
+
+}
+
+/* ---- TMA-staged fill (ABC_FILL_TMA, the default) ---------------------------------------------------------------
+ * The eight node-lanes of a slot read the same one or two coefficient records (a record spans 4-32 days, a step a few
+ * days to a few weeks).  Read with a 16-byte load per lane and pair of terms (the direct fill below, kept as a build
+ * option), the fill ISSUES 750 instructions per series and warp for 170 FP64 ones -- address arithmetic, prefetch
+ * rotation, predicates for odd term counts -- and every load waits for L2: measured 130 k cycles per attempt of a CTA.
+ * Here the records are COPIED INTO SHARED MEMORY BY THE TMA UNIT (cp.async.bulk: one request per slot covering the
+ * consecutive records its eight nodes fall into, completion on an mbarrier) one series ahead of the arithmetic, and
+ * the lanes read the coefficients from the staged copy with broadcast shared-memory loads, four terms per trip (the
+ * packed image pads every record with zero coefficients to a multiple of four terms, see pack_spk in gpu_api.cu).
+ *
+ * Per warp and series: every lane locates its record (integer arithmetic on the segment descriptor in constant
+ * memory, no global access); a slot's records are consecutive in the image, so one bulk copy per slot brings them all;
+ * the four slots share a stage buffer of ABC_ST_BUF doubles (7-13 records), handed out in slot order.  A lane whose
+ * record did not fit (the Moon's 4-day records under a 20-day step), or whose slot straddles two segments, reads from
+ * the image in global memory: same arithmetic, the values are those of the direct fill bit for bit.  Two stage
+ * buffers per warp: series s + 1 is in flight while series s is evaluated. */
+#ifndef ABC_FILL_TMA
+#define ABC_FILL_TMA 1
+#endif
+
+#ifdef AB_HOST_EMUL
+static inline int ab_ffs(unsigned v) { return __builtin_ffs((int)v); }
+#else
+__device__ __forceinline__ int ab_ffs(unsigned v) { return __ffs((int)v); }
+#endif
+
+/* series of the staged fill */
+#define ABC_S_SUN 0
+#define ABC_S_EMB 1
+#define ABC_S_PLANET0 1                      /* series of planet b (1 .. 10) is ABC_S_PLANET0 + b */
+#define ABC_S_AST0 (AB_NPLANETS + 1)
+#define ABC_NSERIES (ABC_S_AST0 + AB_MAX_AST)
+static __constant__ AbSpkTarget c_abc_tg[ABC_NSERIES];   /* the targets in series order, seg[].stage_cap filled in */
+static __constant__ int c_abc_regular;                   /* usual SPK layout: every body and the EMB have a target */
+
+/* Launch-time table of the series (host).  stage_cap: how many records of a segment fit a stage buffer. */
+static inline int abc_series_table(const AbEphem& E, const AbSpkTarget* ast, AbSpkTarget* out) {
+    memset(out, 0, sizeof(AbSpkTarget) * ABC_NSERIES);
+    int regular = (E.planets_source != AB_SRC_ASCII) && E.emb_index >= 0;
+    for (int b = 0; b < AB_NPLANETS && regular; b++) if (E.p_index[b] < 0) regular = 0;
+    if (regular) {
+        out[ABC_S_SUN] = E.p_tgt[E.p_index[0]];
+        out[ABC_S_EMB] = E.p_tgt[E.emb_index];
+        for (int b = 1; b < AB_NPLANETS; b++) out[ABC_S_PLANET0 + b] = E.p_tgt[E.p_index[b]];
+    }
+    for (int m = 0; m < E.n_ast && m < AB_MAX_AST; m++) out[ABC_S_AST0 + m] = ast[m];
+    for (int s = 0; s < ABC_NSERIES; s++)
+        for (int k = 0; k < AB_MAXSEG; k++) out[s].seg[k].stage_cap = out[s].seg[k].R > 0 ? ABC_ST_BUF / out[s].seg[k].R : 0;
+    return regular;
+}
+
+#if ABC_FILL_TMA
+#ifndef AB_HOST_EMUL
+__device__ __forceinline__ unsigned abc_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void abc_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void abc_mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.expect_tx.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void abc_mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool abc_mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+/* global -> shared bulk copy by the TMA unit; `bytes` a multiple of 16, both addresses 16-byte aligned */
+__device__ __forceinline__ void abc_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void abc_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+/* once per kernel, by every warp for its own two barriers (the first CTA barrier of the role loops follows) */
+__device__ __forceinline__ void abc_stage_init() {
+    ABC_SM_HERE(sm);
+    const int warp = (int)(threadIdx.x >> 5) % ABC_GWARPS;
+    if ((threadIdx.x & 31) == 0) {
+        double* mb = sm.d + ABC_ST_MBAR + 3 * warp;
+        abc_mbar_init(abc_smem_addr(mb), 1);
+        abc_mbar_init(abc_smem_addr(mb + 1), 1);
+        *reinterpret_cast<unsigned*>(mb + 2) = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        abc_fence_proxy_async();
+    }
+    __syncwarp();
+}
+#endif
+
+/* what a lane carries through the fill */
+struct AbcFillLane {
+    double t, sx, sy, sz, emb[3];
+    double *tb, *g;
+    int active;
+    int seg, off;            /* series being evaluated: its segment, and where its record lies in the stage buffer (doubles; < 0: not staged) */
+    int nseg, noff;          /* the same for the series after it */
+};
+
+/* Chebyshev argument (and derivative scale) of time t for the record at `rec` = [_jul(MID), RADIUS, ...]: the second
+ * half of ab_spk_record_in */
+__device__ __forceinline__ double abc_record_z(const double* rec, const AbSpkSeg& sg, double jd_ref, double t, double* c) {
+    const double jul_mid = rec[0];
+    if (sg.uniform) {
+        *c = sg.radius_inv;
+        return ab_divc((jd_ref - jul_mid) + t, sg.radius_d, sg.radius_rd);
+    }
+    const double radius = rec[1];
+    *c = 1.0 / radius;
+    return ((jd_ref - jul_mid) + t) / AB_DIVK(radius, 86400.0);
+}
+
+/* Position sums (file units) of one series from the record at `rec` ([_jul(MID), RADIUS, x0 y0 z0 x1 ...], staged or
+ * in the image), four terms per trip: the packed copy holds zero coefficients behind the last term up to a multiple of
+ * four, and adding 0 * T_p leaves a sum unchanged (a sum that starts from +0 is never -0).  The sums and their order
+ * are those of ab_cheb3. */
+__device__ __forceinline__ void abc_series_pos(const double* rec, const AbSpkSeg& sg, double jd_ref, double t, double* u) {
+    double c;
+    const double z = abc_record_z(rec, sg, jd_ref, t, &c);
+    const int P4 = (sg.P + 3) & ~3;
+    const double2* q = reinterpret_cast<const double2*>(rec + 2);
+    const double z2 = 2.0 * z;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, T1, T2;
+    {   /* x0 y0 | z0 x1 | y1 z1 | x2 y2 | z2 x3 | y3 z3 */
+        const double2 c0 = q[0], c1 = q[1], c2 = q[2], c3 = q[3], c4 = q[4], c5 = q[5];
+        a0 += c0.x * 1.0; a1 += c0.y * 1.0; a2 += c1.x * 1.0;
+        a0 += c1.y * z; a1 += c2.x * z; a2 += c2.y * z;
+        const double Ta = z2 * z - 1.0;
+        a0 += c3.x * Ta; a1 += c3.y * Ta; a2 += c4.x * Ta;
+        const double Tb = z2 * Ta - z;
+        a0 += c4.y * Tb; a1 += c5.x * Tb; a2 += c5.y * Tb;
+        T2 = Ta; T1 = Tb;
+    }
+#pragma unroll 1
+    for (int p = 4; p < P4; p += 4) {
+        const double2* qq = q + 3 * (p >> 1);
+        const double2 c0 = qq[0], c1 = qq[1], c2 = qq[2], c3 = qq[3], c4 = qq[4], c5 = qq[5];
+        const double Ta = z2 * T1 - T2;
+        a0 += c0.x * Ta; a1 += c0.y * Ta; a2 += c1.x * Ta;
+        const double Tb = z2 * Ta - T1;
+        a0 += c1.y * Tb; a1 += c2.x * Tb; a2 += c2.y * Tb;
+        const double Tc = z2 * Tb - Ta;
+        a0 += c3.x * Tc; a1 += c3.y * Tc; a2 += c4.x * Tc;
+        const double Td = z2 * Tc - Tb;
+        a0 += c4.y * Td; a1 += c5.x * Td; a2 += c5.y * Td;
+        T2 = Tc; T1 = Td;
+    }
+    u[0] = a0; u[1] = a1; u[2] = a2;
+}
+
+/* what becomes of the sums of series s: the Sun (evaluated with its velocity, ab_spk_planet<1>) gives the barycentric
+ * offset of the asteroids, the EMB is kept for Earth and Moon, planets go into shared memory, asteroids into the
+ * global table */
+__device__ __forceinline__ void abc_series_finish(int s, const double* rec, const AbSpkSeg& sg, double jd_ref, AbcFillLane& X) {
+    const AbEphem& E = c_abcE;
+    if (s == ABC_S_SUN) {
+        double c, u[3], uv[3] = {0, 0, 0}, uw[3] = {0, 0, 0};
+        const double z = abc_record_z(rec, sg, jd_ref, X.t, &c);
+        ab_cheb3<1, true, false>(rec + 2, sg.P, z, c, u, uv, uw);
+        X.sx = ab_divc(u[0], E.u_d[0], E.u_rd[0]); X.sy = ab_divc(u[1], E.u_d[0], E.u_rd[0]); X.sz = ab_divc(u[2], E.u_d[0], E.u_rd[0]);
+        X.g[ABC_GT_SVEL(0) * ABC_SLOTS] = ab_divc(uv[0], E.u_d[1], E.u_rd[1]);
+        X.g[ABC_GT_SVEL(1) * ABC_SLOTS] = ab_divc(uv[1], E.u_d[1], E.u_rd[1]);
+        X.g[ABC_GT_SVEL(2) * ABC_SLOTS] = ab_divc(uv[2], E.u_d[1], E.u_rd[1]);
+        X.tb[ABC_E_POS(0, 0) * ABC_SLOTS] = X.sx; X.tb[ABC_E_POS(0, 1) * ABC_SLOTS] = X.sy; X.tb[ABC_E_POS(0, 2) * ABC_SLOTS] = X.sz;
+        return;
+    }
+    double u[3];
+    abc_series_pos(rec, sg, jd_ref, X.t, u);
+    AbcSeriesRef R;
+    R.img = nullptr; R.tg = nullptr;
+    if (s == ABC_S_EMB) { R.kind = 0; R.idx = -1; }
+    else if (s < ABC_S_AST0) { R.kind = 2; R.idx = s - ABC_S_PLANET0; }
+    else { R.kind = 3; R.idx = s - ABC_S_AST0; }
+    abc_fill_store(R, u, X.emb, X.tb, X.g, X.sx, X.sy, X.sz);
+}
+
+/* Locate the records of series `s` for every lane and request the warp's records into stage buffer `buf` (`bar`: the
+ * shared-memory address of its mbarrier).  Returns true when every active lane reads from the stage buffer. */
+__device__ __forceinline__ bool abc_fill_stage(AbcFillLane* L, int s, double jd_ref, unsigned actmask, double* buf, unsigned bar) {
+    const AbSpkTarget& tg = c_abc_tg[s];
+    const double* img = (s < ABC_S_AST0) ? c_abcE.spkp_img : c_abcE.spka_img;
+    const int first = ab_ffs(actmask) - 1;
+#ifdef AB_HOST_EMUL
+    (void)bar;
+    int bb[32];
+    for (int l = 0; l < 32; l++) {
+        AbcFillLane& X = L[l];
+        X.nseg = 0; X.noff = -1; bb[l] = 0;
+        if (X.active) {
+            X.nseg = ab_spk_segment(tg, jd_ref, X.t);
+            bb[l] = ab_spk_record_index(tg.seg[X.nseg], jd_ref, X.t);
+        }
+    }
+    const int nref = L[first].nseg;
+    bool uni = true;
+    for (int l = 0; l < 32; l++) if (L[l].active && L[l].nseg != nref) uni = false;
+    bool all = true;
+    if (uni) {
+        const AbSpkSeg& sg = tg.seg[nref];
+        int off = 0;
+        for (int k = 0; k < 4; k++) {
+            const int f = 8 * k, e = 8 * k + 7;
+            if (!L[f].active) continue;
+            const int lo = bb[f] < bb[e] ? bb[f] : bb[e];
+            const int span = (bb[f] < bb[e] ? bb[e] - bb[f] : bb[f] - bb[e]) + 1;
+            int nfit = sg.stage_cap - off;
+            if (nfit > span) nfit = span;
+            if (nfit < 0) nfit = 0;
+            if (nfit > 0) memcpy(buf + (size_t)off * sg.R, img + (sg.one - 1) + (long long)lo * sg.R, (size_t)nfit * sg.R * 8);
+            for (int l = f; l <= e; l++)
+                if ((unsigned)(bb[l] - lo) < (unsigned)nfit) L[l].noff = (off + bb[l] - lo) * sg.R;
+            off += span;
+        }
+    }
+    for (int l = 0; l < 32; l++) if (L[l].active && L[l].noff < 0) all = false;
+    return all;
+#else
+    const int l = (int)(threadIdx.x & 31);
+    AbcFillLane& X = L[0];
+    int n = 0, b = 0;
+    if (X.active) {
+        n = ab_spk_segment(tg, jd_ref, X.t);
+        b = ab_spk_record_index(tg.seg[n], jd_ref, X.t);
+    }
+    X.nseg = n; X.noff = -1;
+    const int f = l & ~7, e = l | 7;
+    const int bf = __shfl_sync(0xffffffffu, b, f), be = __shfl_sync(0xffffffffu, b, e);
+    const int nref = __shfl_sync(0xffffffffu, n, first);
+    const bool uni = __all_sync(0xffffffffu, !X.active || n == nref);
+    const int lo = bf < be ? bf : be;
+    const int span = X.active ? ((bf < be ? be - bf : bf - be) + 1) : 0;
+    const int sp0 = __shfl_sync(0xffffffffu, span, 0), sp1 = __shfl_sync(0xffffffffu, span, 8), sp2 = __shfl_sync(0xffffffffu, span, 16);
+    const int k = l >> 3;
+    const int off = (k > 0 ? sp0 : 0) + (k > 1 ? sp1 : 0) + (k > 2 ? sp2 : 0);
+    abc_fence_proxy_async();      /* the buffer was read through the generic proxy two series ago */
+    if (uni && X.active) {
+        const AbSpkSeg& sg = tg.seg[nref];
+        const int Rr = sg.R;
+        int nfit = sg.stage_cap - off;
+        if (nfit > span) nfit = span;
+        if (nfit < 0) nfit = 0;
+        if ((unsigned)(b - lo) < (unsigned)nfit) X.noff = (off + b - lo) * Rr;
+        if (l == f && nfit > 0) {
+            const unsigned bytes = (unsigned)(nfit * Rr) * 8u;
+            abc_mbar_expect_tx(bar, bytes);
+            abc_bulk_g2s(abc_smem_addr(buf + off * Rr), img + (sg.one - 1) + (long long)lo * Rr, bytes, bar);
+        }
+    }
+    __syncwarp();
+    if (l == 0) abc_mbar_arrive(bar);      /* the phase ends when the requested bytes have landed (at once if none were) */
+    return __all_sync(0xffffffffu, !X.active || X.noff >= 0);
+#endif
+}
+
+__device__ __noinline__ void abc_fill_warp(ABC_CTXARG double* gt, int warp) {
+    const AbEphem& E = c_abcE;
+    ABC_SM_HERE(sm);
+    const double jd_ref = E.jd_ref;
+    const bool spk_regular = c_abc_regular != 0;
+    const int s_end = ABC_S_AST0 + E.n_ast;
+    const int s_begin = spk_regular ? 0 : ABC_S_AST0;
+    AbcFillLane L[ABC_NL];
+    unsigned actmask = 0u;
+    ABC_LANES(l) {
+        AbcFillLane& X = L[ABC_LI(l)];
+        const int slot = 4 * warp + (l >> 3);
+        const int node = l & 7;
+        X.active = sm.flag(ABC_SMI_ACTIVE, slot);
+#ifdef AB_HOST_EMUL
+        if (X.active) actmask |= 1u << l;
+#else
+        actmask = __ballot_sync(0xffffffffu, X.active);
+#endif
+        const double t0 = sm.t0(slot);
+        X.t = (node == 0) ? t0 : (t0 + sm.dt(slot) * c_h[node]);
+        X.tb = sm.tab(node, slot);
+        X.g = gt + node * ABC_GT_NODE + slot;
+        X.sx = X.sy = X.sz = 0.0;
+        X.emb[0] = X.emb[1] = X.emb[2] = 0.0;
+        X.seg = X.nseg = 0; X.off = X.noff = -1;
+        if (X.active && !spk_regular) {
+            /* unusual layout (DE-binary planets, a kernel without Earth or EMB target): the one-time routines */
+            int err = AB_OK;
+            for (int b = 0; b < AB_NPLANETS; b++) {
+                double GM, x[3], v[3], a[3];
+                int flag;
+                if (b == 0) {
+                    flag = ab_planet<1>(E, 0, X.t, &GM, x, v, a);
+                    X.g[ABC_GT_SVEL(0) * ABC_SLOTS] = v[0]; X.g[ABC_GT_SVEL(1) * ABC_SLOTS] = v[1]; X.g[ABC_GT_SVEL(2) * ABC_SLOTS] = v[2];
+                    X.sx = x[0]; X.sy = x[1]; X.sz = x[2];
+                } else {
+                    flag = ab_planet<0>(E, b, X.t, &GM, x, v, a);
+                }
+                if (flag != AB_OK && err == AB_OK) err = flag;
+                X.tb[ABC_E_POS(b, 0) * ABC_SLOTS] = x[0]; X.tb[ABC_E_POS(b, 1) * ABC_SLOTS] = x[1]; X.tb[ABC_E_POS(b, 2) * ABC_SLOTS] = x[2];
+            }
+            if (err != AB_OK) sm.flag(ABC_SMI_ERR, slot) = err;      /* the lanes of a slot may race: every value written is a valid code */
+        }
+    }
+    if (actmask == 0u) return;       /* none of the warp's four slots steps in this attempt */
+    if (s_begin < s_end) {
+        double* stage = sm.d + ABC_ST_BASE + warp * ABC_ST_WARP;
+#ifdef AB_HOST_EMUL
+        const unsigned bar0 = 0u;
+#else
+        double* mb = sm.d + ABC_ST_MBAR + 3 * warp;
+        const unsigned bar0 = abc_smem_addr(mb);
+        unsigned phase = *reinterpret_cast<volatile unsigned*>(mb + 2);
+#endif
+        bool nall = abc_fill_stage(L, s_begin, jd_ref, actmask, stage, bar0);
+#pragma unroll 1
+        for (int s = s_begin; s < s_end; s++) {
+            const int j = (s - s_begin) & 1;
+            const bool all = nall;
+            ABC_LANES(l) {
+                AbcFillLane& X = L[ABC_LI(l)];
+                X.seg = X.nseg; X.off = X.noff;
+            }
+            if (s + 1 < s_end) nall = abc_fill_stage(L, s + 1, jd_ref, actmask, stage + (j ^ 1) * ABC_ST_BUF, bar0 + 8u * (unsigned)(j ^ 1));
+#ifndef AB_HOST_EMUL
+            {   /* the records of series s have landed */
+                const unsigned bar = bar0 + 8u * (unsigned)j, par = (phase >> j) & 1u;
+                if (!abc_mbar_try_wait(bar, par)) {
+                    const long long tw = clock64();
+                    while (!abc_mbar_try_wait(bar, par))
+                        if (clock64() - tw > (1LL << 31)) __trap();      /* a lost copy must not hang the grid */
+                }
+                phase ^= 1u << j;
+            }
+#endif
+            const AbSpkTarget& tg = c_abc_tg[s];
+            const double* sbuf = stage + j * ABC_ST_BUF;
+            if (all) {      /* the usual case: every lane reads shared memory */
+                ABC_LANES(l) {
+                    AbcFillLane& X = L[ABC_LI(l)];
+                    if (X.active) abc_series_finish(s, sbuf + X.off, tg.seg[X.seg], jd_ref, X);
+                }
+            } else {
+                const double* img = (s < ABC_S_AST0) ? E.spkp_img : E.spka_img;
+                ABC_LANES(l) {
+                    AbcFillLane& X = L[ABC_LI(l)];
+                    if (X.active) {
+                        const AbSpkSeg& sg = tg.seg[X.seg];
+                        const double* rec = (X.off >= 0) ? (sbuf + X.off) : ab_spk_record_ptr(img, sg, jd_ref, X.t);
+                        abc_series_finish(s, rec, sg, jd_ref, X);
+                    }
+                }
+            }
+#ifndef AB_HOST_EMUL
+            __syncwarp();      /* every lane is done with buffer j before series s + 2 is copied into it */
+#endif
+        }
+#ifndef AB_HOST_EMUL
+        if ((threadIdx.x & 31) == 0) *reinterpret_cast<volatile unsigned*>(mb + 2) = phase;
+#endif
+    }
+    ABC_LANES(l) {
+        AbcFillLane& X = L[ABC_LI(l)];
+        if (X.active) abc_fill_eih(X.tb, X.g, X.sx, X.sy, X.sz);
+    }
+}
+#else
 __device__ __noinline__ void abc_fill_warp(ABC_CTXARG double* gt, int warp) {
     const AbEphem& E = c_abcE;
     const AbForceOpts& F = c_abcF;
@@ -457,62 +894,10 @@ __device__ __noinline__ void abc_fill_warp(ABC_CTXARG double* gt, int warp) {
 #pragma unroll
             for (int j = 0; j < ABC_FILL_NS; j++) abc_fill_store(R[j], u[j], emb, tb, g, sx, sy, sz);
         }
-        /* particle-independent EIH sums of the Sun at this node (ab_fill_nodes, same operations): the lane reads back
-         * the eleven positions it has just written */
-        if (F.forces & 0x40) {
-            double term1 = 0.0, arx = 0.0, ary = 0.0, arz = 0.0;
-#pragma unroll 1
-            for (int k0 = 1; k0 < AB_NPLANETS; k0 += 5) {
-                /* five terms at a time: the square roots and divisions of a group are independent and overlap,
-                 * then the group is added in order */
-                double t1[5], fx[5], fy[5], fz[5], GMk[5], dxjk[5], dyjk[5], dzjk[5], rjk2[5], _rjk[5], den[5];
-                bool ok = true;
-#pragma unroll
-                for (int j = 0; j < 5; j++) {
-                    const int k = k0 + j;
-                    GMk[j] = E.gm[k];
-                    dxjk[j] = sx - tb[ABC_E_POS(k, 0) * ABC_SLOTS];
-                    dyjk[j] = sy - tb[ABC_E_POS(k, 1) * ABC_SLOTS];
-                    dzjk[j] = sz - tb[ABC_E_POS(k, 2) * ABC_SLOTS];
-                    rjk2[j] = dxjk[j] * dxjk[j] + dyjk[j] * dyjk[j] + dzjk[j] * dzjk[j];
-                    ok = ok && ab_nb_ok(rjk2[j]) && ab_nb_ok(GMk[j]);
-                }
-#if !AB_STRICT && !defined(AB_HOST_EMUL)
-#pragma unroll
-                for (int j = 0; j < 5; j++) {
-                    const double ir = ab_rsqrt_fast(rjk2[j]);
-                    _rjk[j] = rjk2[j] * ir; den[j] = rjk2[j] * _rjk[j];
-                    t1[j] = GMk[j] * ir; fx[j] = t1[j] * (ir * ir);
-                }
-#else
-#pragma unroll
-                for (int j = 0; j < 5; j++) _rjk[j] = ab_sqrt_nb(rjk2[j]);
-#pragma unroll
-                for (int j = 0; j < 5; j++) { den[j] = rjk2[j] * _rjk[j]; ok = ok && ab_nb_ok(den[j]); }
-#pragma unroll
-                for (int j = 0; j < 5; j++) { t1[j] = ab_div_nb(GMk[j], _rjk[j]); fx[j] = ab_div_nb(GMk[j], den[j]); }
-#endif
-                if (!ok) {
-#pragma unroll
-                    for (int j = 0; j < 5; j++) {
-                        _rjk[j] = sqrt(rjk2[j]);
-                        t1[j] = GMk[j] / _rjk[j];
-                        fx[j] = GMk[j] / (rjk2[j] * _rjk[j]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 5; j++) {
-                    const double fac = fx[j];
-                    fx[j] = fac * dxjk[j]; fy[j] = fac * dyjk[j]; fz[j] = fac * dzjk[j];
-                }
-#pragma unroll
-                for (int j = 0; j < 5; j++) { term1 += t1[j]; arx -= fx[j]; ary -= fy[j]; arz -= fz[j]; }
-            }
-            g[ABC_GT_TERM1 * ABC_SLOTS] = term1;
-            g[ABC_GT_AR(0) * ABC_SLOTS] = arx; g[ABC_GT_AR(1) * ABC_SLOTS] = ary; g[ABC_GT_AR(2) * ABC_SLOTS] = arz;
-        }
+        abc_fill_eih(tb, g, sx, sy, sz);
     }
 }
+#endif  /* ABC_FILL_TMA */
 
 /* ------------------------------------------------------------------------------------------ */
 /* worker tasks (lane = slot)                                                                 */

@@ -31,7 +31,7 @@ struct AbSpkSeg {
     double radius_rd;    /* 1 / radius_d */
     double radius_inv;   /* 1.0 / RADIUS */
     int uniform;         /* 1 if every record really has the same RADIUS, else evaluate from the record */
-    int pad;
+    int stage_cap;       /* pp_coop_kernel: records of this segment that fit a stage buffer of the fill (set at launch) */
 };
 
 struct AbSpkTarget {

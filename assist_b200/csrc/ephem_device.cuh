@@ -85,12 +85,19 @@ __device__ __forceinline__ int ab_spk_segment(const AbSpkTarget& tg, double jd_r
 }
 
 /* Locate the type-2 record of segment `sg` that holds jd_ref + t (reference src/spk.c:503-517). */
-__device__ __forceinline__ const double* ab_spk_record_in(const double* __restrict__ img, const AbSpkSeg& sg,
-                                                          double jd_ref, double t, double* z, double* c) {
+__device__ __forceinline__ int ab_spk_record_index(const AbSpkSeg& sg, double jd_ref, double t) {
     int b = (int)ab_divc((jd_ref - sg.jul_init) + t, sg.intlen_d, sg.intlen_rd);
     if (b > sg.nrec - 1) b = sg.nrec - 1;
     if (b < 0) b = 0;
-    const double* rec = img + (sg.one - 1) + (long long)b * sg.R;
+    return b;
+}
+__device__ __forceinline__ const double* ab_spk_record_ptr(const double* __restrict__ img, const AbSpkSeg& sg, double jd_ref, double t) {
+    /* the record in the packed copy: [_jul(MID), RADIUS, coefficients] */
+    return img + (sg.one - 1) + (long long)ab_spk_record_index(sg, jd_ref, t) * sg.R;
+}
+__device__ __forceinline__ const double* ab_spk_record_in(const double* __restrict__ img, const AbSpkSeg& sg,
+                                                          double jd_ref, double t, double* z, double* c) {
+    const double* rec = ab_spk_record_ptr(img, sg, jd_ref, t);
     const double jul_mid = __ldg(rec);          /* the packed copy holds _jul(MID) = 2451545.0 + MID / 86400.0, formed at upload */
     if (sg.uniform) {
         *z = ab_divc((jd_ref - jul_mid) + t, sg.radius_d, sg.radius_rd);

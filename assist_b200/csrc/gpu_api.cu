@@ -125,10 +125,15 @@ static int upload_image(void** slot, const void* host, size_t len) {
 }
 
 /* Device copy of an SPK kernel: only the type-2 records, segment after segment, each record as
- * [MID, RADIUS, (x y z) of term 0, (x y z) of term 1, ...] padded to an even number of doubles, so that the
- * coefficients of a record start on a 16-byte boundary and the three components of a term are adjacent
- * (ephem_device.cuh reads two terms with three 16-byte loads).  Values are copied, never recomputed.
+ * [MID, RADIUS, (x y z) of term 0, (x y z) of term 1, ...], the term list padded with ZERO coefficients to a multiple
+ * of four terms: the coefficients of a record start on a 16-byte boundary, the three components of a term are
+ * adjacent (two terms are three 16-byte loads) and the staged fill of pp_coop_kernel takes four terms per trip without
+ * a test for the end of the list (a zero coefficient adds nothing to a sum).  Values are copied, never recomputed.
  * off[m * AB_MAXSEG + s] = first word of segment s of target m in that copy. */
+static inline int packed_record_words(int R) {       /* R = 2 + 3 P words in the file */
+    const int P = (R - 2) / 3;
+    return 2 + 3 * ((P + 3) & ~3);
+}
 static int spk_layout(const struct spk_s* file, std::vector<long long>& off, size_t* total_words) {
     const double* img = (const double*)file->map;
     const size_t words = file->len / sizeof(double);
@@ -147,7 +152,7 @@ static int spk_layout(const struct spk_s* file, std::vector<long long>& off, siz
             if (R < 8 || R > 98 || nrec < 1 || (size_t)(t->one[s] - 1) + (size_t)nrec * R > words)
                 return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "SPK target %d: not a type-2 Chebyshev segment", t->code);
             off[(size_t)m * AB_MAXSEG + s] = cur;
-            cur += (long long)nrec * ((R + 1) & ~1);
+            cur += (long long)nrec * packed_record_words(R);
         }
     }
     *total_words = (size_t)cur + 2;      /* the last 16-byte pair of an odd-length record may be read past its end */
@@ -191,7 +196,7 @@ static void pack_spk(const struct spk_s* file, const std::vector<long long>& off
         const struct spk_target* t = &file->targets[m];
         for (int s = 0; s <= t->ind; s++) {
             const double* val = img + t->two[s] - 1;
-            const int R = (int)val[-1], nrec = (int)val[0], P = (R - 2) / 3, Rp = (R + 1) & ~1;
+            const int R = (int)val[-1], nrec = (int)val[0], P = (R - 2) / 3, Rp = packed_record_words(R);
             for (int b = 0; b < nrec; b++) {
                 const double* src = img + (t->one[s] - 1) + (size_t)b * R;
                 double* dst = buf.data() + off[(size_t)m * AB_MAXSEG + s] + (size_t)b * Rp;
@@ -237,7 +242,7 @@ static int fill_target(AbSpkTarget* d, const struct spk_target* t, const struct 
             if (rec0[(size_t)b * sg->R + 1] != radius) { sg->uniform = 0; break; }
         /* from here on the descriptor addresses the packed device copy, not the file */
         sg->one = (int)(seg_off[s] + 1);
-        sg->R = (sg->R + 1) & ~1;
+        sg->R = packed_record_words(sg->R);
     }
     return 0;
 }

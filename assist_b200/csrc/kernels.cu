@@ -777,6 +777,9 @@ __global__ void __launch_bounds__(ABC_THREADS, ABC_CTAS_PER_SM)
 pp_coop_kernel(const __grid_constant__ AbEphem E, const __grid_constant__ AbForceOpts F, const __grid_constant__ AbcArgs A) {
     ABC_SM_HERE(sm);
     const int warp = (int)(threadIdx.x >> 5) % ABC_GWARPS;       /* role inside the group */
+#if ABC_FILL_TMA
+    abc_stage_init();
+#endif
     if (warp < 3) abc_comp_main(E, F, A, sm, warp);
     else if (warp == ABC_CTRL_WARP) abc_control_main(E, F, A, sm);
     else abc_worker_main(E, F, A, sm, warp);
@@ -959,6 +962,11 @@ cudaError_t AB_CAT2(ab_launch_pp_coop, AB_SFX)(const AbEphem& E, const AbForceOp
         if ((ec = cudaMemcpyToSymbolAsync(c_abcP, plan, sizeof(AbcPlan), 0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return ec;
         if (host_ast_tg && E.n_ast > 0 &&
             (ec = cudaMemcpyToSymbolAsync(c_abc_ast, host_ast_tg, sizeof(AbSpkTarget) * E.n_ast, 0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return ec;
+        if (E.n_ast > 0 && !host_ast_tg) return cudaErrorInvalidValue;
+        static thread_local AbSpkTarget series[ABC_NSERIES];
+        const int regular = abc_series_table(E, host_ast_tg, series);
+        if ((ec = cudaMemcpyToSymbolAsync(c_abc_tg, series, sizeof(series), 0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return ec;
+        if ((ec = cudaMemcpyToSymbolAsync(c_abc_regular, &regular, sizeof(int), 0, cudaMemcpyHostToDevice, st)) != cudaSuccess) return ec;
     }
     AbcArgs A;
     A.Bt = Bt; A.W = W; A.tmax = tmax; A.exact_finish_time = exact; A.queue_head = queue_head; A.SL = SL;

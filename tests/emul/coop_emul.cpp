@@ -172,6 +172,7 @@ extern "C" int abc_emul_run(void* h, const void* E_, const void* F_, const void*
     memcpy(c_d, AB_D, sizeof(AB_D));
     c_abcE = E; c_abcF = F; c_abcP = *(const AbcPlan*)plan_;
     for (int m = 0; m < E.n_ast && m < AB_MAX_AST; m++) c_abc_ast[m] = E.a_tgt[m];
+    c_abc_regular = abc_series_table(E, E.a_tgt, c_abc_tg);
 
     AbcArgs A;
     hb->w.epsilon = hb->d.epsilon; hb->w.min_dt = hb->d.min_dt; hb->w.has_params = hb->d.has_params;

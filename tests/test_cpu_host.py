@@ -171,7 +171,8 @@ def test_synthetic_inputs_are_deterministic(tmp_path):
 
 def test_packed_spk_copy_is_a_pure_rearrangement(lib, paths):
     """The device copy of an SPK kernel (gpu_api.cu, upload_packed_spk) against an independent reader of the file:
-    records 16-byte aligned, [_jul(MID), RADIUS, (x y z) per term], nothing else changed."""
+    records 16-byte aligned, [_jul(MID), RADIUS, (x y z) per term, zero terms up to a multiple of four], nothing else
+    changed."""
     import sys
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import np_oracle
@@ -200,7 +201,8 @@ def test_packed_spk_copy_is_a_pure_rearrangement(lib, paths):
             for s, (one, two) in enumerate(f.targets[code]["segs"]):
                 init, intlen, rsize, nrec = f.words[two - 4: two]
                 R, nrec = int(rsize), int(nrec)
-                P, Rp = (R - 2) // 3, (R + 1) & ~1
+                P = (R - 2) // 3
+                Rp = 2 + 3 * ((P + 3) & ~3)
                 o = off[4 * m + s]
                 assert o % 2 == 0 and o == expect_words
                 src = f.words[one - 1: one - 1 + nrec * R].reshape(nrec, R)
