@@ -1377,6 +1377,87 @@ extern "C" int ab_gpu_batch_get_last_state(assist_gpu_batch* b, double* state, d
     return 0;
 }
 
+/* b coefficients of the last completed step (dense output), br[7][n][K][3]: what a snapshot of the simulation keeps */
+extern "C" int ab_gpu_batch_get_br(assist_gpu_batch* b, double* br) {
+    if (!b || !br) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(b->device));
+    const size_t n = b->n, per = 3 * n * b->K;
+    for (int j = 0; j < 7; j++) {
+        soa_to_aos_kernel<<<blocks_for((long long)n * b->K), 256>>>(b->d.br + (size_t)j * per, b->n, b->K, 3, 0, 3, b->d_stage_prm); AB_COUNT(1);
+        CU(cudaMemcpy(br + (size_t)j * per, b->d_stage_prm, sizeof(double) * per, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+/* assist_interpolate_simulation (reference src/assist.c:682-752): positions and velocities at fraction h of the step
+ * that starts at (x0, v0, a0) with the b coefficients br[7][m], m = 3 N components.  One thread per component, the
+ * reference's expressions operation by operation (round-to-nearest intrinsics: no contraction whatever the build). */
+__global__ void interpolate_simulation_kernel(const double* __restrict__ x0, const double* __restrict__ v0, const double* __restrict__ a0,
+                                              const double* __restrict__ br, int m, double dt_last_done, double h,
+                                              double* __restrict__ pos, double* __restrict__ vel) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+#define MUL(a, b) __dmul_rn((a), (b))
+#define ADD(a, b) __dadd_rn((a), (b))
+#define DIV(a, b) __ddiv_rn((a), (b))
+    double s[9];
+    s[0] = MUL(dt_last_done, h);
+    s[1] = DIV(MUL(s[0], s[0]), 2.);
+    s[2] = DIV(MUL(s[1], h), 3.);
+    s[3] = DIV(MUL(s[2], h), 2.);
+    s[4] = DIV(MUL(MUL(3., s[3]), h), 5.);
+    s[5] = DIV(MUL(MUL(2., s[4]), h), 3.);
+    s[6] = DIV(MUL(MUL(5., s[5]), h), 7.);
+    s[7] = DIV(MUL(MUL(3., s[6]), h), 4.);
+    s[8] = DIV(MUL(MUL(7., s[7]), h), 9.);
+    const double b0 = br[k], b1 = br[m + k], b2 = br[2 * m + k], b3 = br[3 * m + k], b4 = br[4 * m + k], b5 = br[5 * m + k], b6 = br[6 * m + k];
+    double sum = MUL(s[8], b6);
+    sum = ADD(sum, MUL(s[7], b5)); sum = ADD(sum, MUL(s[6], b4)); sum = ADD(sum, MUL(s[5], b3)); sum = ADD(sum, MUL(s[4], b2));
+    sum = ADD(sum, MUL(s[3], b1)); sum = ADD(sum, MUL(s[2], b0)); sum = ADD(sum, MUL(s[1], a0[k])); sum = ADD(sum, MUL(s[0], v0[k]));
+    pos[k] = ADD(x0[k], sum);
+    s[0] = MUL(dt_last_done, h);
+    s[1] = DIV(MUL(s[0], h), 2.);
+    s[2] = DIV(MUL(MUL(2., s[1]), h), 3.);
+    s[3] = DIV(MUL(MUL(3., s[2]), h), 4.);
+    s[4] = DIV(MUL(MUL(4., s[3]), h), 5.);
+    s[5] = DIV(MUL(MUL(5., s[4]), h), 6.);
+    s[6] = DIV(MUL(MUL(6., s[5]), h), 7.);
+    s[7] = DIV(MUL(MUL(7., s[6]), h), 8.);
+    double v = ADD(v0[k], MUL(s[7], b6));
+    v = ADD(v, MUL(s[6], b5)); v = ADD(v, MUL(s[5], b4)); v = ADD(v, MUL(s[4], b3)); v = ADD(v, MUL(s[3], b2));
+    v = ADD(v, MUL(s[2], b1)); v = ADD(v, MUL(s[1], b0)); v = ADD(v, MUL(s[0], a0[k]));
+    vel[k] = v;
+#undef MUL
+#undef ADD
+#undef DIV
+}
+
+/* host arrays in, host arrays out: x0, v0, a0 [m], br [7][m], pos, vel [m]; *dt_step = dt_last_done * h as the device
+ * formed it (the reference advances sim1->t by it) */
+extern "C" int assist_gpu_interpolate_simulation(int m, const double* x0, const double* v0, const double* a0, const double* br,
+                                                 double dt_last_done, double h, double* pos, double* vel) {
+    if (m < 1 || !x0 || !v0 || !a0 || !br || !pos || !vel) return set_err(ASSIST_GPU_ERR_ARG, "interpolate_simulation: bad argument");
+    int dev = 0;
+    int rc = ensure_device(&dev);
+    if (rc) return rc;
+    double* d = nullptr;
+    const size_t M = (size_t)m;
+    CU(cudaMalloc((void**)&d, sizeof(double) * 12 * M));
+    cudaError_t e = cudaMemcpy(d, x0, sizeof(double) * M, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + M, v0, sizeof(double) * M, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + 2 * M, a0, sizeof(double) * M, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + 3 * M, br, sizeof(double) * 7 * M, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        interpolate_simulation_kernel<<<(m + 127) / 128, 128>>>(d, d + M, d + 2 * M, d + 3 * M, m, dt_last_done, h, d + 10 * M, d + 11 * M); AB_COUNT(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(pos, d + 10 * M, sizeof(double) * M, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(vel, d + 11 * M, sizeof(double) * M, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return set_err(ASSIST_GPU_ERR_CUDA, "interpolate_simulation: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 extern "C" int assist_gpu_batch_interpolate(assist_gpu_batch* b, double h, double* out) {
     if (!b || !out) return set_err(ASSIST_GPU_ERR_ARG, "NULL argument");
     if (b->mode != ASSIST_GPU_SHARED_STEP) return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "interpolate needs a shared-step batch");

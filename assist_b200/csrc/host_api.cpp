@@ -549,16 +549,61 @@ void assist_integrate_or_interpolate(struct assist_extras* ax, double t) {
     swap_particles(sim, ax);
 }
 
+/* reference src/assist.c:682-752: sim1 (a snapshot) moved to fraction h of the step that sim2 (the next snapshot) has
+ * just completed: x0, v0 of sim1, a0, br and dt_last_done of sim2.  The polynomial is evaluated on the GPU
+ * (assist_gpu_interpolate_simulation), operation by operation as the reference writes it. */
 int assist_interpolate_simulation(struct reb_simulation* sim1, struct reb_simulation* sim2, double h) {
-    (void)sim1; (void)sim2; (void)h;
-    fprintf(stderr, "(ASSIST) assist_interpolate_simulation needs REBOUND SimulationArchive snapshots, which are outside the scope of assist-b200.\n");
-    return 0;
+    if (!sim1 || !sim2 || sim1->N != sim2->N || sim1->N == 0) return 0;
+    const struct reb_integrator_ias15* r1 = &sim1->ri_ias15;
+    const struct reb_integrator_ias15* r2 = &sim2->ri_ias15;
+    if (!r1->x0 || !r1->v0 || !r2->a0 || !r2->br.p0) {
+        reb_simulation_error(sim1, "assist_interpolate_simulation: the simulations carry no IAS15 step data (not restored from a snapshot file).");
+        return 0;
+    }
+    const int m = 3 * (int)sim1->N;
+    std::vector<double> br((size_t)7 * m), pos(m), vel(m);
+    const double* seven[7] = {r2->br.p0, r2->br.p1, r2->br.p2, r2->br.p3, r2->br.p4, r2->br.p5, r2->br.p6};
+    for (int q = 0; q < 7; q++) memcpy(&br[(size_t)q * m], seven[q], sizeof(double) * m);
+    if (assist_gpu_interpolate_simulation(m, r1->x0, r1->v0, r2->a0, br.data(), sim2->dt_last_done, h, pos.data(), vel.data())) {
+        reb_simulation_error(sim1, assist_gpu_last_error());
+        return 0;
+    }
+    for (unsigned int j = 0; j < sim1->N; j++) {
+        struct reb_particle* p = &sim1->particles[j];
+        p->x = pos[3 * j]; p->y = pos[3 * j + 1]; p->z = pos[3 * j + 2];
+        p->vx = vel[3 * j]; p->vy = vel[3 * j + 1]; p->vz = vel[3 * j + 2];
+    }
+    sim1->t += sim2->dt_last_done * h;
+    return 1;
 }
 
+/* reference src/assist.c:599-633 */
 struct reb_simulation* assist_create_interpolated_simulation(struct reb_simulationarchive* sa, double t) {
-    (void)sa; (void)t;
-    fprintf(stderr, "(ASSIST) assist_create_interpolated_simulation needs REBOUND SimulationArchive snapshots, which are outside the scope of assist-b200.\n");
-    return NULL;
+    if (sa == NULL) return NULL;
+    /* the first snapshot cannot be used: it precedes the first step (no accelerations, no b coefficients) */
+    if (sa->nblobs < 2 || t <= sa->t[1]) {
+        printf("Requested time outside range of SimulationArchive.\n");
+        return NULL;
+    }
+    if (t >= sa->t[sa->nblobs - 1]) {
+        printf("Requested time outside range of SimulationArchive.\n");
+        return NULL;
+    }
+    long blob = 0;
+    for (long i = 1; i < sa->nblobs; i++) {
+        if (sa->t[i] >= t) { blob = i; break; }
+    }
+    enum reb_simulation_binary_error_codes warnings = REB_SIMULATION_BINARY_WARNING_NONE;
+    struct reb_simulation* r2 = reb_simulation_create();
+    reb_simulation_create_from_simulationarchive_with_messages(r2, sa, blob - 1, &warnings);
+    struct reb_simulation* r3 = reb_simulation_create();
+    reb_simulation_create_from_simulationarchive_with_messages(r3, sa, blob, &warnings);
+    if (r2->messages_waiting || r3->messages_waiting) { reb_simulation_free(r2); reb_simulation_free(r3); return NULL; }
+    const double h = (t - r2->t) / (r3->dt_last_done);
+    const int ok = assist_interpolate_simulation(r2, r3, h);
+    reb_simulation_free(r3);
+    if (!ok) { reb_simulation_free(r2); return NULL; }
+    return r2;
 }
 
 /* reference src/tools.c:35-70: a plain REBOUND simulation holding the ephemeris bodies at r->t as active particles

@@ -24,6 +24,7 @@ void ab_host_pre_timestep_marker(struct reb_simulation* r);
 int ab_gpu_batch_integrate_ex(assist_gpu_batch* b, double t_end, int exact_finish_time, long max_steps, int flags);
 int ab_gpu_batch_update_params(assist_gpu_batch* b, const double* params);
 int ab_gpu_batch_get_last_state(assist_gpu_batch* b, double* state, double* acc);
+int ab_gpu_batch_get_br(assist_gpu_batch* b, double* br);      /* br[7][n][K][3] */
 struct spk_s;
 int ab_gpu_spk_target_eval(struct spk_s* file, int target_index, int emb_index, double jd_ref, double jd_rel,
                            int mode, const double* ud, double* out);

@@ -20,6 +20,8 @@
 #include "assist_gpu.h"
 #include "host_internal.h"
 
+static void ias15_free(struct reb_simulation* r);
+
 /* ------------------------------------------------------------------------ */
 /* bookkeeping                                                              */
 /* ------------------------------------------------------------------------ */
@@ -46,6 +48,8 @@ extern "C" void reb_simulation_free(struct reb_simulation* const r) {
     free(r->particles);
     free(r->var_config);
     free(r->messages);
+    free(r->simulationarchive_filename);
+    ias15_free(r);
     free(r);
 }
 
@@ -165,13 +169,6 @@ extern "C" struct reb_particle reb_particle_com_of_pair(struct reb_particle p1, 
         p1.ax /= p1.m; p1.ay /= p1.m; p1.az /= p1.m;
     }
     return p1;
-}
-
-extern "C" void reb_simulation_create_from_simulationarchive_with_messages(
-        struct reb_simulation* r, struct reb_simulationarchive* sa, int64_t snapshot,
-        enum reb_simulation_binary_error_codes* warnings) {
-    (void)sa; (void)snapshot; (void)warnings;
-    reb_simulation_error(r, "SimulationArchive is outside the scope of assist-b200.");
 }
 
 /* ------------------------------------------------------------------------ */
@@ -388,6 +385,206 @@ static int sync_from_device(struct reb_simulation* r, AbHostBatch* hb) {
 }
 
 /* ------------------------------------------------------------------------ */
+/* snapshots of an attached simulation (SimulationArchive)                  */
+/* ------------------------------------------------------------------------ */
+/* The reference reads snapshots back through REBOUND's SimulationArchive (src/assist.c:599-633: two consecutive
+ * snapshots give x0, v0 of a step's start and a0, br, dt_last_done of the step).  REBOUND's binary format is not
+ * available here, so the file layout is assist-b200's own; the API (reb_simulation_save_to_file_step,
+ * reb_simulationarchive_create_from_file, sa->t / sa->nblobs, reb_simulation_create_from_simulationarchive_with_messages)
+ * is REBOUND's.  File: 16-byte magic, then per snapshot
+ *     uint64 payload bytes | double t, dt, dt_last_done | uint64 steps_done | uint32 N, N_var, N_var_config, 0 |
+ *     N_var_config x (int32 index, int32 testparticle) | N x reb_particle | a0[3N] | br[7][3N]
+ * a0 = acceleration at the start of the last completed step, br = its b coefficients (zeros before the first step). */
+static const char AB_SA_MAGIC[16] = {'A', 'S', 'S', 'I', 'S', 'T', '-', 'B', '2', '0', '0', ' ', 'S', 'A', '1', '\n'};
+
+struct AbSnapHead {
+    double t, dt, dt_last_done;
+    uint64_t steps_done;
+    uint32_t N, N_var, N_var_config, zero;
+};
+
+static void ias15_alloc(struct reb_simulation* r, unsigned int N) {
+    struct reb_integrator_ias15* ri = &r->ri_ias15;
+    if (ri->N_allocated >= N && ri->x0) return;
+    const size_t m = 3 * (size_t)N;
+    double** one[] = {&ri->x0, &ri->v0, &ri->a0};
+    for (double** p : one) { free(*p); *p = (double*)calloc(m, sizeof(double)); }
+    double** seven[] = {&ri->br.p0, &ri->br.p1, &ri->br.p2, &ri->br.p3, &ri->br.p4, &ri->br.p5, &ri->br.p6};
+    for (double** p : seven) { free(*p); *p = (double*)calloc(m, sizeof(double)); }
+    ri->N_allocated = N;
+}
+
+static void ias15_free(struct reb_simulation* r) {
+    struct reb_integrator_ias15* ri = &r->ri_ias15;
+    free(ri->x0); free(ri->v0); free(ri->a0);
+    free(ri->br.p0); free(ri->br.p1); free(ri->br.p2); free(ri->br.p3); free(ri->br.p4); free(ri->br.p5); free(ri->br.p6);
+    ri->x0 = ri->v0 = ri->a0 = NULL;
+    ri->br.p0 = ri->br.p1 = ri->br.p2 = ri->br.p3 = ri->br.p4 = ri->br.p5 = ri->br.p6 = NULL;
+    ri->N_allocated = 0;
+}
+
+extern "C" void reb_simulation_save_to_file_step(struct reb_simulation* const r, const char* filename, unsigned long long step) {
+    if (!r || !filename) return;
+    free(r->simulationarchive_filename);
+    r->simulationarchive_filename = strdup(filename);
+    if (r->simulationarchive_auto_step != step) {
+        r->simulationarchive_auto_step = step;
+        r->simulationarchive_next_step = r->steps_done;
+    }
+}
+
+/* Appends a snapshot of `r` as it stands (the device batch, if any, supplies a0 and br of the last completed step). */
+extern "C" void reb_simulation_save_to_file(struct reb_simulation* const r, const char* filename) {
+    if (!r) return;
+    if (!filename) filename = r->simulationarchive_filename;
+    if (!filename) { reb_simulation_error(r, "reb_simulation_save_to_file: no file name."); return; }
+    const size_t m = 3 * (size_t)r->N;
+    std::vector<double> a0(m, 0.0), br(7 * m, 0.0);
+    AbHostBatch* hb = (AbHostBatch*)r->b200_batch;
+    if (hb && r->steps_done > 0) {
+        const size_t per = (size_t)hb->n_real * hb->K;
+        std::vector<double> la(per * 3), bb(7 * per * 3);
+        if (ab_gpu_batch_get_last_state(hb->gb, NULL, la.data()) || ab_gpu_batch_get_br(hb->gb, bb.data())) { fail(r, assist_gpu_last_error()); return; }
+        const int nvmax = hb->K - 1;
+        for (int i = 0; i < hb->n_real; i++)
+            for (int j = 0; j < hb->K; j++) {
+                const int pidx = (j == 0) ? i : hb->var_pidx[(size_t)i * nvmax + (j - 1)];
+                if (pidx < 0) continue;
+                for (int c = 0; c < 3; c++) {
+                    a0[3 * (size_t)pidx + c] = la[((size_t)i * hb->K + j) * 3 + c];
+                    for (int q = 0; q < 7; q++) br[q * m + 3 * (size_t)pidx + c] = bb[(size_t)q * per * 3 + ((size_t)i * hb->K + j) * 3 + c];
+                }
+            }
+    }
+    FILE* f = fopen(filename, "rb");
+    const bool exists = f != NULL;
+    if (f) fclose(f);
+    f = fopen(filename, "ab");
+    if (!f) { reb_simulation_error(r, "reb_simulation_save_to_file: cannot open the file."); return; }
+    if (!exists) fwrite(AB_SA_MAGIC, 1, sizeof(AB_SA_MAGIC), f);
+    AbSnapHead h;
+    h.t = r->t; h.dt = r->dt; h.dt_last_done = r->dt_last_done; h.steps_done = r->steps_done;
+    h.N = r->N; h.N_var = (uint32_t)r->N_var; h.N_var_config = r->N_var_config; h.zero = 0;
+    const uint64_t bytes = sizeof(h) + 8 * (uint64_t)r->N_var_config + sizeof(struct reb_particle) * (uint64_t)r->N + 8 * (uint64_t)(8 * m);
+    fwrite(&bytes, 8, 1, f);
+    fwrite(&h, sizeof(h), 1, f);
+    for (unsigned int v = 0; v < r->N_var_config; v++) {
+        const int32_t pair[2] = {r->var_config[v].index, r->var_config[v].testparticle};
+        fwrite(pair, 4, 2, f);
+    }
+    for (unsigned int i = 0; i < r->N; i++) {
+        struct reb_particle p = r->particles[i];
+        p.sim = NULL; p.c = NULL; p.ap = NULL;      /* pointers mean nothing in a file */
+        fwrite(&p, sizeof(p), 1, f);
+    }
+    fwrite(a0.data(), 8, m, f);
+    fwrite(br.data(), 8, 7 * m, f);
+    fclose(f);
+}
+
+/* what REBOUND's heartbeat does for the archive: before the first step and after every completed step */
+static void archive_heartbeat(struct reb_simulation* r) {
+    if (r->simulationarchive_auto_step && r->simulationarchive_next_step <= r->steps_done) {
+        r->simulationarchive_next_step += r->simulationarchive_auto_step;
+        reb_simulation_save_to_file(r, NULL);
+    }
+}
+
+extern "C" struct reb_simulationarchive* reb_simulationarchive_create_from_file(const char* filename) {
+    FILE* f = filename ? fopen(filename, "rb") : NULL;
+    if (!f) return NULL;
+    char magic[16];
+    if (fread(magic, 1, 16, f) != 16 || memcmp(magic, AB_SA_MAGIC, 16)) {
+        fprintf(stderr, "\n(assist-b200) Error: %s is not a snapshot file written by reb_simulation_save_to_file.\n", filename);
+        fclose(f);
+        return NULL;
+    }
+    std::vector<double> t;
+    std::vector<long> off;
+    for (;;) {
+        const long here = ftell(f);
+        uint64_t bytes;
+        AbSnapHead h;
+        if (fread(&bytes, 8, 1, f) != 1) break;
+        if (bytes < sizeof(h) || fread(&h, sizeof(h), 1, f) != 1) break;
+        if (fseek(f, (long)(bytes - sizeof(h)), SEEK_CUR)) break;
+        if (ftell(f) != here + 8 + (long)bytes) break;
+        /* a truncated last snapshot is dropped */
+        {
+            const long end_of_blob = ftell(f);
+            fseek(f, 0, SEEK_END);
+            const long end = ftell(f);
+            if (end_of_blob > end) break;
+            fseek(f, end_of_blob, SEEK_SET);
+        }
+        t.push_back(h.t);
+        off.push_back(here);
+    }
+    fclose(f);
+    struct reb_simulationarchive* sa = (struct reb_simulationarchive*)calloc(1, sizeof(*sa));
+    sa->filename = strdup(filename);
+    sa->nblobs = (long)t.size();
+    sa->t = (double*)malloc(sizeof(double) * (t.size() + 1));
+    sa->b200_offset = (long*)malloc(sizeof(long) * (off.size() + 1));
+    for (size_t i = 0; i < t.size(); i++) { sa->t[i] = t[i]; sa->b200_offset[i] = off[i]; }
+    return sa;
+}
+
+extern "C" void reb_simulationarchive_free(struct reb_simulationarchive* sa) {
+    if (!sa) return;
+    free(sa->filename); free(sa->t); free(sa->b200_offset);
+    free(sa);
+}
+
+extern "C" void reb_simulation_create_from_simulationarchive_with_messages(
+        struct reb_simulation* r, struct reb_simulationarchive* sa, int64_t snapshot,
+        enum reb_simulation_binary_error_codes* warnings) {
+    if (warnings) *warnings = REB_SIMULATION_BINARY_WARNING_NONE;
+    if (!r || !sa) return;
+    if (snapshot < 0) snapshot += sa->nblobs;
+    if (snapshot < 0 || snapshot >= sa->nblobs) { reb_simulation_error(r, "Snapshot index out of range."); return; }
+    FILE* f = fopen(sa->filename, "rb");
+    if (!f) { reb_simulation_error(r, "Cannot open the snapshot file."); return; }
+    uint64_t bytes;
+    AbSnapHead h;
+    bool ok = !fseek(f, sa->b200_offset[snapshot], SEEK_SET) && fread(&bytes, 8, 1, f) == 1 && fread(&h, sizeof(h), 1, f) == 1;
+    if (ok) {
+        r->t = h.t; r->dt = h.dt; r->dt_last_done = h.dt_last_done; r->steps_done = h.steps_done;
+        r->integrator = REB_INTEGRATOR_IAS15; r->gravity = REB_GRAVITY_NONE; r->force_is_velocity_dependent = 1;
+        r->ri_ias15.adaptive_mode = 1;
+        r->N = 0; r->N_var = 0;
+        free(r->var_config);
+        r->var_config = NULL;
+        r->N_var_config = h.N_var_config;
+        if (h.N_var_config) r->var_config = (struct reb_variational_configuration*)calloc(h.N_var_config, sizeof(struct reb_variational_configuration));
+        for (unsigned int v = 0; ok && v < h.N_var_config; v++) {
+            int32_t pair[2];
+            ok = fread(pair, 4, 2, f) == 2;
+            r->var_config[v].sim = r; r->var_config[v].order = 1; r->var_config[v].index = pair[0]; r->var_config[v].testparticle = pair[1];
+        }
+        for (unsigned int i = 0; ok && i < h.N; i++) {
+            struct reb_particle p;
+            ok = fread(&p, sizeof(p), 1, f) == 1;
+            if (ok) reb_simulation_add(r, p);
+        }
+        r->N_var = (int)h.N_var;
+        const size_t m = 3 * (size_t)h.N;
+        ias15_alloc(r, h.N);
+        struct reb_integrator_ias15* ri = &r->ri_ias15;
+        ok = ok && fread(ri->a0, 8, m, f) == m;
+        double* seven[] = {ri->br.p0, ri->br.p1, ri->br.p2, ri->br.p3, ri->br.p4, ri->br.p5, ri->br.p6};
+        for (double* p : seven) ok = ok && fread(p, 8, m, f) == m;
+        /* as REBOUND leaves them after a completed step: x0, v0 = the particles' state */
+        for (unsigned int i = 0; ok && i < h.N; i++) {
+            ri->x0[3 * i] = r->particles[i].x; ri->x0[3 * i + 1] = r->particles[i].y; ri->x0[3 * i + 2] = r->particles[i].z;
+            ri->v0[3 * i] = r->particles[i].vx; ri->v0[3 * i + 1] = r->particles[i].vy; ri->v0[3 * i + 2] = r->particles[i].vz;
+        }
+    }
+    fclose(f);
+    if (!ok) reb_simulation_error(r, "Snapshot file is truncated or corrupt.");
+}
+
+/* ------------------------------------------------------------------------ */
 /* compute entry points                                                     */
 /* ------------------------------------------------------------------------ */
 
@@ -397,15 +594,17 @@ extern "C" enum REB_STATUS reb_simulation_integrate(struct reb_simulation* const
     AbHostBatch* hb = sync_to_device(r);
     if (!hb) return r->status;
     int rc;
-    if (r->heartbeat) {
-        /* one accepted step per launch so the callback sees every step */
-        r->heartbeat(r);
+    if (r->heartbeat || r->simulationarchive_auto_step) {
+        /* one accepted step per launch so the callback (and the snapshot file) sees every step */
+        if (r->heartbeat) r->heartbeat(r);
+        archive_heartbeat(r);
         int resume = 0;
         while (true) {
             rc = ab_gpu_batch_integrate_ex(hb->gb, tmax, r->exact_finish_time, 1, resume);
             if (rc) break;
             if (sync_from_device(r, hb)) return r->status;
-            r->heartbeat(r);
+            if (r->heartbeat) r->heartbeat(r);
+            archive_heartbeat(r);
             if (r->status >= 0) break;
             resume = 1;
         }

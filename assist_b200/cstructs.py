@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import ctypes
 from ctypes import (CFUNCTYPE, POINTER, Structure, c_char_p, c_double, c_int, c_int64,
-                    c_long, c_size_t, c_uint, c_uint32, c_uint64, c_void_p)
+                    c_long, c_size_t, c_uint, c_uint32, c_uint64, c_ulonglong, c_void_p)
 
 
 class Particle(Structure):
@@ -64,7 +64,15 @@ Simulation._fields_ = [
     ("additional_forces", FORCE_FN), ("pre_timestep_modifications", FORCE_FN),
     ("post_timestep_modifications", FORCE_FN), ("heartbeat", FORCE_FN),
     ("extras", c_void_p), ("extras_cleanup", FORCE_FN),
-    ("messages", c_char_p), ("messages_waiting", c_int), ("b200_batch", c_void_p)]
+    ("messages", c_char_p), ("messages_waiting", c_int), ("b200_batch", c_void_p),
+    ("simulationarchive_filename", c_char_p), ("simulationarchive_auto_step", c_uint64),
+    ("simulationarchive_next_step", c_uint64)]
+
+
+class SimulationArchive(Structure):
+    """include/rebound.h: struct reb_simulationarchive (snapshot file of an attached simulation)."""
+    _fields_ = [("r", POINTER(Simulation)), ("filename", c_char_p), ("nblobs", c_long), ("t", POINTER(c_double)),
+                ("b200_offset", POINTER(c_long))]
 
 
 class Ephem(Structure):
@@ -150,4 +158,21 @@ def bind(lib):
     lib.assist_all_ephem.argtypes = [P(Ephem), c_void_p, c_int, c_double] + [P(c_double)] * 10
     lib.assist_detect_ephemeris_file_format.restype = c_int
     lib.assist_detect_ephemeris_file_format.argtypes = [c_int]
+    lib.reb_simulation_create_from_simulationarchive_with_messages.restype = None
+    lib.reb_simulation_create_from_simulationarchive_with_messages.argtypes = [P(Simulation), P(SimulationArchive), c_int64, c_void_p]
+    lib.reb_simulation_steps.restype = None
+    lib.reb_simulation_steps.argtypes = [P(Simulation), c_uint]
+    lib.assist_interpolate_simulation.restype = c_int
+    lib.assist_interpolate_simulation.argtypes = [P(Simulation), P(Simulation), c_double]
+    lib.assist_create_interpolated_simulation.restype = P(Simulation)
+    lib.assist_create_interpolated_simulation.argtypes = [P(SimulationArchive), c_double]
+    if hasattr(lib, "reb_simulation_save_to_file_step"):      # the snapshot file: product library only
+        lib.reb_simulation_save_to_file_step.restype = None
+        lib.reb_simulation_save_to_file_step.argtypes = [P(Simulation), c_char_p, c_ulonglong]
+        lib.reb_simulation_save_to_file.restype = None
+        lib.reb_simulation_save_to_file.argtypes = [P(Simulation), c_char_p]
+        lib.reb_simulationarchive_create_from_file.restype = P(SimulationArchive)
+        lib.reb_simulationarchive_create_from_file.argtypes = [c_char_p]
+        lib.reb_simulationarchive_free.restype = None
+        lib.reb_simulationarchive_free.argtypes = [P(SimulationArchive)]
     return lib

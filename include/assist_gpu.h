@@ -159,6 +159,11 @@ int assist_gpu_multi_get_counters(assist_gpu_multi* m, unsigned long long* steps
 /* sums over the devices; last_kernel_ms = the slowest device; kernel_ms_per_device (may be NULL): n_devices entries */
 int assist_gpu_multi_get_stats(assist_gpu_multi* m, struct assist_gpu_stats* stats, double* kernel_ms_per_device);
 
+/* assist_interpolate_simulation (reference src/assist.c:682-752) for m = 3 N components: the state at fraction h of
+ * the step that starts at (x0, v0, a0) and has the b coefficients br[7][m] and length dt_last_done.  Host arrays. */
+int assist_gpu_interpolate_simulation(int m, const double* x0, const double* v0, const double* a0, const double* br,
+                                      double dt_last_done, double h, double* pos, double* vel);
+
 /* Page-locked host memory for state / output buffers (cudaHostAlloc). */
 void* assist_gpu_host_alloc(size_t bytes);
 void assist_gpu_host_free(void* p);
@@ -167,7 +172,7 @@ double assist_gpu_measure_fp64_peak(int iters);
 /* Number of CUDA kernels this library has launched in this process so far (all devices, all batches). */
 unsigned long long assist_gpu_kernel_launches(void);
 /* Host-only test hook: the re-packed copy of an SPK kernel that is uploaded to the device (type-2 records only,
- * each [_jul(MID), RADIUS, (x y z) of term 0, (x y z) of term 1, ...] padded to an even number of doubles).
+ * each [_jul(MID), RADIUS, (x y z) of term 0, (x y z) of term 1, ...], zero terms up to a multiple of four).
  * *out is malloc'ed; seg_off[target * 4 + segment] = first word of that segment in the copy. */
 struct spk_s;
 int assist_gpu_spk_pack_host(const struct spk_s* file, double** out, size_t* words, long long* seg_off, int seg_off_len);

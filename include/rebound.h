@@ -168,13 +168,20 @@ struct reb_simulation {
     int messages_waiting;
     /* assist-b200 extension: opaque handle of the device batch mirroring this sim */
     void* b200_batch;
+    /* snapshots during reb_simulation_integrate (reb_simulation_save_to_file_step) */
+    char* simulationarchive_filename;
+    uint64_t simulationarchive_auto_step;   /* a snapshot every this many completed steps; 0: none */
+    uint64_t simulationarchive_next_step;
 };
 
+/* A file of snapshots of an attached simulation (what assist_create_interpolated_simulation reads back): t[] and
+ * nblobs as in REBOUND; the layout of the file is assist-b200's own (reb_surface.cpp), not REBOUND's binary format. */
 struct reb_simulationarchive {
     struct reb_simulation* r;
     char* filename;
     long nblobs;
     double* t;
+    long* b200_offset;      /* file offset of every snapshot */
 };
 
 /* ---- simulation life cycle --------------------------------------------- */
@@ -202,7 +209,16 @@ void reb_particle_isub(struct reb_particle* p1, struct reb_particle* p2);
 double reb_particle_distance(struct reb_particle* p1, struct reb_particle* p2);
 struct reb_particle reb_particle_com_of_pair(struct reb_particle p1, struct reb_particle p2);
 
-/* ---- SimulationArchive: declared for source compatibility, not provided -- */
+/* ---- SimulationArchive ------------------------------------------------- */
+/* Snapshots of an ASSIST-attached simulation: time, step sizes, particles and what dense output needs of the last
+ * completed step (its start acceleration and b coefficients).  One is appended before the first step of
+ * reb_simulation_integrate and after every `step` completed steps. */
+void reb_simulation_save_to_file_step(struct reb_simulation* const r, const char* filename, unsigned long long step);
+void reb_simulation_save_to_file(struct reb_simulation* const r, const char* filename);
+struct reb_simulationarchive* reb_simulationarchive_create_from_file(const char* filename);
+void reb_simulationarchive_free(struct reb_simulationarchive* sa);
+/* Fills `r` (a fresh reb_simulation_create()) from snapshot `snapshot`: t, dt, dt_last_done, particles, and
+ * ri_ias15.x0 / v0 / a0 / br as REBOUND leaves them after a completed step.  ASSIST is not attached to it. */
 void reb_simulation_create_from_simulationarchive_with_messages(
         struct reb_simulation* r, struct reb_simulationarchive* sa, int64_t snapshot,
         enum reb_simulation_binary_error_codes* warnings);

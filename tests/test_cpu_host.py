@@ -218,8 +218,8 @@ def test_packed_spk_copy_is_a_pure_rearrangement(lib, paths):
 
 def test_reference_programs_compile_and_link_unmodified():
     """Every C program of the reference (unit_tests/*/problem.c, examples/*/problem.c) compiles UNMODIFIED against
-    include/ and links with the product library; only the two that need REBOUND's SimulationArchive do not
-    (SURVEY 8f rank 4).  Covers the header names spk.h / ascii_ephem.h / forces.h / tools.h and the evaluator
+    include/ and links with the product library, the two SimulationArchive programs included.
+    Covers the header names spk.h / ascii_ephem.h / forces.h / tools.h and the evaluator
     entry points of reference src/spk.h:113-122, src/ascii_ephem.h:15-22."""
     import ref_programs
     if not os.path.isdir(ref_programs.REF):
@@ -228,3 +228,41 @@ def test_reference_programs_compile_and_link_unmodified():
     assert len(res) >= 34
     failed = {k for k, v in res.items() if not v[0]}
     assert failed == ref_programs.NEED_ARCHIVE, {k: res[k][1] for k in failed}
+
+
+def test_snapshot_file_round_trip_without_a_gpu(lib, paths, tmp_path):
+    """The snapshot file (include/rebound.h: reb_simulation_save_to_file / reb_simulationarchive_create_from_file /
+    reb_simulation_create_from_simulationarchive_with_messages) is host code: particles, times and the variational
+    configuration come back as written; a file that is not a snapshot file is refused; outside the stored range
+    assist_create_interpolated_simulation returns NULL as the reference does (src/assist.c:602-610)."""
+    eph = lib.assist_ephem_create(paths["planets_bsp"].encode(), paths["asteroids_bsp"].encode())
+    r = lib.reb_simulation_create()
+    ax = lib.assist_attach(r, eph)
+    fn = str(tmp_path / "snap.bin").encode()
+    lib.reb_simulation_add(r, Particle(x=1.0, y=2.0, z=3.0, vx=0.1, vy=0.2, vz=0.3))
+    assert lib.reb_simulation_add_variation_1st_order(r, 0) == 1
+    for k in range(3):
+        r.contents.t = 100.0 + k
+        r.contents.dt = 0.5 + k
+        r.contents.particles[0].x = 1.0 + k
+        lib.reb_simulation_save_to_file(r, fn)
+    lib.assist_free(ax)
+    lib.reb_simulation_free(r)
+    sa = lib.reb_simulationarchive_create_from_file(fn)
+    assert sa and sa.contents.nblobs == 3 and [sa.contents.t[i] for i in range(3)] == [100.0, 101.0, 102.0]
+    r2 = lib.reb_simulation_create()
+    lib.reb_simulation_create_from_simulationarchive_with_messages(r2, sa, 1, None)
+    c = r2.contents
+    assert (c.t, c.dt, c.N, c.N_var, c.N_var_config) == (101.0, 1.5, 2, 1, 1)
+    assert (c.particles[0].x, c.particles[0].vz) == (2.0, 0.3)
+    assert c.var_config[0].index == 1 and c.var_config[0].testparticle == 0
+    assert c.ri_ias15.x0[0] == 2.0 and c.ri_ias15.v0[2] == 0.3 and c.ri_ias15.br.p6[5] == 0.0
+    lib.reb_simulation_free(r2)
+    assert not lib.assist_create_interpolated_simulation(sa, 100.5)      # inside the first interval: no accelerations yet
+    assert not lib.assist_create_interpolated_simulation(sa, 102.0)
+    lib.reb_simulationarchive_free(sa)
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(b"not a snapshot file" * 4)
+    assert not lib.reb_simulationarchive_create_from_file(str(bad).encode())
+    assert not lib.reb_simulationarchive_create_from_file(b"/nonexistent/file.bin")
+    lib.assist_ephem_free(eph)

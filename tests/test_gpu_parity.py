@@ -543,3 +543,57 @@ def test_convert_to_rebound_matches_the_reference(eph, fmt, ref, paths, lib, mer
     assert out[0][0] == out[1][0] == 11 + merge_moon + 3 and out[0][1] == out[1][1] == 11 + merge_moon
     assert out[0][2] == out[1][2] and out[0][3] == out[1][3]
     assert np.array_equal(out[0][4], out[1][4])
+
+
+def test_dropin_snapshot_file_and_interpolated_simulation(eph, fmt, ref, paths, lib, tmp_path):
+    """reference unit_tests/interpolation_spk / interpolation_ascii on the synthetic files: a snapshot
+    after every step (reb_simulation_save_to_file_step), the file read back, assist_create_interpolated_simulation at
+    a time inside a step.  The snapshots carry the times of the reference's own steps bit for bit; the interpolated
+    state equals the reference's assist_interpolate_simulation (src/assist.c:682-752) run on two reference
+    simulations stepped to either side of that time, bit for bit; and it agrees with a direct integration."""
+    t0 = cases.T0
+    st = np.array([[-2.724183384883979E+00, -3.523994546329214E-02, 9.036596202793466E-02,
+                    -1.374545432301129E-04, -1.027075301472321E-02, -4.195690627695180E-03],
+                   [1.1, 0.3, 0.05, -0.004, 0.014, 0.002]])
+    tq = t0 + 30.0
+    fn = str(tmp_path / ("out_%s.bin" % fmt)).encode()
+    r, ax = _product_sim(lib, eph.ptr, t0, st)
+    lib.reb_simulation_save_to_file_step(r, fn, 1)
+    assert lib.reb_simulation_integrate(r, t0 + 584.0) == 0
+    steps = int(r.contents.steps_done)
+    lib.assist_free(ax)
+    lib.reb_simulation_free(r)
+    sa = lib.reb_simulationarchive_create_from_file(fn)
+    assert sa and sa.contents.nblobs == steps + 1 and sa.contents.t[0] == t0
+    times = np.array([sa.contents.t[i] for i in range(sa.contents.nblobs)])
+    blob = int(np.argmax(times[1:] >= tq)) + 1
+    assert 1 < blob < steps
+    ri = lib.assist_create_interpolated_simulation(sa, tq)
+    assert ri and ri.contents.N == 2
+    got = np.array([[ri.contents.particles[i].x, ri.contents.particles[i].y, ri.contents.particles[i].z,
+                     ri.contents.particles[i].vx, ri.contents.particles[i].vy, ri.contents.particles[i].vz] for i in range(2)])
+    got_t = ri.contents.t
+    lib.reb_simulation_free(ri)
+    # outside the stored range: NULL, as the reference
+    assert not lib.assist_create_interpolated_simulation(sa, times[1]) and not lib.assist_create_interpolated_simulation(sa, times[-1])
+    lib.reb_simulationarchive_free(sa)
+
+    reph = rh.open_ephem(ref, planets_path(paths, fmt), paths["asteroids_bsp"])
+    s1 = rh.Sim(ref, reph, t0, st)
+    s2 = rh.Sim(ref, reph, t0, st)
+    ref.reb_simulation_steps(s1.r, blob - 1)
+    ref.reb_simulation_steps(s2.r, blob)
+    assert s1.t == times[blob - 1] and s2.t == times[blob]
+    h = (tq - s1.t) / s2.dt_last_done
+    assert ref.assist_interpolate_simulation(s1.r, s2.r, h) == 1
+    want = s1.state()[:, 0, :]
+    assert np.array_equal(got, want) and got_t == s1.t
+    s1.close()
+    s2.close()
+
+    b = ab.Batch(eph, 2, 0, ab.SHARED_STEP)
+    b.set_state(t0, st[:, None, :])
+    b.integrate(tq)
+    direct = b.get_state()["state"][:, 0, :]
+    b.close()
+    assert np.abs(got[:, :3] - direct[:, :3]).max() < 5e-13
