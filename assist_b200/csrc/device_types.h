@@ -5,7 +5,8 @@
 #include <stdint.h>
 
 #define AB_NPLANETS 11
-#define AB_MAX_AST 16            /* asteroids held in the per-time body table */
+#define AB_MAX_AST 16            /* asteroids held in the per-time body table (sb441-n16) */
+#define AB_MAX_AST_ALL 1024      /* targets of a small-body kernel: those beyond the table (sb441-n373) are evaluated where the direct term needs them */
 #define AB_MAX_BODIES (AB_NPLANETS + AB_MAX_AST)
 #define AB_MAXSEG 4              /* SPK segments per target */
 #define AB_MAX_PTGT 16           /* SPK targets in a planets kernel */
@@ -44,7 +45,8 @@ struct AbSpkTarget {
 struct AbEphem {
     double jd_ref;
     int planets_source;
-    int n_ast;
+    int n_ast;                   /* asteroids in the body tables: min(targets of the small-body kernel, AB_MAX_AST) */
+    int n_ast_x;                 /* further asteroids (sb441-n373: 357), direct term only, evaluated on the fly */
     /* constants, reference src/assist.h:140-154 */
     double AU, EMRAT, J2E, J3E, J4E, J2SUN, Re_eq, Rs_eq, c_squared, over_c_squared;
     /* unit-conversion divisors and their reciprocals (position, velocity, acceleration) */
@@ -98,6 +100,7 @@ struct AbBodies {
     double eih_term1[AB_NPLANETS];
     double eih_ar[AB_NPLANETS][3];  /* a_j as the real-particle pass rounds it */
     double eih_av[AB_NPLANETS][3];  /* a_j as the variational pass rounds it */
+    double t;                       /* the time the table is for (the asteroids beyond the table are evaluated at it) */
     int status;
 };
 
@@ -111,6 +114,7 @@ struct AbNode {
     double eih_term1[1];
     double eih_ar[1][3];
     double eih_av[1][3];
+    double t;
 };
 
 /* time slices of the work-queue scheduler (kernels.cu, pp_queue_kernel) */
@@ -123,7 +127,7 @@ struct AbSlices {
     const int* order;         /* [n] or NULL: the queue hands out system order[k] as its k-th item of a window (longest expected first) */
 };
 
-#define AB_NODE_DOUBLES 94   /* doubles of an AbNode after the gm pointer */
+#define AB_NODE_DOUBLES 95   /* doubles of an AbNode after the gm pointer */
 
 /* Device-side state of a batch.  Arrays are structure-of-arrays over systems:
  * element (component k, system i) lives at [k * n + i]; the seven-deep IAS15

@@ -215,7 +215,7 @@ __device__ __forceinline__ int ab_planet(const AbEphem& E, int body, double t, d
 /* Heliocentric asteroid position in AU, reference src/spk.c:405-481. */
 __device__ __forceinline__ int ab_asteroid(const AbEphem& E, int m, double t, double* GM, double x[3]) {
     if (E.spka_img == nullptr) return AB_ERR_AST_FILE;
-    if (m < 0 || m >= E.n_ast) return AB_ERR_NAST;
+    if (m < 0 || m >= E.n_ast + E.n_ast_x) return AB_ERR_NAST;
     const AbSpkTarget& tg = E.a_tgt[m];
     const double jd_ref = E.jd_ref;
     if (jd_ref + t < tg.beg || jd_ref + t > tg.end) return AB_ERR_COVERAGE;
@@ -225,6 +225,21 @@ __device__ __forceinline__ int ab_asteroid(const AbEphem& E, int m, double t, do
     double u[3], dv[3], dw[3];
     ab_cheb3<0, true>(cf, P, z, c, u, dv, dw);
     x[0] = AB_DIVK(u[0], 149597870.7); x[1] = AB_DIVK(u[1], 149597870.7); x[2] = AB_DIVK(u[2], 149597870.7);
+    return AB_OK;
+}
+
+/* An asteroid beyond the body table (sb441-n373), barycentric, for the direct term (reference src/forces.c:208-224 via
+ * assist_all_ephem): evaluated where it is needed.  Out of line: the direct loop of the n16 runs stays as it is. */
+__device__ __noinline__ void ab_extra_asteroid(const AbEphem& E, int m, double t, double sx, double sy, double sz, double* GM, double* c) {
+    double x[3] = {0.0, 0.0, 0.0};
+    *GM = 0.0;
+    ab_asteroid(E, m, t, GM, x);        /* coverage has been checked for the whole step (ab_extra_coverage) */
+    c[0] = x[0] + sx; c[1] = x[1] + sy; c[2] = x[2] + sz;
+}
+__device__ __forceinline__ int ab_extra_coverage(const AbEphem& E, double t) {
+    const double jd = E.jd_ref + t;
+    for (int m = E.n_ast; m < E.n_ast + E.n_ast_x; m++)
+        if (jd < E.a_tgt[m].beg || jd > E.a_tgt[m].end) return AB_ERR_COVERAGE;
     return AB_OK;
 }
 
@@ -260,6 +275,8 @@ __device__ void ab_body_states(const AbEphem& E, const AbForceOpts& F, double t,
         B.pos[AB_NPLANETS + m][1] = x[1] + B.pos[0][1];
         B.pos[AB_NPLANETS + m][2] = x[2] + B.pos[0][2];
     }
+    if (E.n_ast_x > 0 && status == AB_OK) status = ab_extra_coverage(E, t);
+    B.t = t;
     if (need_eih && status == AB_OK) {
         for (int j = 0; j < ns; j++) {
             double term1 = 0.0;
@@ -441,9 +458,10 @@ __device__ __noinline__ int ab_fill_nodes(const AbEphem& E, const AbForceOpts& F
                 if (jd < E.p_tgt[idx].beg || jd > E.p_tgt[idx].end) return AB_ERR_COVERAGE;
             }
         }
-        for (int m = 0; m < E.n_ast; m++)
+        for (int m = 0; m < E.n_ast + E.n_ast_x; m++)
             if (jd < E.a_tgt[m].beg || jd > E.a_tgt[m].end) return AB_ERR_COVERAGE;
     }
+    for (int k = 0; k < AB_NT; k++) nodes[k].t = t[k];
     double u[AB_NT][3];
     if (E.planets_source == AB_SRC_ASCII) {
         double emb[AB_NT][3], lun[AB_NT][3];

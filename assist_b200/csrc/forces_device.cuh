@@ -708,7 +708,9 @@ __device__ __forceinline__ int ab_direct_body(int k, int ast_num) {
 template <int KM, class BT>
 __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT& B, AbSysT<KM>& S,
                                 double xo, double yo, double zo) {
-    const int ast_num = E.n_ast;
+    /* all asteroids of the small-body kernel, in file order, come first in the reference's loop; those beyond the
+     * body table (sb441-n373: indices AB_MAX_BODIES ...) are evaluated here, at the table's time */
+    const int ast_num = E.n_ast + E.n_ast_x;
     const int nb = AB_NPLANETS + ast_num;
     const double px = S.x[0][0], py = S.x[0][1], pz = S.x[0][2];
     const int fmask = F.forces;
@@ -725,7 +727,13 @@ __device__ void ab_force_direct(const AbEphem& E, const AbForceOpts& F, const BT
         const double cx = bx, cy = by, cz = bz;
         if (k + 1 < nb) {
             i_next = ab_direct_body(k + 1, ast_num);
-            bx = B.pos[i_next][0]; by = B.pos[i_next][1]; bz = B.pos[i_next][2]; bgm = gm[i_next];
+            if (i_next < AB_MAX_BODIES) {
+                bx = B.pos[i_next][0]; by = B.pos[i_next][1]; bz = B.pos[i_next][2]; bgm = gm[i_next];
+            } else {
+                double c3[3];
+                ab_extra_asteroid(E, i_next - AB_NPLANETS, B.t, B.pos[0][0], B.pos[0][1], B.pos[0][2], &bgm, c3);
+                bx = c3[0]; by = c3[1]; bz = c3[2];
+            }
         }
         const double dx = px + (xo - cx);
         const double dy = py + (yo - cy);

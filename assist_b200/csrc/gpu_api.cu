@@ -352,12 +352,15 @@ static int build_ephem_impl(const struct assist_ephem* e, AbEphem* E, bool host_
     for (int q = 0; q < 3; q++) E->u_rd[q] = 1.0 / E->u_d[q];
     if (e->spk_asteroids) {
         struct spk_s* sb = e->spk_asteroids;
-        if (sb->num > AB_MAX_AST)
-            return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "small-body kernel has %d targets (max %d in this build)", sb->num, AB_MAX_AST);
+        if (sb->num > AB_MAX_AST_ALL)
+            return set_err(ASSIST_GPU_ERR_UNSUPPORTED, "small-body kernel has %d targets (max %d in this build)", sb->num, AB_MAX_AST_ALL);
         AbSpkDesc* ad = nullptr;
         if ((rc = spk_desc(sb, &ad))) return rc;
         for (int m = 0; m < sb->num; m++) ad->tg[m].mass = sb->targets[m].mass;
-        E->n_ast = sb->num;
+        /* the first AB_MAX_AST targets (all of sb441-n16) live in the per-time body tables; the others (sb441-n373)
+         * act through the direct term only and are evaluated inside it */
+        E->n_ast = sb->num < AB_MAX_AST ? sb->num : AB_MAX_AST;
+        E->n_ast_x = sb->num - E->n_ast;
         if (host_mode) {
             if (ad->host_copy.empty()) { ad->host_copy.assign(ad->words, 0.0); pack_spk(sb, ad->off, ad->host_copy); }
             E->spka_img = ad->host_copy.data();
@@ -370,14 +373,14 @@ static int build_ephem_impl(const struct assist_ephem* e, AbEphem* E, bool host_
             bool same = sb->b200_dev_targets[dev] != nullptr && sent.size() == (size_t)sb->num;
             for (int m = 0; same && m < sb->num; m++) same = (sent[m] == sb->targets[m].mass);
             if (!same) {
-                if (!sb->b200_dev_targets[dev]) CU(cudaMalloc(&sb->b200_dev_targets[dev], sizeof(AbSpkTarget) * AB_MAX_AST));
+                if (!sb->b200_dev_targets[dev]) CU(cudaMalloc(&sb->b200_dev_targets[dev], sizeof(AbSpkTarget) * (sb->num > AB_MAX_AST ? sb->num : AB_MAX_AST)));
                 CU(cudaMemcpy(sb->b200_dev_targets[dev], ad->tg.data(), sizeof(AbSpkTarget) * sb->num, cudaMemcpyHostToDevice));
                 sent.resize((size_t)sb->num);
                 for (int m = 0; m < sb->num; m++) sent[m] = sb->targets[m].mass;
             }
             E->a_tgt = (const AbSpkTarget*)sb->b200_dev_targets[dev];
         }
-        for (int m = 0; m < sb->num; m++) E->gm[AB_NPLANETS + m] = sb->targets[m].mass;
+        for (int m = 0; m < E->n_ast; m++) E->gm[AB_NPLANETS + m] = sb->targets[m].mass;
     }
     /* common coverage window (the checks of ab_fill_nodes / abc_coverage, folded) */
     E->cov_lo = -1e300; E->cov_hi = 1e300; E->cov_simple = 1;
@@ -467,7 +470,7 @@ extern "C" int assist_gpu_ephem_eval(const struct assist_ephem* ephem, int math,
     int rc = build_ephem(ephem, &E);
     if (rc) return rc;
     if (n_t <= 0) return 0;
-    const int nb = AB_NPLANETS + E.n_ast;
+    const int nb = AB_NPLANETS + E.n_ast + E.n_ast_x;
     double *d_t = nullptr, *d_out = nullptr;
     int* d_st = nullptr;
     SCRATCH(0, sizeof(double) * n_t, d_t);
@@ -1012,7 +1015,8 @@ static int ensure_working_batch(assist_gpu_batch* b) {
 /* ---- pp_coop_kernel: who runs it, its working slots and the plan of its worker warps ---- */
 
 static bool coop_applies(const assist_gpu_batch* b, const AbForceOpts& F) {
-    return b->sched_coop && b->mode == ASSIST_GPU_PER_PARTICLE && b->K == 1 && F.gr_eih_sources == 1 && !F.geocentric;
+    return b->sched_coop && b->mode == ASSIST_GPU_PER_PARTICLE && b->K == 1 && F.gr_eih_sources == 1 && !F.geocentric &&
+           !(b->ephem->spk_asteroids && b->ephem->spk_asteroids->num > AB_MAX_AST);      /* sb441-n373: the work-queue kernel */
 }
 
 /* Spread the force terms over the worker warps: longest task first onto the least loaded warp.  The weights are

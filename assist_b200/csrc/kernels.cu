@@ -58,7 +58,7 @@ __device__ __noinline__ void ab_forces_ol(const AbEphem& E, const AbForceOpts& F
 /* out[n_t][nbodies][10], status[n_t][nbodies]; one thread per (time, body). */
 __global__ void ephem_eval_kernel(const __grid_constant__ AbEphem E, const double* __restrict__ t, int n_t,
                                   double* __restrict__ out, int* __restrict__ status) {
-    const int nb = AB_NPLANETS + E.n_ast;
+    const int nb = AB_NPLANETS + E.n_ast + E.n_ast_x;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)n_t * nb) return;
     const int it = (int)(gid / nb);
@@ -840,7 +840,7 @@ cudaError_t AB_CAT3(ab_upload_constants, AB_SFX, AB_TU)() {
 
 #if AB_TU == 0
 cudaError_t AB_CAT2(ab_launch_ephem_eval, AB_SFX)(const AbEphem& E, const double* t, int n_t, double* out, int* status, cudaStream_t st) {
-    const long long total = (long long)n_t * (AB_NPLANETS + E.n_ast);
+    const long long total = (long long)n_t * (AB_NPLANETS + E.n_ast + E.n_ast_x);
     const int grid = (int)((total + AB_BLOCK - 1) / AB_BLOCK);
     ephem_eval_kernel<<<grid, AB_BLOCK, 0, st>>>(E, t, n_t, out, status);
     return cudaGetLastError();

@@ -138,7 +138,7 @@ def _ecl2equ(v):
 class SolarSystemModel:
     """Closed-form positions (km) of every body the files describe."""
 
-    def __init__(self):
+    def __init__(self, n_extra_asteroids=0):
         self.gms = CONSTANTS["GMS"]
         self.emrat = CONSTANTS["EMRAT"]
         self.planets = {}
@@ -157,6 +157,14 @@ class SolarSystemModel:
             n = np.sqrt(self.gms / a ** 3)
             self.asteroids.append(dict(num=num, a=a, e=e, i=np.deg2rad(i), node=np.deg2rad(node),
                                        argp=np.deg2rad(argp), M0=np.deg2rad(M0), n=n, gm=gm))
+
+        # further perturbers of an sb441-n373 style kernel: seeded main-belt ellipses, numbers 1001 ...
+        rng = np.random.default_rng(20261737)
+        for k in range(n_extra_asteroids):
+            a = rng.uniform(2.2, 3.4)
+            self.asteroids.append(dict(num=1001 + k, a=a, e=rng.uniform(0.02, 0.25), i=np.deg2rad(rng.uniform(0.5, 25.0)),
+                                       node=rng.uniform(0, 2 * np.pi), argp=rng.uniform(0, 2 * np.pi), M0=rng.uniform(0, 2 * np.pi),
+                                       n=np.sqrt(self.gms / a ** 3), gm=10.0 ** rng.uniform(-16.5, -14.0)))
 
     def _helio(self, el, jd):
         M = el["M0"] + el["n"] * (jd - JD_J2000)
@@ -420,6 +428,23 @@ def write_asteroids_bsp(path, model=None, jd_beg=JD_BEG, jd_end=JD_END, nseg=2, 
             c = cheb_fit(lambda jd: model.position("AST%d" % i, jd), t0, t0 + intlen, P)
             segments.append((2000000 + a["num"], 10, jb, jb + span, intlen, c))
     return _write_daf(path, segments, ["; synthetic sb441-n16 style kernel (assist-b200)"], "SYNTH-SB16")
+
+
+def write_extended(outdir, n_asteroids=40, jd_beg=JD_BEG, jd_end=JD_END):
+    """An sb441-n373 style pair: a small-body kernel with `n_asteroids` targets (the 16 of sb441-n16 first) and a
+    planets kernel whose comment area carries the MAxxxx masses of all of them (same planet records as
+    synth_planets.bsp).  Returns dict of paths.  Idempotent."""
+    os.makedirs(outdir, exist_ok=True)
+    paths = {"planets_bsp": os.path.join(outdir, "synth_planets_n%d.bsp" % n_asteroids),
+             "asteroids_bsp": os.path.join(outdir, "synth_sb%d.bsp" % n_asteroids)}
+    if all(os.path.exists(p) for p in paths.values()):
+        return paths
+    model = SolarSystemModel(n_extra_asteroids=n_asteroids - len(ASTEROIDS))
+    write_planets_bsp(paths["planets_bsp"] + ".tmp", model, jd_beg, jd_end)
+    write_asteroids_bsp(paths["asteroids_bsp"] + ".tmp", model, jd_beg, jd_end)
+    for p in paths.values():
+        os.replace(p + ".tmp", p)
+    return paths
 
 
 def write_all(outdir, jd_beg=JD_BEG, jd_end=JD_END):

@@ -100,3 +100,25 @@ def geocentric_case(earth_state):
     (earth_state(t) -> [x y z vx vy vz] of ASSIST body 3)."""
     st = populations.neo(12, seed=37)
     return st - np.asarray(earth_state(T0))[None, :]
+
+
+# ---- small-body kernels with more than 16 targets (tests/golden/make_golden_n373.py, SURVEY 8f rank 2) ----
+N373_SIZES = (40, 373)
+
+
+def n373_times():
+    return np.array([T0, T0 + 17.3, T0 - 1234.56789, T0 + 3000.25, T0 + 199.99999])
+
+
+def n373_force_systems():
+    """6 systems, real particle + 2 variational particles (the direct term's Jacobians see every asteroid too)."""
+    st = populations.neo_mba_mix(6, seed=373)
+    return populations.with_variations(st, 2)
+
+
+def n373_pp_particles():
+    return populations.neo_mba_mix(8, seed=374)
+
+
+def n373_shared_systems():
+    return populations.with_variations(populations.neo_mba_mix(6, seed=375), 1)

@@ -54,6 +54,23 @@ def test_reference_reproduces_golden(ref, reph, fmt, golden):
     assert cnt["steps"] == g["pp_counts"][0]
 
 
+def test_reference_reproduces_golden_n373(ref):
+    """tests/golden/golden_n373.npz (small-body kernels with 40 and 373 targets) is what the reference
+    build produces today: N = 40 in full (ephemeris, one force evaluation, the per-particle integrations)."""
+    from conftest import ROOT
+    from assist_b200.synth import ephem_writer
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_n373.npz"))
+    N = cases.N373_SIZES[0]
+    p = ephem_writer.write_extended(os.path.join(ROOT, "data"), N)
+    e = rh.open_ephem(ref, p["planets_bsp"], p["asteroids_bsp"])
+    assert e.contents.spk_asteroids and ref.assist_gpu_ephem_nbodies(e) == 11 + N if hasattr(ref, "assist_gpu_ephem_nbodies") else True
+    out, st = rh.all_bodies(ref, e, cases.n373_times(), nbodies=11 + N)
+    assert (st == 0).all() and np.array_equal(np.nan_to_num(out, nan=-7), np.nan_to_num(g["eph%d" % N], nan=-7))
+    assert np.array_equal(rh.forces(ref, e, cases.T0 + 17.25, cases.n373_force_systems(), forces=0x7F), g["acc%d" % N])
+    fin, ts, dts, _ = rh.integrate_each(ref, e, cases.T0, cases.n373_pp_particles(), cases.T0 + 400.0, forces=0x7F)
+    assert np.array_equal(fin, g["pp_final"]) and np.array_equal(ts, g["pp_t"]) and np.array_equal(dts, g["pp_dt"])
+
+
 def test_ephemeris_formats_agree(ref, paths):
     """SPK and DE-binary providers hold the same Chebyshev data: same states (reference
     unit_tests/apophis_drift checks the same thing on real files)."""
