@@ -441,6 +441,13 @@ extern "C" void reb_simulation_save_to_file(struct reb_simulation* const r, cons
     const size_t m = 3 * (size_t)r->N;
     std::vector<double> a0(m, 0.0), br(7 * m, 0.0);
     AbHostBatch* hb = (AbHostBatch*)r->b200_batch;
+    if (!hb && r->ri_ias15.a0 && r->ri_ias15.br.p0 && r->ri_ias15.N_allocated >= r->N) {
+        /* a simulation restored from a snapshot: it carries the step data itself */
+        const struct reb_integrator_ias15* ri = &r->ri_ias15;
+        const double* seven[7] = {ri->br.p0, ri->br.p1, ri->br.p2, ri->br.p3, ri->br.p4, ri->br.p5, ri->br.p6};
+        memcpy(a0.data(), ri->a0, sizeof(double) * m);
+        for (int q = 0; q < 7; q++) memcpy(&br[q * m], seven[q], sizeof(double) * m);
+    }
     if (hb && r->steps_done > 0) {
         const size_t per = (size_t)hb->n_real * hb->K;
         std::vector<double> la(per * 3), bb(7 * per * 3);

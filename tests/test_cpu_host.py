@@ -257,7 +257,18 @@ def test_snapshot_file_round_trip_without_a_gpu(lib, paths, tmp_path):
     assert (c.particles[0].x, c.particles[0].vz) == (2.0, 0.3)
     assert c.var_config[0].index == 1 and c.var_config[0].testparticle == 0
     assert c.ri_ias15.x0[0] == 2.0 and c.ri_ias15.v0[2] == 0.3 and c.ri_ias15.br.p6[5] == 0.0
+    # a restored simulation written out again carries its step data along
+    c.ri_ias15.a0[1] = 0.25
+    c.ri_ias15.br.p3[4] = -0.5
+    fn2 = str(tmp_path / "snap2.bin").encode()
+    lib.reb_simulation_save_to_file(r2, fn2)
     lib.reb_simulation_free(r2)
+    sa2 = lib.reb_simulationarchive_create_from_file(fn2)
+    r3 = lib.reb_simulation_create()
+    lib.reb_simulation_create_from_simulationarchive_with_messages(r3, sa2, 0, None)
+    assert r3.contents.ri_ias15.a0[1] == 0.25 and r3.contents.ri_ias15.br.p3[4] == -0.5 and r3.contents.t == 101.0
+    lib.reb_simulation_free(r3)
+    lib.reb_simulationarchive_free(sa2)
     assert not lib.assist_create_interpolated_simulation(sa, 100.5)      # inside the first interval: no accelerations yet
     assert not lib.assist_create_interpolated_simulation(sa, 102.0)
     lib.reb_simulationarchive_free(sa)
