@@ -528,6 +528,21 @@ static inline int abc_series_table(const AbEphem& E, const AbSpkTarget* ast, AbS
     for (int m = 0; m < E.n_ast && m < AB_MAX_AST; m++) out[ABC_S_AST0 + m] = ast[m];
     for (int s = 0; s < ABC_NSERIES; s++)
         for (int k = 0; k < AB_MAXSEG; k++) out[s].seg[k].stage_cap = out[s].seg[k].R > 0 ? ABC_ST_BUF / out[s].seg[k].R : 0;
+    /* pad = 1: the series has the time grid of the series before it (same segments, same record boundaries, same record
+     * size -- the 16 asteroids of sb441-n16, the outer planets): segment, record index and staging layout of a lane are
+     * then the same numbers, formed from the same operands, and are not formed again */
+    for (int s = 0; s < ABC_NSERIES; s++) {
+        out[s].pad = 0;
+        if (s == 0 || out[s].nseg < 1 || out[s].nseg != out[s - 1].nseg) continue;
+        const AbSpkTarget &a = out[s], &b = out[s - 1];
+        bool same = a.beg == b.beg && a.end == b.end && a.res == b.res && a.res_rd == b.res_rd;
+        for (int k = 0; same && k < a.nseg; k++) {
+            const AbSpkSeg &p = a.seg[k], &q = b.seg[k];
+            same = p.R == q.R && p.nrec == q.nrec && p.jul_init == q.jul_init && p.intlen_d == q.intlen_d &&
+                   p.intlen_rd == q.intlen_rd && p.stage_cap == q.stage_cap;
+        }
+        out[s].pad = same ? 1 : 0;
+    }
     return regular;
 }
 
@@ -579,6 +594,8 @@ struct AbcFillLane {
     int active;
     int seg, off;            /* series being evaluated: its segment, and where its record lies in the stage buffer (doubles; < 0: not staged) */
     int nseg, noff;          /* the same for the series after it */
+    int lo, nfit, offr, uni; /* the slot's run of records as the last located series staged it: first record, records staged, offset in
+                              * the stage buffer (doubles), and whether the warp staged at all -- reused by series on the same time grid */
 };
 
 /* Chebyshev argument (and derivative scale) of time t for the record at `rec` = [_jul(MID), RADIUS, ...]: the second
@@ -660,12 +677,25 @@ __device__ __forceinline__ void abc_series_finish(int s, const double* rec, cons
 
 /* Locate the records of series `s` for every lane and request the warp's records into stage buffer `buf` (`bar`: the
  * shared-memory address of its mbarrier).  Returns true when every active lane reads from the stage buffer. */
-__device__ __forceinline__ bool abc_fill_stage(AbcFillLane* L, int s, double jd_ref, unsigned actmask, double* buf, unsigned bar) {
+__device__ __forceinline__ bool abc_fill_stage(AbcFillLane* L, int s, bool have_prev, bool prev_all, double jd_ref, unsigned actmask,
+                                               double* buf, unsigned bar) {
     const AbSpkTarget& tg = c_abc_tg[s];
     const double* img = (s < ABC_S_AST0) ? c_abcE.spkp_img : c_abcE.spka_img;
     const int first = ab_ffs(actmask) - 1;
+    const bool reuse = have_prev && tg.pad != 0;      /* same time grid as the series just promoted to "current" */
 #ifdef AB_HOST_EMUL
     (void)bar;
+    if (reuse) {
+        for (int l = 0; l < 32; l++) {
+            AbcFillLane& X = L[l];
+            X.nseg = X.seg; X.noff = X.off;
+            if (X.active && X.uni && (l & 7) == 0 && X.nfit > 0) {
+                const AbSpkSeg& sg = tg.seg[X.seg];
+                memcpy(buf + X.offr, img + (sg.one - 1) + (long long)X.lo * sg.R, (size_t)X.nfit * sg.R * 8);
+            }
+        }
+        return prev_all;
+    }
     int bb[32];
     for (int l = 0; l < 32; l++) {
         AbcFillLane& X = L[l];
@@ -679,6 +709,7 @@ __device__ __forceinline__ bool abc_fill_stage(AbcFillLane* L, int s, double jd_
     bool uni = true;
     for (int l = 0; l < 32; l++) if (L[l].active && L[l].nseg != nref) uni = false;
     bool all = true;
+    for (int l = 0; l < 32; l++) { L[l].uni = uni ? 1 : 0; L[l].lo = 0; L[l].nfit = 0; L[l].offr = 0; }
     if (uni) {
         const AbSpkSeg& sg = tg.seg[nref];
         int off = 0;
@@ -691,8 +722,10 @@ __device__ __forceinline__ bool abc_fill_stage(AbcFillLane* L, int s, double jd_
             if (nfit > span) nfit = span;
             if (nfit < 0) nfit = 0;
             if (nfit > 0) memcpy(buf + (size_t)off * sg.R, img + (sg.one - 1) + (long long)lo * sg.R, (size_t)nfit * sg.R * 8);
-            for (int l = f; l <= e; l++)
+            for (int l = f; l <= e; l++) {
+                L[l].lo = lo; L[l].nfit = nfit; L[l].offr = off * sg.R;
                 if ((unsigned)(bb[l] - lo) < (unsigned)nfit) L[l].noff = (off + bb[l] - lo) * sg.R;
+            }
             off += span;
         }
     }
@@ -701,6 +734,19 @@ __device__ __forceinline__ bool abc_fill_stage(AbcFillLane* L, int s, double jd_
 #else
     const int l = (int)(threadIdx.x & 31);
     AbcFillLane& X = L[0];
+    if (reuse) {
+        X.nseg = X.seg; X.noff = X.off;
+        abc_fence_proxy_async();
+        if (X.active && X.uni && (l & 7) == 0 && X.nfit > 0) {
+            const AbSpkSeg& sg = tg.seg[X.seg];
+            const unsigned bytes = (unsigned)(X.nfit * sg.R) * 8u;
+            abc_mbar_expect_tx(bar, bytes);
+            abc_bulk_g2s(abc_smem_addr(buf + X.offr), img + (sg.one - 1) + (long long)X.lo * sg.R, bytes, bar);
+        }
+        __syncwarp();
+        if (l == 0) abc_mbar_arrive(bar);
+        return prev_all;
+    }
     int n = 0, b = 0;
     if (X.active) {
         n = ab_spk_segment(tg, jd_ref, X.t);
@@ -717,12 +763,14 @@ __device__ __forceinline__ bool abc_fill_stage(AbcFillLane* L, int s, double jd_
     const int k = l >> 3;
     const int off = (k > 0 ? sp0 : 0) + (k > 1 ? sp1 : 0) + (k > 2 ? sp2 : 0);
     abc_fence_proxy_async();      /* the buffer was read through the generic proxy two series ago */
+    X.uni = uni ? 1 : 0; X.lo = lo; X.nfit = 0; X.offr = 0;
     if (uni && X.active) {
         const AbSpkSeg& sg = tg.seg[nref];
         const int Rr = sg.R;
         int nfit = sg.stage_cap - off;
         if (nfit > span) nfit = span;
         if (nfit < 0) nfit = 0;
+        X.nfit = nfit; X.offr = off * Rr;
         if ((unsigned)(b - lo) < (unsigned)nfit) X.noff = (off + b - lo) * Rr;
         if (l == f && nfit > 0) {
             const unsigned bytes = (unsigned)(nfit * Rr) * 8u;
@@ -762,6 +810,7 @@ __device__ __noinline__ void abc_fill_warp(ABC_CTXARG double* gt, int warp) {
         X.sx = X.sy = X.sz = 0.0;
         X.emb[0] = X.emb[1] = X.emb[2] = 0.0;
         X.seg = X.nseg = 0; X.off = X.noff = -1;
+        X.lo = X.nfit = X.offr = X.uni = 0;
         if (X.active && !spk_regular) {
             /* unusual layout (DE-binary planets, a kernel without Earth or EMB target): the one-time routines */
             int err = AB_OK;
@@ -791,7 +840,7 @@ __device__ __noinline__ void abc_fill_warp(ABC_CTXARG double* gt, int warp) {
         const unsigned bar0 = abc_smem_addr(mb);
         unsigned phase = *reinterpret_cast<volatile unsigned*>(mb + 2);
 #endif
-        bool nall = abc_fill_stage(L, s_begin, jd_ref, actmask, stage, bar0);
+        bool nall = abc_fill_stage(L, s_begin, false, false, jd_ref, actmask, stage, bar0);
 #pragma unroll 1
         for (int s = s_begin; s < s_end; s++) {
             const int j = (s - s_begin) & 1;
@@ -800,7 +849,7 @@ __device__ __noinline__ void abc_fill_warp(ABC_CTXARG double* gt, int warp) {
                 AbcFillLane& X = L[ABC_LI(l)];
                 X.seg = X.nseg; X.off = X.noff;
             }
-            if (s + 1 < s_end) nall = abc_fill_stage(L, s + 1, jd_ref, actmask, stage + (j ^ 1) * ABC_ST_BUF, bar0 + 8u * (unsigned)(j ^ 1));
+            if (s + 1 < s_end) nall = abc_fill_stage(L, s + 1, true, all, jd_ref, actmask, stage + (j ^ 1) * ABC_ST_BUF, bar0 + 8u * (unsigned)(j ^ 1));
 #ifndef AB_HOST_EMUL
             {   /* the records of series s have landed */
                 const unsigned bar = bar0 + 8u * (unsigned)j, par = (phase >> j) & 1u;
