@@ -6,7 +6,7 @@
  * working set lives ON CHIP -- the planets at its 8 node times in shared memory, its IAS15 state in the
  * registers of three "component" warps -- and the independent work of a step is spread over warps:
  *
- *     group = 32 systems with 8 warps of their own, a 102 KB block of shared memory and a 110 KB table in global
+ *     group = 32 systems with 8 warps of their own, a 113.5 KB block of shared memory and a 110 KB table in global
  *             memory (L2) for what one task reads once per node (asteroid positions, Sun velocity, EIH pair sums).
  *             A CTA holds TWO groups that walk through the phases of a step attempt together (CTA-wide barriers):
  *             every latency-bound phase serves 64 systems, and all 16 warps of the SM run the same code at the
@@ -22,8 +22,9 @@
  *                      potential sum) and of the single-body terms (Earth J2-J4, solar J2, EIH source block,
  *                      Marsden, GR variants), from a launch-time plan (gpu_api.cu: build_coop_plan)
  *         all 8        the Chebyshev fill of the node tables: thread = (slot, node), so the eight nodes of a
- *                      system read the same one or two coefficient records (broadcast loads instead of 32 lanes
- *                      gathering 32 records), and everything one (slot, node) needs comes from one thread
+ *                      system read the same one or two coefficient records -- which the TMA unit copies into
+ *                      shared memory one series ahead (cp.async.bulk per slot, mbarrier completion) -- and
+ *                      everything one (slot, node) needs comes from one thread
  *
  * Values are those of the one-thread-per-system path, bit for bit in the strict build: every term is formed
  * by the same operations, and the sums that the reference accumulates in a fixed order (27 direct terms,
