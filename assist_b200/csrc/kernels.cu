@@ -171,25 +171,45 @@ __global__ void ascii_work_kernel(const double* __restrict__ P, int ncm, int ncf
 #define PP_KM AB_KMAX
 #endif
 
-/* One reb_simulation_step of system i: force evaluation at the current state, then
- * IAS15 attempts until one is accepted.  Each thread owns its times, so the body
- * table is evaluated per thread. */
-template <int KM>
-__device__ __noinline__ void pp_step(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, long long i, PPState& P) {
+/* One reb_simulation_step of system i: force evaluation at the current state, then IAS15 attempts until one is
+ * accepted.  Each thread owns its times, so the body tables are evaluated per thread, in one of two ways:
+ *   NODES = false  one table per force evaluation (any configuration);
+ *   NODES = true   the common configuration (one EIH source, barycentric): the body tables of the 8 times of an attempt
+ *                  are evaluated once, side by side (ab_fill_nodes), and every predictor-corrector sweep reuses them --
+ *                  what the reference's 7-slot time cache does.
+ * One text for both: the control flow (sweeps, convergence, step-size control, rejection) is REBOUND's and must not
+ * drift apart between the two. */
+template <int KM, bool NODES>
+__device__ __forceinline__ void pp_step_impl(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, long long i, PPState& P) {
     AbSysT<KM> S;
-    AbBodies B;
+    AbBodies B;                              /* NODES = false */
+    AbNode nodes[NODES ? AB_NT : 1];         /* NODES = true */
+    double times[AB_NT];
     ab_load_sys(Bt, i, S);
     const int nv = S.nv();
-    ab_body_states_ol(E, F, P.t, B);
-    if (B.status != AB_OK) { P.status = 1; Bt.status[i] = 1000 + B.status; return; }
-    ab_zero_acc(S);
-    ab_forces_ol<KM, AbBodies>(E, F, B, S);
-    P.evals++;
-    ab_store_a0(Bt, i, S);
-
+    bool have_a0 = false;
     while (true) {   /* attempts */
-        ab_attempt_begin(Bt, i, nv);
         const double t_beginning = P.t;
+        if constexpr (NODES) {
+            times[0] = t_beginning;
+            for (int nn = 1; nn < 8; nn++) times[nn] = t_beginning + P.dt * c_h[nn];
+            const int flag = ab_fill_nodes(E, F, times, nodes);
+            if (flag != AB_OK) { P.status = 1; Bt.status[i] = 1000 + flag; return; }
+        }
+        if (!have_a0) {      /* the force at the start of the step: once, a rejected attempt keeps it */
+            ab_zero_acc(S);
+            if constexpr (NODES) {
+                ab_forces_ol<KM, AbNode>(E, F, nodes[0], S);
+            } else {
+                ab_body_states_ol(E, F, P.t, B);
+                if (B.status != AB_OK) { P.status = 1; Bt.status[i] = 1000 + B.status; return; }
+                ab_forces_ol<KM, AbBodies>(E, F, B, S);
+            }
+            P.evals++;
+            ab_store_a0(Bt, i, S);
+            have_a0 = true;
+        }
+        ab_attempt_begin(Bt, i, nv);
         double pc_err = 1e300, pc_err_last = 2;
         int iterations = 0;
         while (true) {
@@ -202,12 +222,16 @@ __device__ __noinline__ void pp_step(const AbEphem& E, const AbForceOpts& F, con
             P.iters++;
             double maxak = 0.0, maxb6 = 0.0;
             for (int nn = 1; nn < 8; nn++) {
-                const double ts = t_beginning + P.dt * c_h[nn];
                 ab_predict(Bt, i, nn, P.dt, S);
-                ab_body_states_ol(E, F, ts, B);
-                if (B.status != AB_OK) { P.status = 1; Bt.status[i] = 1000 + B.status; return; }
-                ab_zero_acc(S);
-                ab_forces_ol<KM, AbBodies>(E, F, B, S);
+                if constexpr (NODES) {
+                    ab_zero_acc(S);
+                    ab_forces_ol<KM, AbNode>(E, F, nodes[nn], S);
+                } else {
+                    ab_body_states_ol(E, F, t_beginning + P.dt * c_h[nn], B);
+                    if (B.status != AB_OK) { P.status = 1; Bt.status[i] = 1000 + B.status; return; }
+                    ab_zero_acc(S);
+                    ab_forces_ol<KM, AbBodies>(E, F, B, S);
+                }
                 P.evals++;
                 ab_update_gb(Bt, i, nn, S, maxak, maxb6);
             }
@@ -238,77 +262,13 @@ __device__ __noinline__ void pp_step(const AbEphem& E, const AbForceOpts& F, con
         return;
     }
 }
-
-/* The same step for the common configuration (one EIH source, barycentric): the body tables of
- * the 8 times of the step are evaluated once, side by side (ab_fill_nodes), and every
- * predictor-corrector sweep reuses them -- what the reference's 7-slot time cache does. */
+template <int KM>
+__device__ __noinline__ void pp_step(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, long long i, PPState& P) {
+    pp_step_impl<KM, false>(E, F, Bt, i, P);
+}
 template <int KM>
 __device__ void pp_step_nodes(const AbEphem& E, const AbForceOpts& F, const AbBatch& Bt, long long i, PPState& P) {
-#define AB_NODE_FORCES(N) ab_forces_ol<KM, AbNode>(E, F, N, S)
-    AbSysT<KM> S;
-    AbNode nodes[AB_NT];
-    double times[AB_NT];
-    ab_load_sys(Bt, i, S);
-    const int nv = S.nv();
-    bool have_a0 = false;
-    while (true) {   /* attempts */
-        const double t_beginning = P.t;
-        times[0] = t_beginning;
-        for (int nn = 1; nn < 8; nn++) times[nn] = t_beginning + P.dt * c_h[nn];
-        const int flag = ab_fill_nodes(E, F, times, nodes);
-        if (flag != AB_OK) { P.status = 1; Bt.status[i] = 1000 + flag; return; }
-        if (!have_a0) {
-            ab_zero_acc(S);
-            AB_NODE_FORCES(nodes[0]);
-            P.evals++;
-            ab_store_a0(Bt, i, S);
-            have_a0 = true;
-        }
-        ab_attempt_begin(Bt, i, nv);
-        double pc_err = 1e300, pc_err_last = 2;
-        int iterations = 0;
-        while (true) {
-            if (pc_err < 1e-16) break;
-            if (iterations > 2 && pc_err_last <= pc_err) break;
-            if (iterations >= 12) break;
-            pc_err_last = pc_err;
-            pc_err = 0;
-            iterations++;
-            P.iters++;
-            double maxak = 0.0, maxb6 = 0.0;
-            for (int nn = 1; nn < 8; nn++) {
-                ab_predict(Bt, i, nn, P.dt, S);
-                ab_zero_acc(S);
-                AB_NODE_FORCES(nodes[nn]);
-                P.evals++;
-                ab_update_gb(Bt, i, nn, S, maxak, maxb6);
-            }
-            pc_err = maxb6 / maxak;
-        }
-        const double dt_done = P.dt;
-        if (Bt.epsilon > 0) {
-            double maxa = 0.0, maxj = 0.0;
-            ab_dt_monitor(Bt, i, S, P.dt, maxa, maxj);
-            double dt_new = ab_dt_new(Bt.epsilon, Bt.min_dt, maxa, maxj, dt_done);
-            if (fabs(dt_new / dt_done) < 0.25) {
-                ab_restore(Bt, i, nv);
-                P.dt = dt_new;
-                if (P.dt_last != 0.) ab_predict_next(Bt, i, nv, P.dt / P.dt_last, Bt.er, Bt.br);
-                P.rejected++;
-                continue;
-            }
-            if (fabs(dt_new / dt_done) > 1.0) {
-                if (dt_new / dt_done > 1. / 0.25) dt_new = dt_done / 0.25;
-            }
-            P.dt = dt_new;
-        }
-        ab_advance(Bt, i, nv, dt_done);
-        P.t += dt_done;
-        P.dt_last = dt_done;
-        ab_predict_next(Bt, i, nv, P.dt / dt_done, Bt.e, Bt.b);
-        P.steps++;
-        return;
-    }
+    pp_step_impl<KM, true>(E, F, Bt, i, P);
 }
 
 /* reb_simulation_integrate(tmax) for one system, at most `step_cap` steps in this call.
