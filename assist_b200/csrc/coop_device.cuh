@@ -337,63 +337,6 @@ __device__ __forceinline__ void abc_multi_eval(const AbcSeriesRef* R, double jd_
     for (int s = 0; s < NS; s++) { u[s][0] = a0[s]; u[s][1] = a1[s]; u[s][2] = a2[s]; }
 }
 
-/* ONE series at time t with the coefficients FOUR pairs of terms ahead: the record comes from L2 (~1000 cycles a trip
- * under load) and a pair of terms is ~16 FP64 instructions, so a distance of one pair leaves most of every trip
- * exposed; with four pairs in flight nearly the whole record is requested before the first sums are formed.  Same
- * sums in the same order as abc_multi_eval. */
-__device__ __forceinline__ void abc_ring_pair(const double2* qq, int p, int P, double2& A, double2& B, double2& C) {
-    A = B = C = double2{0.0, 0.0};
-    if (p < P) {
-        A = __ldg(qq); B = __ldg(qq + 1);
-        if (p + 1 < P) C = __ldg(qq + 2);
-    }
-}
-__device__ __forceinline__ void abc_ring_use(int p, int P, double z, const double2& A, const double2& B, const double2& C,
-                                             double& a0, double& a1, double& a2, double& T1, double& T2) {
-    if (p < P) {
-        const double Ta = 2.0 * z * T1 - T2;
-        a0 += A.x * Ta; a1 += A.y * Ta; a2 += B.x * Ta;
-        if (p + 1 < P) {      /* an odd number of terms: the second half of the last pair is padding */
-            const double Tb = 2.0 * z * Ta - T1;
-            a0 += B.y * Tb; a1 += C.x * Tb; a2 += C.y * Tb;
-            T2 = Ta; T1 = Tb;
-        }
-    }
-}
-__device__ __forceinline__ void abc_single_eval(const AbcSeriesRef& R, double jd_ref, double t, double* u) {
-    if (R.kind < 0) { u[0] = u[1] = u[2] = 0.0; return; }
-    const AbSpkTarget& tg = *R.tg;
-    const AbSpkSeg& sg = tg.seg[ab_spk_segment(tg, jd_ref, t)];
-    double z, c;
-    const double2* q = reinterpret_cast<const double2*>(ab_spk_record_in(R.img, sg, jd_ref, t, &z, &c));
-    const int P = sg.P;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, T2 = 1.0, T1 = z;
-    double2 A0, B0, C0, A1, B1, C1, A2, B2, C2, A3, B3, C3;
-    double2 hA = double2{0.0, 0.0}, hB = hA, hC = hA;
-    if (P > 0) { hA = __ldg(q); hB = __ldg(q + 1); hC = __ldg(q + 2); }      /* x0 y0 | z0 x1 | y1 z1 */
-    abc_ring_pair(q + 3, 2, P, A0, B0, C0);
-    abc_ring_pair(q + 6, 4, P, A1, B1, C1);
-    abc_ring_pair(q + 9, 6, P, A2, B2, C2);
-    abc_ring_pair(q + 12, 8, P, A3, B3, C3);
-    if (P > 0) {
-        a0 += hA.x * 1.0; a1 += hA.y * 1.0; a2 += hB.x * 1.0;
-        a0 += hB.y * z; a1 += hC.x * z; a2 += hC.y * z;
-    }
-#pragma unroll 1
-    for (int p = 2; p < P; p += 8) {
-        const double2* qn = q + 3 * ((p + 8) >> 1);
-        abc_ring_use(p, P, z, A0, B0, C0, a0, a1, a2, T1, T2);
-        abc_ring_pair(qn, p + 8, P, A0, B0, C0);
-        abc_ring_use(p + 2, P, z, A1, B1, C1, a0, a1, a2, T1, T2);
-        abc_ring_pair(qn + 3, p + 10, P, A1, B1, C1);
-        abc_ring_use(p + 4, P, z, A2, B2, C2, a0, a1, a2, T1, T2);
-        abc_ring_pair(qn + 6, p + 12, P, A2, B2, C2);
-        abc_ring_use(p + 6, P, z, A3, B3, C3, a0, a1, a2, T1, T2);
-        abc_ring_pair(qn + 9, p + 14, P, A3, B3, C3);
-    }
-    u[0] = a0; u[1] = a1; u[2] = a2;
-}
-
 /* what becomes of the sums of one series: EMB kept, planets into shared memory, asteroids (heliocentric / 149597870.7,
  * reference src/spk.c:470, + Sun, reference src/forces.c:213-219) into the global table */
 __device__ __forceinline__ void abc_fill_store(const AbcSeriesRef& R, double* u, double* emb, double* tb, double* g,
@@ -936,11 +879,7 @@ __device__ __noinline__ void abc_fill_warp(ABC_CTXARG double* gt, int warp) {
 #pragma unroll
             for (int j = 0; j < ABC_FILL_NS; j++) R[j] = abc_series_ref(s + j, s_end);
             double u[ABC_FILL_NS][3];
-#if ABC_FILL_NS == 1
-            abc_single_eval(R[0], jd_ref, t, u[0]);
-#else
             abc_multi_eval<ABC_FILL_NS>(R, jd_ref, t, u);
-#endif
 #pragma unroll
             for (int j = 0; j < ABC_FILL_NS; j++) abc_fill_store(R[j], u[j], emb, tb, g, sx, sy, sz);
         }
