@@ -800,7 +800,7 @@ __device__ __noinline__ void abc_fill_warp(ABC_CTXARG double* gt, int warp) {
                 if (!abc_mbar_try_wait(bar, par)) {
                     const long long tw = clock64();
                     while (!abc_mbar_try_wait(bar, par))
-                        if (clock64() - tw > (1LL << 31)) __trap();      /* a lost copy must not hang the grid */
+                        if (clock64() - tw > (1LL << 34)) __trap();      /* ~9 s: a lost copy must not hang the grid */
                 }
                 phase ^= 1u << j;
             }
