@@ -152,3 +152,24 @@ def test_emul_c3_subsample_ten_years(eph, fmt):
     c = got["counters"].astype(np.int64)          # steps, rejected, iters, evals
     assert np.array_equal(np.stack([c[:, 0], c[:, 2], c[:, 3], c[:, 1]], axis=1), G["c3_counts"][pick])
     b.close()
+
+
+@pytest.mark.parametrize("direction", [1.0, -1.0])
+def test_emul_steps_across_the_segment_boundary(eph, fmt, ref, paths, direction):
+    """The synthetic kernels hold two segments per target (boundary at JD 2453000.5, t = 1455.5): steps whose eight nodes
+    straddle it read their records from two segments (the staged fill then leaves such a series to the global path),
+    forward and backward, against one reference simulation per particle."""
+    if fmt != "bsp":
+        pytest.skip("segments are an SPK notion")
+    reph = rh.open_ephem(ref, planets_path(paths, fmt), paths["asteroids_bsp"])
+    tb = 1455.5
+    st = populations.neo_mba_mix(12, seed=4242)
+    t0, t1 = tb - direction * 35.0, tb + direction * 70.0
+    b = coop_emul.EmulBatch(eph, st.shape[0], forces=0x7F)
+    b.set_state(t0, st)
+    b.integrate(t1)
+    got = b.get_state()
+    b.close()
+    want, wt, wdt, tot = rh.integrate_each(ref, reph, t0, st, t1, forces=0x7F)
+    assert np.array_equal(got["state"], want) and np.array_equal(got["t"], wt) and np.array_equal(got["dt"], wdt)
+    assert int(got["counters"][:, 0].sum()) == tot["steps"]

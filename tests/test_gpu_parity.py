@@ -597,3 +597,23 @@ def test_dropin_snapshot_file_and_interpolated_simulation(eph, fmt, ref, paths, 
     direct = b.get_state()["state"][:, 0, :]
     b.close()
     assert np.abs(got[:, :3] - direct[:, :3]).max() < 5e-13
+
+
+@pytest.mark.parametrize("direction", [1.0, -1.0])
+def test_steps_across_the_segment_boundary(eph, fmt, ref, paths, direction):
+    """Two SPK segments per target (boundary at t = 1455.5): steps whose nodes straddle it, forward and backward, on
+    pp_coop_kernel (the staged fill leaves a series whose slots straddle segments to the global path) against one
+    reference simulation per particle: bit-identical."""
+    if fmt != "bsp":
+        pytest.skip("segments are an SPK notion")
+    reph = rh.open_ephem(ref, planets_path(paths, fmt), paths["asteroids_bsp"])
+    tb = 1455.5
+    st = populations.neo_mba_mix(96, seed=4242)
+    t0, t1 = tb - direction * 35.0, tb + direction * 70.0
+    b = ab.Batch(eph, st.shape[0], 0, ab.PER_PARTICLE, forces=0x7F)
+    b.set_state(t0, st[:, None, :])
+    b.integrate(t1)
+    got = b.get_state()
+    b.close()
+    want, wt, wdt, _ = rh.integrate_each(ref, reph, t0, st, t1, forces=0x7F)
+    assert np.array_equal(got["state"], want) and np.array_equal(got["t"], wt) and np.array_equal(got["dt"], wdt)
