@@ -11,7 +11,8 @@
 
 Same names, arguments and error behaviour as the reference (`Ephem.get_particle`, `Ephem.time_bounds`,
 `Extras.forces`, `Extras.particle_params`, `Extras.detach`, `Extras.integrate_or_interpolate`,
-`ASSIST_BODY_IDS`, `ASSIST_FORCES`).  The `rebound` Python package is not needed: `Simulation` and
+`ASSIST_BODY_IDS`, `ASSIST_FORCES`, and assist/tools.py's `simulation_convert_to_rebound` and
+`assist_create_interpolated_simulation` with `Simulation.save_to_file` / `SimulationArchive` standing in for rebound's).  The `rebound` Python package is not needed: `Simulation` and
 `Particle` are thin ctypes views of the REBOUND surface in include/rebound.h -- the members ASSIST users
 touch (t, dt, N, particles, add, add_variation, integrate, step, copy, ri_ias15.{epsilon,min_dt},
 exact_finish_time, steps_done, status).  Many-particle work goes through `assist_b200.Batch`.
@@ -158,6 +159,16 @@ class Simulation:
         self._lib.reb_simulation_step(self._r)
         self._raise_messages()
 
+    def save_to_file(self, filename, step=None):
+        """rebound's sim.save_to_file(filename, step=n): a snapshot before the first step of integrate() and after every
+        n completed steps (what assist_create_interpolated_simulation reads back); step=None appends one snapshot now."""
+        fn = str(filename).encode()
+        if step is None:
+            self._lib.reb_simulation_save_to_file(self._r, fn)
+        else:
+            self._lib.reb_simulation_save_to_file_step(self._r, fn, int(step))
+        self._raise_messages()
+
     def copy(self):
         """Particles, time and step settings; ASSIST must be attached to the copy again (as in the reference)."""
         c = self._lib.reb_simulation_copy(self._r)
@@ -182,6 +193,65 @@ class Simulation:
                 self._r = None
         except Exception:
             pass
+
+
+class SimulationArchive:
+    """Stand-in for rebound.Simulationarchive: the snapshot file written by Simulation.save_to_file."""
+
+    def __init__(self, filename):
+        self._lib = _lib.load()
+        self._sa = self._lib.reb_simulationarchive_create_from_file(str(filename).encode())
+        if not self._sa:
+            raise RuntimeError("cannot read the snapshot file %s" % filename)
+
+    @property
+    def nblobs(self):
+        return int(self._sa.contents.nblobs)
+
+    def __len__(self):
+        return self.nblobs
+
+    @property
+    def t(self):
+        return [self._sa.contents.t[i] for i in range(self.nblobs)]
+
+    def __getitem__(self, i):
+        """Snapshot i as a Simulation (time, particles, step data; ASSIST is not attached to it)."""
+        r = self._lib.reb_simulation_create()
+        self._lib.reb_simulation_create_from_simulationarchive_with_messages(r, self._sa, int(i), None)
+        sim = Simulation(_ptr=r)
+        if r.contents.messages_waiting:
+            raise IndexError(r.contents.messages.decode("ascii", "replace"))
+        return sim
+
+    def __del__(self):
+        try:
+            if self._sa:
+                self._lib.reb_simulationarchive_free(self._sa)
+                self._sa = None
+        except Exception:
+            pass
+
+
+def assist_create_interpolated_simulation(sa, t):
+    """reference assist/tools.py:11-15: the simulation at time t, interpolated inside the step between two snapshots."""
+    r = sa._lib.assist_create_interpolated_simulation(sa._sa, float(t))
+    if not r:
+        raise RuntimeError("requested time outside the range of the snapshot file")
+    return Simulation(_ptr=r)
+
+
+def simulation_convert_to_rebound(sim, ephem, merge_moon=1):
+    """reference assist/tools.py:6-9: a plain simulation holding the ephemeris bodies at sim.t followed by sim's
+    particles."""
+    from .cstructs import Simulation as _CSimulation
+    lib = sim._lib
+    lib.assist_simulation_convert_to_rebound.restype = POINTER(_CSimulation)
+    lib.assist_simulation_convert_to_rebound.argtypes = [POINTER(_CSimulation), ctypes.c_void_p, c_int]
+    r = lib.assist_simulation_convert_to_rebound(sim._r, ctypes.cast(byref(ephem._c), ctypes.c_void_p), int(merge_moon))
+    if not r:
+        raise RuntimeError("assist_simulation_convert_to_rebound failed")
+    return Simulation(_ptr=r)
 
 
 class Ephem:

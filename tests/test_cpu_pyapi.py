@@ -96,3 +96,26 @@ def test_compute_fails_loudly_without_gpu(ephem, have_gpu):
     with pytest.raises(RuntimeError):
         sim.integrate(8420.0)
     del extras
+
+
+def test_snapshot_file_through_the_python_mirror(ephem, tmp_path):
+    """assist/tools.py's assist_create_interpolated_simulation with Simulation.save_to_file / SimulationArchive
+    standing in for rebound's: host part (files, ranges, errors)."""
+    sim = assist.Simulation()
+    extras = assist.Extras(sim, ephem)
+    sim.add(x=2.0, y=0.1, z=0.0, vx=0.0, vy=0.012, vz=0.001)
+    fn = tmp_path / "py_snap.bin"
+    for k in range(3):
+        sim.t = 10.0 + k
+        sim.save_to_file(fn)
+    sa = assist.SimulationArchive(fn)
+    assert len(sa) == 3 and sa.t == [10.0, 11.0, 12.0]
+    s1 = sa[1]
+    assert s1.t == 11.0 and s1.N == 1 and s1.particles[0].x == 2.0
+    with pytest.raises(IndexError):
+        sa[7]
+    with pytest.raises(RuntimeError, match="outside the range"):
+        assist.assist_create_interpolated_simulation(sa, 10.5)
+    with pytest.raises(RuntimeError, match="cannot read"):
+        assist.SimulationArchive(tmp_path / "missing.bin")
+    del extras

@@ -132,3 +132,30 @@ def test_variational_and_params(ephem, ref, reph):
     assert sim.t == r.t
     r.close()
     del extras
+
+
+def test_snapshots_and_interpolated_simulation(ephem, tmp_path):
+    """assist/tools.py:11-15 through the Python mirror: snapshots after every step, the simulation interpolated inside
+    a step agrees with a direct integration to that time (reference unit_tests/interpolation_spk, 10 cm bound)."""
+    t0 = 8416.5
+    fn = tmp_path / "py_out.bin"
+    sim = assist.Simulation()
+    sim.t = t0
+    sim.add(**HOLMAN)
+    extras = assist.Extras(sim, ephem)
+    sim.save_to_file(fn, step=1)
+    sim.integrate(t0 + 583.5)
+    sa = assist.SimulationArchive(fn)
+    assert len(sa) == sim.steps_done + 1 and sa.t[0] == t0
+    si = assist.assist_create_interpolated_simulation(sa, t0 + 30.0)
+    assert si.t == pytest.approx(t0 + 30.0, abs=1e-9) and si.N == 1
+    sim2 = assist.Simulation()
+    sim2.t = t0
+    sim2.add(**HOLMAN)
+    extras2 = assist.Extras(sim2, ephem)
+    sim2.integrate(t0 + 30.0)
+    d = si.particles[0] - sim2.particles[0]
+    assert math.fabs(d.x * AU2M) < 0.1 and math.fabs(d.y * AU2M) < 0.1 and math.fabs(d.z * AU2M) < 0.1
+    conv = assist.simulation_convert_to_rebound(sim2, ephem, merge_moon=0)
+    assert conv.N == 11 + 1 and conv.particles[11].x == sim2.particles[0].x
+    del extras, extras2
