@@ -291,3 +291,25 @@ def variational_by_differences(eph, t, x, v, dx, dv, params=None, dparams=None, 
     ap = accelerations(eph, t, x + eps * dx, v + eps * dv, p1, **kw)
     am = accelerations(eph, t, x - eps * dx, v - eps * dv, p2, **kw)
     return (ap - am) / (2.0 * eps)
+
+
+def interpolate_simulation(x0, v0, a0, br, dt_last_done, h):
+    """Dense output between two snapshots, reference src/assist.c:682-752, from the IAS15 series itself rather than
+    from the reference's running products: with s = dt_last_done * h,
+
+        x(h) = x0 + s v0 + s^2 (a0/2 + h b0/6 + h^2 b1/12 + h^3 b2/20 + h^4 b3/30 + h^5 b4/42 + h^6 b5/56 + h^7 b6/72)
+        v(h) = v0 + s (a0 + h b0/2 + h^2 b1/3 + h^3 b2/4 + h^4 b3/5 + h^5 b4/6 + h^6 b5/7 + h^7 b6/8)
+
+    x0, v0: state at the start of the step (the earlier snapshot), a0, br[7]: start acceleration and b coefficients of
+    the step (the later snapshot).  Arrays of any common shape; not bit-faithful (different operation order)."""
+    x0, v0, a0 = (np.asarray(q, dtype=np.float64) for q in (x0, v0, a0))
+    br = np.asarray(br, dtype=np.float64)
+    s = dt_last_done * h
+    px = a0 / 2.0
+    pv = a0.copy()
+    hp = 1.0
+    for k, (dx, dv) in enumerate(zip((6., 12., 20., 30., 42., 56., 72.), (2., 3., 4., 5., 6., 7., 8.))):
+        hp = hp * h
+        px = px + hp * br[k] / dx
+        pv = pv + hp * br[k] / dv
+    return x0 + s * v0 + s * s * px, v0 + s * pv

@@ -324,3 +324,54 @@ def test_ias15_variant_spread(ref, paths):
     assert 0.0 < d.max() <= 1e-12
     assert abs(ca["steps"] - cb["steps"]) <= 3
     assert cb["rejected"] == 0 and np.array_equal(keep, base) and ck == cb
+
+
+def test_numpy_restatement_beyond_sixteen_asteroids():
+    """The numpy restatement takes any number of small-body targets: ephemeris and one force evaluation on the
+    40-target kernel against tests/golden/golden_n373.npz (the reference build's outputs)."""
+    from conftest import ROOT
+    from assist_b200.synth import ephem_writer
+    npo = _np_oracle()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_n373.npz"))
+    N = cases.N373_SIZES[0]
+    p = ephem_writer.write_extended(os.path.join(ROOT, "data"), N)
+    eph = npo.Ephemeris(p["planets_bsp"], p["asteroids_bsp"])
+    assert eph.nbodies == 11 + N
+    for it, t in enumerate(cases.n373_times()):
+        gm, pos, _ = eph.states(float(t))
+        assert np.array_equal(gm, g["eph%d" % N][it, :, 0])
+        assert np.max(np.abs(pos - g["eph%d" % N][it, :, 1:4])) < 1e-14
+    st = cases.n373_force_systems()
+    a = npo.accelerations(eph, cases.T0 + 17.25, st[:, 0, :3], st[:, 0, 3:], None, forces=0x7F)
+    assert relerr(a, g["acc%d" % N][:, 0, :]) < 2e-13
+
+
+def test_numpy_restatement_of_the_snapshot_interpolation(ref, reph):
+    """oracle/np_oracle.interpolate_simulation (the IAS15 series written out) against the reference's
+    assist_interpolate_simulation (src/assist.c:682-752) on two reference simulations one step apart."""
+    npo = _np_oracle()
+    st = cases.pp_case()[:5]
+    s1 = rh.Sim(ref, reph, cases.T0, st)
+    s2 = rh.Sim(ref, reph, cases.T0, st)
+    ref.reb_simulation_steps(s1.r, 6)
+    ref.reb_simulation_steps(s2.r, 7)
+    n = st.shape[0]
+    r1, r2 = s1.r.contents.ri_ias15, s2.r.contents.ri_ias15
+    x0 = np.array([r1.x0[k] for k in range(3 * n)]); v0 = np.array([r1.v0[k] for k in range(3 * n)])
+    a0 = np.array([r2.a0[k] for k in range(3 * n)])
+    br = np.array([[getattr(r2.br, "p%d" % q)[k] for k in range(3 * n)] for q in range(7)])
+    dt, t1 = s2.dt_last_done, s1.t
+    for h in (0.0, 0.3, 0.77, 1.0):
+        sa = rh.Sim(ref, reph, cases.T0, st)
+        ref.reb_simulation_steps(sa.r, 6)
+        assert ref.assist_interpolate_simulation(sa.r, s2.r, h) == 1
+        want = sa.state()[:, 0, :]
+        px, pv = npo.interpolate_simulation(x0, v0, a0, br, dt, h)
+        assert np.max(np.abs(px.reshape(n, 3) - want[:, :3])) < 5e-15 * np.max(np.abs(want[:, :3]))
+        assert np.max(np.abs(pv.reshape(n, 3) - want[:, 3:])) < 5e-15 * np.max(np.abs(want[:, 3:]))
+        assert sa.t == t1 + dt * h
+        sa.close()
+    # h = 1 is the later snapshot itself (to rounding)
+    assert np.max(np.abs(px.reshape(n, 3) - s2.state()[:, 0, :3])) < 1e-14
+    s1.close()
+    s2.close()
