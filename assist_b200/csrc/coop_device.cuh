@@ -472,11 +472,11 @@ static inline int abc_series_table(const AbEphem& E, const AbSpkTarget* ast, AbS
     for (int m = 0; m < E.n_ast && m < AB_MAX_AST; m++) out[ABC_S_AST0 + m] = ast[m];
     for (int s = 0; s < ABC_NSERIES; s++)
         for (int k = 0; k < AB_MAXSEG; k++) out[s].seg[k].stage_cap = out[s].seg[k].R > 0 ? ABC_ST_BUF / out[s].seg[k].R : 0;
-    /* pad = 1: the series has the time grid of the series before it (same segments, same record boundaries, same record
+    /* same_grid = 1: the series has the time grid of the series before it (same segments, same record boundaries, same record
      * size -- the 16 asteroids of sb441-n16, the outer planets): segment, record index and staging layout of a lane are
      * then the same numbers, formed from the same operands, and are not formed again */
     for (int s = 0; s < ABC_NSERIES; s++) {
-        out[s].pad = 0;
+        out[s].same_grid = 0;
         if (s == 0 || out[s].nseg < 1 || out[s].nseg != out[s - 1].nseg) continue;
         const AbSpkTarget &a = out[s], &b = out[s - 1];
         bool same = a.beg == b.beg && a.end == b.end && a.res == b.res && a.res_rd == b.res_rd;
@@ -485,7 +485,7 @@ static inline int abc_series_table(const AbEphem& E, const AbSpkTarget* ast, AbS
             same = p.R == q.R && p.nrec == q.nrec && p.jul_init == q.jul_init && p.intlen_d == q.intlen_d &&
                    p.intlen_rd == q.intlen_rd && p.stage_cap == q.stage_cap;
         }
-        out[s].pad = same ? 1 : 0;
+        out[s].same_grid = same ? 1 : 0;
     }
     return regular;
 }
@@ -626,7 +626,7 @@ __device__ __forceinline__ bool abc_fill_stage(AbcFillLane* L, int s, bool have_
     const AbSpkTarget& tg = c_abc_tg[s];
     const double* img = (s < ABC_S_AST0) ? c_abcE.spkp_img : c_abcE.spka_img;
     const int first = ab_ffs(actmask) - 1;
-    const bool reuse = have_prev && tg.pad != 0;      /* same time grid as the series just promoted to "current" */
+    const bool reuse = have_prev && tg.same_grid != 0;      /* same time grid as the series just promoted to "current" */
 #ifdef AB_HOST_EMUL
     (void)bar;
     if (reuse) {

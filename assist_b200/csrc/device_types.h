@@ -37,7 +37,8 @@ struct AbSpkSeg {
 
 struct AbSpkTarget {
     double beg, end, res, res_rd, mass;
-    int code, cen, nseg, pad;
+    int code, cen, nseg;
+    int same_grid;       /* pp_coop_kernel's series table: same segments, record boundaries and record size as the series before (set at launch) */
     AbSpkSeg seg[AB_MAXSEG];
 };
 

@@ -468,25 +468,29 @@ extern "C" void reb_simulation_save_to_file(struct reb_simulation* const r, cons
     if (f) fclose(f);
     f = fopen(filename, "ab");
     if (!f) { reb_simulation_error(r, "reb_simulation_save_to_file: cannot open the file."); return; }
-    if (!exists) fwrite(AB_SA_MAGIC, 1, sizeof(AB_SA_MAGIC), f);
+    size_t bad = 0;      /* short writes (disk full): reported once at the end */
+#define AB_WR(ptr, size, count) do { if (fwrite((ptr), (size), (count), f) != (size_t)(count)) bad++; } while (0)
+    if (!exists) AB_WR(AB_SA_MAGIC, 1, sizeof(AB_SA_MAGIC));
     AbSnapHead h;
     h.t = r->t; h.dt = r->dt; h.dt_last_done = r->dt_last_done; h.steps_done = r->steps_done;
     h.N = r->N; h.N_var = (uint32_t)r->N_var; h.N_var_config = r->N_var_config; h.zero = 0;
     const uint64_t bytes = sizeof(h) + 8 * (uint64_t)r->N_var_config + sizeof(struct reb_particle) * (uint64_t)r->N + 8 * (uint64_t)(8 * m);
-    fwrite(&bytes, 8, 1, f);
-    fwrite(&h, sizeof(h), 1, f);
+    AB_WR(&bytes, 8, 1);
+    AB_WR(&h, sizeof(h), 1);
     for (unsigned int v = 0; v < r->N_var_config; v++) {
         const int32_t pair[2] = {r->var_config[v].index, r->var_config[v].testparticle};
-        fwrite(pair, 4, 2, f);
+        AB_WR(pair, 4, 2);
     }
     for (unsigned int i = 0; i < r->N; i++) {
         struct reb_particle p = r->particles[i];
         p.sim = NULL; p.c = NULL; p.ap = NULL;      /* pointers mean nothing in a file */
-        fwrite(&p, sizeof(p), 1, f);
+        AB_WR(&p, sizeof(p), 1);
     }
-    fwrite(a0.data(), 8, m, f);
-    fwrite(br.data(), 8, 7 * m, f);
-    fclose(f);
+    AB_WR(a0.data(), 8, m);
+    AB_WR(br.data(), 8, 7 * m);
+#undef AB_WR
+    if (fclose(f) != 0) bad++;
+    if (bad) reb_simulation_error(r, "reb_simulation_save_to_file: the snapshot could not be written completely.");
 }
 
 /* what REBOUND's heartbeat does for the archive: before the first step and after every completed step */
